@@ -1,0 +1,688 @@
+// ops_kernels.cuh — the non-FFT kernels of the path, hand-written for sm_100a.
+// All are HBM-bound streaming kernels: 16-byte vector accesses, fully coalesced,
+// grid sized as a multiple of the SM count, reductions by warp shuffles.
+// Reference operators are cited per kernel (S/ = userspace/include/srtb/).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace srtb_b200 {
+
+// ------------------------------------------------------------------------------
+// FFT window (S/fft/fft_window.hpp:27-50,112-123): w(i) = sum_k (-1)^k a_k cos(2 pi k x),
+// x = float(i) / float(n - 1), the cosine evaluated in double as the reference's
+// `2 * M_PI * k * x` expression is. window 0 = rectangle (identity, the default).
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ float window_value(int window, size_t i, float n_minus_1) {
+  if (window == 0) return 1.0f;
+  const float a0 = (window == 1) ? 0.5f : (float)(25.0 / 46.0);
+  const float a1 = (window == 1) ? 0.5f : (float)(21.0 / 46.0);
+  const float x = (float)i / n_minus_1;
+  float ret = 0.0f;
+  ret = (float)((double)ret + (double)a0 * cos(2.0 * 3.14159265358979323846 * 0.0 * (double)x));
+  ret = (float)((double)ret + (double)(-a1) * cos(2.0 * 3.14159265358979323846 * 1.0 * (double)x));
+  return ret;
+}
+
+// ------------------------------------------------------------------------------
+// K1 unpack "simple" (S/unpack.hpp:43-156,171-197): eight output samples per thread
+// per iteration (two float4 stores, 32 B contiguous per thread, 1 KiB per warp).
+// ------------------------------------------------------------------------------
+template <int BITS>
+struct unpack_src {};  // loads the bytes of 8 consecutive samples starting at sample 8*g
+
+template <>
+struct unpack_src<1> {
+  __device__ static void get(const void* in, size_t g, float (&o)[8]) {
+    const unsigned v = static_cast<const uint8_t*>(in)[g];
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = (float)((v >> (7 - i)) & 1u);
+  }
+};
+template <>
+struct unpack_src<2> {
+  __device__ static void get(const void* in, size_t g, float (&o)[8]) {
+    const unsigned v = static_cast<const uint16_t*>(in)[g];  // little endian: byte 0 = low
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[i] = (float)(((v & 0xffu) >> (6 - 2 * i)) & 3u);
+#pragma unroll
+    for (int i = 0; i < 4; i++) o[4 + i] = (float)(((v >> 8) >> (6 - 2 * i)) & 3u);
+  }
+};
+template <>
+struct unpack_src<4> {
+  __device__ static void get(const void* in, size_t g, float (&o)[8]) {
+    const unsigned v = static_cast<const uint32_t*>(in)[g];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const unsigned byte = (v >> (8 * b)) & 0xffu;
+      o[2 * b] = (float)(byte >> 4);
+      o[2 * b + 1] = (float)(byte & 0xfu);
+    }
+  }
+};
+template <>
+struct unpack_src<8> {
+  __device__ static void get(const void* in, size_t g, float (&o)[8]) {
+    const uint2 v = static_cast<const uint2*>(in)[g];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      o[b] = (float)((v.x >> (8 * b)) & 0xffu);
+      o[4 + b] = (float)((v.y >> (8 * b)) & 0xffu);
+    }
+  }
+};
+template <>
+struct unpack_src<-8> {
+  __device__ static void get(const void* in, size_t g, float (&o)[8]) {
+    const uint2 v = static_cast<const uint2*>(in)[g];
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      o[b] = (float)(int)(int8_t)((v.x >> (8 * b)) & 0xffu);
+      o[4 + b] = (float)(int)(int8_t)((v.y >> (8 * b)) & 0xffu);
+    }
+  }
+};
+template <>
+struct unpack_src<16> {
+  __device__ static void get(const void* in, size_t g, float (&o)[8]) {
+    const uint4 v = static_cast<const uint4*>(in)[g];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      o[2 * b] = (float)(w[b] & 0xffffu);
+      o[2 * b + 1] = (float)(w[b] >> 16);
+    }
+  }
+};
+template <>
+struct unpack_src<-16> {
+  __device__ static void get(const void* in, size_t g, float (&o)[8]) {
+    const uint4 v = static_cast<const uint4*>(in)[g];
+    const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      o[2 * b] = (float)(int)(int16_t)(w[b] & 0xffffu);
+      o[2 * b + 1] = (float)(int)(int16_t)(w[b] >> 16);
+    }
+  }
+};
+template <>
+struct unpack_src<32> {
+  __device__ static void get(const void* in, size_t g, float (&o)[8]) {
+    const float4 a = static_cast<const float4*>(in)[2 * g], b = static_cast<const float4*>(in)[2 * g + 1];
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+    o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+};
+template <>
+struct unpack_src<64> {
+  __device__ static void get(const void* in, size_t g, float (&o)[8]) {
+    const double2* p = static_cast<const double2*>(in) + 4 * g;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const double2 d = p[b];
+      o[2 * b] = (float)d.x;
+      o[2 * b + 1] = (float)d.y;
+    }
+  }
+};
+
+// scalar element access for tails and unaligned inputs
+template <int BITS>
+__device__ __forceinline__ float unpack_one(const void* in, size_t i) {
+  if (BITS == 1 || BITS == 2 || BITS == 4) {
+    constexpr int B = (BITS > 0 && BITS < 8) ? BITS : 1;
+    constexpr int CNT = 8 / B;
+    const unsigned v = static_cast<const uint8_t*>(in)[i / CNT];
+    const int j = (int)(i % CNT);
+    return (float)((v >> ((CNT - 1 - j) * B)) & ((1u << B) - 1u));
+  }
+  if (BITS == 8) return (float)static_cast<const uint8_t*>(in)[i];
+  if (BITS == -8) return (float)static_cast<const int8_t*>(in)[i];
+  if (BITS == 16) return (float)static_cast<const uint16_t*>(in)[i];
+  if (BITS == -16) return (float)static_cast<const int16_t*>(in)[i];
+  if (BITS == 32) return static_cast<const float*>(in)[i];
+  return (float)static_cast<const double*>(in)[i];
+}
+
+template <int BITS, bool WIN>
+__global__ void __launch_bounds__(256) unpack_simple_kernel(const void* __restrict__ in,
+                                                            float* __restrict__ out, size_t n,
+                                                            int window) {
+  const size_t groups = n / 8;
+  const float nm1 = (float)(n - 1);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    float o[8];
+    unpack_src<BITS>::get(in, g, o);
+    if (WIN) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) o[i] *= window_value(window, 8 * g + i, nm1);
+    }
+    float4* dst = reinterpret_cast<float4*>(out) + 2 * g;
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+  // tail (n % 8 samples) by the first threads of block 0
+  if (blockIdx.x == 0) {
+    const size_t i = groups * 8 + threadIdx.x;
+    if (threadIdx.x < 8 && i < n) {
+      float v = unpack_one<BITS>(in, i);
+      if (WIN) v *= window_value(window, i, nm1);
+      out[i] = v;
+    }
+  }
+}
+
+// scalar fallback for inputs whose base pointer is not 16-byte aligned
+template <int BITS>
+__global__ void __launch_bounds__(256) unpack_simple_scalar_kernel(const void* __restrict__ in,
+                                                                   float* __restrict__ out, size_t n,
+                                                                   int window) {
+  const float nm1 = (float)(n - 1);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = unpack_one<BITS>(in, i) * window_value(window, i, nm1);
+}
+
+// K2 "1 2 1 2" de-interleave (S/unpack.hpp:221-244): thread writes 4 samples per stream
+template <int BITS>
+__global__ void __launch_bounds__(256) unpack_interleaved2_kernel(const void* __restrict__ in,
+                                                                  float* __restrict__ o1,
+                                                                  float* __restrict__ o2, size_t n,
+                                                                  int window) {
+  const float nm1 = (float)(n - 1);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t groups = n / 4;
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    float o[8];
+    unpack_src<BITS>::get(in, g, o);  // 8 interleaved samples = 4 per stream
+    float a[4] = {o[0], o[2], o[4], o[6]}, b[4] = {o[1], o[3], o[5], o[7]};
+    if (window != 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float w = window_value(window, 4 * g + i, nm1);
+        a[i] *= w;
+        b[i] *= w;
+      }
+    }
+    reinterpret_cast<float4*>(o1)[g] = make_float4(a[0], a[1], a[2], a[3]);
+    reinterpret_cast<float4*>(o2)[g] = make_float4(b[0], b[1], b[2], b[3]);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 4) {
+    const size_t i = groups * 4 + threadIdx.x;
+    if (i < n) {
+      const float w = window_value(window, i, nm1);
+      o1[i] = unpack_one<BITS>(in, 2 * i) * w;
+      o2[i] = unpack_one<BITS>(in, 2 * i + 1) * w;
+    }
+  }
+}
+
+// K3 naocpsr_snap1 "1 1 2 2" int8 (S/unpack.hpp:255-283)
+__global__ void __launch_bounds__(256) unpack_snap1_kernel(const void* __restrict__ in,
+                                                           float* __restrict__ o1,
+                                                           float* __restrict__ o2, size_t n,
+                                                           int window) {
+  const float nm1 = (float)(n - 1);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t groups = n / 4;  // 4 samples per stream = 8 input bytes
+  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
+    float o[8];
+    unpack_src<-8>::get(in, g, o);  // a0 a1 b0 b1 a2 a3 b2 b3
+    float a[4] = {o[0], o[1], o[4], o[5]}, b[4] = {o[2], o[3], o[6], o[7]};
+    if (window != 0) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const float w = window_value(window, 4 * g + i, nm1);
+        a[i] *= w;
+        b[i] *= w;
+      }
+    }
+    reinterpret_cast<float4*>(o1)[g] = make_float4(a[0], a[1], a[2], a[3]);
+    reinterpret_cast<float4*>(o2)[g] = make_float4(b[0], b[1], b[2], b[3]);
+  }
+  // tail: the reference launches n/2 work items of 2 samples per stream (:280-282)
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int8_t* p = static_cast<const int8_t*>(in);
+    for (size_t x = groups * 2; x < n / 2; x++) {
+      o1[2 * x] = (float)p[4 * x] * window_value(window, 2 * x, nm1);
+      o1[2 * x + 1] = (float)p[4 * x + 1] * window_value(window, 2 * x + 1, nm1);
+      o2[2 * x] = (float)p[4 * x + 2] * window_value(window, 2 * x, nm1);
+      o2[2 * x + 1] = (float)p[4 * x + 3] * window_value(window, 2 * x + 1, nm1);
+    }
+  }
+}
+
+// K4 gznupsr_a1 (S/unpack.hpp:293-403): 4-sample words round-robin to S streams.
+// S = 4 applies float(int(int8) ^ 0x80) (:315-316); S = 2 does not (:356-357).
+template <int S>
+__global__ void __launch_bounds__(256) unpack_gznupsr_kernel(const void* __restrict__ in,
+                                                             float* __restrict__ o0,
+                                                             float* __restrict__ o1,
+                                                             float* __restrict__ o2,
+                                                             float* __restrict__ o3, size_t n,
+                                                             int window) {
+  const float nm1 = (float)(n - 1);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t words = n / 4;
+  float* outs[4] = {o0, o1, o2, o3};
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < words; x += stride) {
+    unsigned w[4];
+    if (S == 4) {
+      const uint4 v = static_cast<const uint4*>(in)[x];
+      w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    } else {
+      const uint2 v = static_cast<const uint2*>(in)[x];
+      w[0] = v.x; w[1] = v.y; w[2] = 0; w[3] = 0;
+    }
+    float wv[4] = {1.f, 1.f, 1.f, 1.f};
+    if (window != 0) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) wv[j] = window_value(window, 4 * x + j, nm1);
+    }
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+      float f[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int s = (int)(int8_t)((w[i] >> (8 * j)) & 0xffu);
+        f[j] = (S == 4) ? (float)(s ^ 0x80) : (float)s;
+        f[j] *= wv[j];
+      }
+      reinterpret_cast<float4*>(outs[i])[x] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------
+// K8 R2C split post-process (S/fft/naive_fft.hpp:229-260), in place on M + 1 bins:
+// H = FFT_M(x_even + i x_odd);  F = (H_k + conj H_{M-k})/2, G = -i (H_k - conj H_{M-k})/2,
+// X_k = F + G w,  X_{M-k} = conj(F - G w),  w = e^{-i pi k / M};  k = 0 also writes X_M.
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ float2 r2c_twiddle(size_t k, size_t M) {
+  // e^{-i pi k / M}; k/M is exact in fp32 while k < 2^24, otherwise split k = kh*2^12 + kl
+  float s, c;
+  if (M <= ((size_t)1 << 25)) {
+    sincospif(-(float)k / (float)M, &s, &c);
+    return make_float2(c, s);
+  }
+  const size_t kh = k >> 12, kl = k & 4095;
+  float s1, c1, s2, c2;
+  sincospif(-(float)kh / (float)(M >> 12), &s1, &c1);
+  sincospif(-(float)kl / (float)M, &s2, &c2);
+  return make_float2(c1 * c2 - s1 * s2, c1 * s2 + s1 * c2);
+}
+
+__global__ void __launch_bounds__(256) r2c_post_kernel(float2* __restrict__ H, size_t M) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k <= M / 2; k += stride) {
+    const float2 hk = H[k];
+    const float2 hm = (k == 0) ? hk : H[M - k];
+    const float2 F = make_float2(0.5f * (hk.x + hm.x), 0.5f * (hk.y - hm.y));
+    // d = hk - conj(hm) = (hk.x - hm.x, hk.y + hm.y);  G = -i/2 * d = (d.y/2, -d.x/2)
+    const float2 G = make_float2(0.5f * (hk.y + hm.y), -0.5f * (hk.x - hm.x));
+    const float2 w = r2c_twiddle(k, M);
+    const float2 gw = make_float2(G.x * w.x - G.y * w.y, G.x * w.y + G.y * w.x);
+    const float2 xk = make_float2(F.x + gw.x, F.y + gw.y);
+    const float2 xm = make_float2(F.x - gw.x, -(F.y - gw.y));
+    H[k] = xk;
+    H[M - k] = xm;  // k == M/2 writes the same bin twice; the reference keeps this one (:257-258)
+  }
+}
+
+// ------------------------------------------------------------------------------
+// reductions
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum; result valid in thread 0. sm must hold 32 values.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* sm) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[wid] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  T r = (threadIdx.x < nw) ? sm[threadIdx.x] : T(0);
+  if (wid == 0) r = warp_sum(r);
+  return r;
+}
+
+// K9 mean of |X|^2 (S/algorithm/map_reduce.hpp:84-91 over rfi_mitigation_pipe.hpp:53-60).
+// fp32 per-thread partials, fp64 combine, deterministic: per-CTA partials are summed in
+// index order by the last CTA to finish. mean = float(sum) / float(count).
+__global__ void __launch_bounds__(256) power_sum_kernel(const float2* __restrict__ x, size_t count,
+                                                        double* __restrict__ partial,
+                                                        unsigned* __restrict__ ticket,
+                                                        float* __restrict__ mean_out) {
+  __shared__ double sm[32];
+  __shared__ bool last;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t pairs = count / 2;
+  float acc0 = 0.f, acc1 = 0.f;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+    const float4 v = x4[i];
+    acc0 += v.x * v.x + v.y * v.y;
+    acc1 += v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (count & 1)) {
+    const float2 v = x[count - 1];
+    acc0 += v.x * v.x + v.y * v.y;
+  }
+  const double s = block_sum<double>((double)acc0 + (double)acc1, sm);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = s;
+    __threadfence();
+    const unsigned t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) a += partial[i];
+    a = block_sum<double>(a, sm);
+    if (threadIdx.x == 0) {
+      *mean_out = (float)a / (float)count;
+      *ticket = 0;
+    }
+  }
+}
+
+// K10 zap + normalise (S/pipeline/rfi_mitigation_pipe.hpp:66-79)
+__global__ void __launch_bounds__(256) rfi_s1_apply_kernel(float2* __restrict__ x, size_t count,
+                                                           const float* __restrict__ mean,
+                                                           float threshold, float coef) {
+  const float limit = threshold * (*mean);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t pairs = count / 2;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+    float4 v = x4[i];
+    const float p0 = v.x * v.x + v.y * v.y, p1 = v.z * v.z + v.w * v.w;
+    if (p0 > limit) { v.x = 0.f; v.y = 0.f; } else { v.x *= coef; v.y *= coef; }
+    if (p1 > limit) { v.z = 0.f; v.w = 0.f; } else { v.z *= coef; v.w *= coef; }
+    x4[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (count & 1)) {
+    float2 v = x[count - 1];
+    if (v.x * v.x + v.y * v.y > limit) v = make_float2(0.f, 0.f);
+    else { v.x *= coef; v.y *= coef; }
+    x[count - 1] = v;
+  }
+}
+
+// K11 manual zap (S/spectrum/rfi_mitigation.hpp:137-143): blockIdx.y = range
+struct bin_ranges {
+  unsigned long long lo[16], hi[16];
+};
+__global__ void __launch_bounds__(256) rfi_zero_ranges_kernel(float2* __restrict__ x, bin_ranges r) {
+  const size_t lo = r.lo[blockIdx.y], hi = r.hi[blockIdx.y];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i <= hi; i += stride)
+    x[i] = make_float2(0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------
+// K12 chirp multiply (S/coherent_dedispersion.hpp:133-150 phase_factor_v3, :228-236).
+// f = f_min + df*i in fp64 (f32 inputs promoted), k = (D*1e6*dm)/f * ((f-f_c)/f_c)^2,
+// phi = -2 pi frac(k); the sincos is taken as sincospi(-2 frac) in fp32.
+// ------------------------------------------------------------------------------
+__device__ __forceinline__ float2 chirp_factor(double f_min, double df, double f_c, double ddm,
+                                               size_t i) {
+  const double f = f_min + df * (double)i;
+  const double delta_f = f - f_c;
+  const double q = delta_f / f_c;
+  const double k = ddm / f * (q * q);
+  const float frac = (float)(k - trunc(k));
+  float s, c;
+  sincospif(-2.0f * frac, &s, &c);
+  return make_float2(c, s);
+}
+
+__global__ void __launch_bounds__(256) dedisperse_kernel(float2* __restrict__ x, size_t count,
+                                                         double f_min, double df, double f_c,
+                                                         double ddm) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t pairs = count / 2;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+    float4 v = x4[i];
+    const float2 w0 = chirp_factor(f_min, df, f_c, ddm, 2 * i);
+    const float2 w1 = chirp_factor(f_min, df, f_c, ddm, 2 * i + 1);
+    const float4 o = make_float4(v.x * w0.x - v.y * w0.y, v.x * w0.y + v.y * w0.x,
+                                 v.z * w1.x - v.w * w1.y, v.z * w1.y + v.w * w1.x);
+    x4[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (count & 1)) {
+    const float2 v = x[count - 1];
+    const float2 w = chirp_factor(f_min, df, f_c, ddm, count - 1);
+    x[count - 1] = make_float2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
+  }
+}
+
+// ------------------------------------------------------------------------------
+// K14 + K15 spectral kurtosis (S/spectrum/rfi_mitigation.hpp:292-341; sums by
+// S/algorithm/multi_reduce.hpp:115-155). One CTA per channel row: s2, s4, decide, zero.
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sk_kernel(float2* __restrict__ x, size_t time_count,
+                                                 float thr_lo, float thr_hi,
+                                                 float* __restrict__ sk_out) {
+  __shared__ float sm[32];
+  __shared__ int zap;
+  float2* row = x + (size_t)blockIdx.x * time_count;
+  float s2 = 0.f, s4 = 0.f;
+  const size_t pairs = time_count / 2;
+  const float4* r4 = reinterpret_cast<const float4*>(row);
+  const bool vec = ((((size_t)blockIdx.x * time_count) & 1) == 0);
+  if (vec) {
+    for (size_t i = threadIdx.x; i < pairs; i += blockDim.x) {
+      const float4 v = r4[i];
+      const float p0 = v.x * v.x + v.y * v.y, p1 = v.z * v.z + v.w * v.w;
+      s2 += p0 + p1;
+      s4 += p0 * p0 + p1 * p1;
+    }
+    if (threadIdx.x == 0 && (time_count & 1)) {
+      const float2 v = row[time_count - 1];
+      const float p = v.x * v.x + v.y * v.y;
+      s2 += p;
+      s4 += p * p;
+    }
+  } else {
+    for (size_t i = threadIdx.x; i < time_count; i += blockDim.x) {
+      const float2 v = row[i];
+      const float p = v.x * v.x + v.y * v.y;
+      s2 += p;
+      s4 += p * p;
+    }
+  }
+  const float t2 = block_sum<float>(s2, sm);
+  const float t4 = block_sum<float>(s4, sm);
+  if (threadIdx.x == 0) {
+    const float sk = (float)time_count * (t4 / (t2 * t2));
+    zap = (sk > thr_hi || sk < thr_lo) ? 1 : 0;  // NaN compares false: row left as is
+    if (sk_out) sk_out[blockIdx.x] = sk;
+  }
+  __syncthreads();
+  if (zap) {
+    for (size_t i = threadIdx.x; i < time_count; i += blockDim.x) row[i] = make_float2(0.f, 0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------
+// signal detect (S/pipeline/signal_detect_pipe.hpp:252-442, S/signal_detect.hpp:32-72)
+// ------------------------------------------------------------------------------
+struct detect_dev_result {
+  unsigned long long zero_count;
+  unsigned long long time_series_count;
+  int detect_enabled;
+  int n_boxcars;
+  unsigned long long boxcar_length[32];
+  unsigned long long series_length[32];
+  unsigned long long signal_count[32];
+  float variance[32];
+  float threshold[32];
+};
+
+// K17 stage 1: partial column sums over a chunk of channels. Thread = 2 adjacent time
+// samples (one float4 load), lanes along time (coalesced); blockIdx.y = channel chunk.
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float2* __restrict__ x,
+                                                             size_t time_count, size_t chan_count,
+                                                             size_t ts_count, size_t rows_per_chunk,
+                                                             float* __restrict__ partial) {
+  const size_t j2 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (j2 >= ts_count) return;
+  const size_t c0 = (size_t)blockIdx.y * rows_per_chunk;
+  const size_t c1 = min(c0 + rows_per_chunk, chan_count);
+  float a0 = 0.f, a1 = 0.f;
+  const bool two = (j2 + 1 < ts_count);
+  const bool vec = ((time_count & 1) == 0);
+  if (vec && two) {
+#pragma unroll 4
+    for (size_t c = c0; c < c1; c++) {
+      const float4 v = *reinterpret_cast<const float4*>(x + c * time_count + j2);
+      a0 += v.x * v.x + v.y * v.y;
+      a1 += v.z * v.z + v.w * v.w;
+    }
+  } else {
+    for (size_t c = c0; c < c1; c++) {
+      const float2 v = x[c * time_count + j2];
+      a0 += v.x * v.x + v.y * v.y;
+      if (two) {
+        const float2 w = x[c * time_count + j2 + 1];
+        a1 += w.x * w.x + w.y * w.y;
+      }
+    }
+  }
+  float* p = partial + (size_t)blockIdx.y * ts_count + j2;
+  p[0] = a0;
+  if (two) p[1] = a1;
+}
+
+// K17 stage 2 + K16: ts[j] = sum over chunks (ascending), zero_count
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial,
+                                                           size_t ts_count, size_t chunks,
+                                                           float* __restrict__ ts,
+                                                           const float2* __restrict__ x,
+                                                           size_t time_count, size_t chan_count,
+                                                           detect_dev_result* __restrict__ res) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < ts_count; j += stride) {
+    float a = 0.f;
+    for (size_t c = 0; c < chunks; c++) a += partial[c * ts_count + j];
+    ts[j] = a;
+  }
+  if (blockIdx.x == 0) {
+    __shared__ float sm[32];
+    float z = 0.f;
+    for (size_t c = threadIdx.x; c < chan_count; c += blockDim.x) {
+      const float2 v = x[c * time_count];
+      if (v.x * v.x + v.y * v.y == 0.f) z += 1.f;
+    }
+    z = block_sum<float>(z, sm);
+    if (threadIdx.x == 0) res->zero_count = (unsigned long long)z;
+  }
+}
+
+// K18-K21 in one CTA: mean removal, count_signal, inclusive scan, boxcar ladder.
+// series layout: row b (stride row_stride) = series of entry b. acc = scan buffer.
+__global__ void __launch_bounds__(1024) detect_tail_kernel(float* __restrict__ series,
+                                                           size_t row_stride, float* __restrict__ acc,
+                                                           size_t ts_count, size_t chan_count,
+                                                           float snr, float chan_thr,
+                                                           size_t max_boxcar,
+                                                           detect_dev_result* __restrict__ res) {
+  __shared__ double smd[32];
+  __shared__ double chunk_off[1024];
+  __shared__ float s_thr;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  float* ts = series;
+  // mean removal (:324-334)
+  double a = 0.0;
+  for (size_t i = tid; i < ts_count; i += nt) a += (double)ts[i];
+  a = block_sum<double>(a, smd);
+  __shared__ float s_mean;
+  if (tid == 0) s_mean = (float)a / (float)ts_count;
+  __syncthreads();
+  const float mean = s_mean;
+  for (size_t i = tid; i < ts_count; i += nt) ts[i] -= mean;
+  __syncthreads();
+  if (tid == 0) {
+    res->time_series_count = ts_count;
+    res->detect_enabled = ((float)res->zero_count < chan_thr * (float)chan_count) ? 1 : 0;
+    res->n_boxcars = 0;
+  }
+  __syncthreads();
+  if (!res->detect_enabled) return;
+
+  // inclusive scan of ts -> acc: per-thread contiguous chunk, chunk offsets in fp64
+  const size_t per = (ts_count + nt - 1) / nt;
+  const size_t lo = min((size_t)tid * per, ts_count), hi = min(lo + per, ts_count);
+  double local = 0.0;
+  for (size_t i = lo; i < hi; i++) local += (double)ts[i];
+  chunk_off[tid] = local;
+  __syncthreads();
+  if (tid == 0) {
+    double run = 0.0;
+    for (int i = 0; i < nt; i++) {
+      const double t = chunk_off[i];
+      chunk_off[i] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+  {
+    double run = chunk_off[tid];
+    for (size_t i = lo; i < hi; i++) {
+      run += (double)ts[i];
+      acc[i] = (float)run;
+    }
+  }
+  __syncthreads();
+
+  int nb = 0;
+  for (size_t b = 1; (b == 1) || (b <= max_boxcar && b < ts_count); b *= 2) {
+    if (nb >= 32) break;
+    float* v = series + (size_t)nb * row_stride;
+    const size_t n = (b == 1) ? ts_count : ts_count - b;
+    if (b > 1) {
+      for (size_t i = tid; i < n; i += nt) v[i] = acc[i + b] - acc[i];
+      __syncthreads();
+    }
+    double sq = 0.0;
+    for (size_t i = tid; i < n; i += nt) sq += (double)v[i] * (double)v[i];
+    sq = block_sum<double>(sq, smd);
+    if (tid == 0) {
+      const float var = (float)sq / (float)n;
+      s_thr = snr * sqrtf(var);
+      res->variance[nb] = var;
+      res->threshold[nb] = s_thr;
+      res->boxcar_length[nb] = b;
+      res->series_length[nb] = n;
+    }
+    __syncthreads();
+    const float thr = s_thr;
+    double cnt = 0.0;
+    for (size_t i = tid; i < n; i += nt)
+      if (v[i] > thr) cnt += 1.0;
+    cnt = block_sum<double>(cnt, smd);
+    if (tid == 0) res->signal_count[nb] = (unsigned long long)cnt;
+    __syncthreads();
+    nb++;
+  }
+  if (tid == 0) res->n_boxcars = nb;
+}
+
+}  // namespace srtb_b200

@@ -1,0 +1,833 @@
+// srtb_b200.cu — C-ABI implementation (include/srtb_b200.h): context, FFT planning,
+// kernel launches. Host logic only mirrors the reference's host-side arithmetic; every
+// data-path byte is touched by the CUDA kernels in fft_engine.cuh / ops_kernels.cuh.
+// There is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/srtb_b200.h"
+#include "fft_engine.cuh"
+#include "ops_kernels.cuh"
+
+using namespace srtb_b200;
+
+static thread_local std::string g_last_error;
+
+struct srtb_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::string err;
+  uint64_t launches = 0;
+  std::set<const void*> configured;  // kernels whose smem attribute is set on this device
+  // FFT
+  float2* tw[13] = {nullptr};
+  std::map<int, float2*> bigtw;  // log2(n_i) -> [3 << q]
+  void* fft_scratch = nullptr;
+  size_t fft_scratch_bytes = 0;
+  // s1
+  double* partial = nullptr;
+  unsigned* ticket = nullptr;
+  float* mean = nullptr;
+  // detect (slots = streams in flight)
+  float* colsum_partial = nullptr;
+  size_t colsum_partial_elems = 0;
+  float* series[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t series_elems = 0;
+  float* acc = nullptr;
+  size_t acc_elems = 0;
+  detect_dev_result* d_res = nullptr;
+  detect_dev_result* h_res = nullptr;  // pinned, 4 slots
+  size_t slot_time_count[4] = {0, 0, 0, 0};
+  // process_block
+  void* d_baseband = nullptr;
+  size_t d_baseband_bytes = 0;
+  float* stream_buf[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t stream_buf_elems = 0;
+};
+
+static int fail(srtb_b200_ctx* ctx, int code, const std::string& msg) {
+  g_last_error = msg;
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(ctx, SRTB_B200_E_CUDA,                                                  \
+                  std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                      std::to_string(__LINE__) + ")");                                    \
+  } while (0)
+
+static int ensure(srtb_b200_ctx* ctx, void** p, size_t* have, size_t want_bytes) {
+  if (*have >= want_bytes && *p) return 0;
+  if (*p) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+  }
+  cudaError_t e = cudaMalloc(p, want_bytes);
+  if (e != cudaSuccess)
+    return fail(ctx, SRTB_B200_E_NOMEM, std::string("cudaMalloc(") + std::to_string(want_bytes) +
+                                            "): " + cudaGetErrorString(e));
+  *have = want_bytes;
+  return 0;
+}
+
+static inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+static inline int ilog2(size_t n) {
+  int k = 0;
+  while (((size_t)1 << k) < n) k++;
+  return k;
+}
+static inline unsigned grid_for(const srtb_b200_ctx* ctx, size_t work_items, int threads, int per_sm = 8) {
+  const size_t need = (work_items + threads - 1) / threads;
+  const size_t cap = (size_t)ctx->sm_count * per_sm;
+  return (unsigned)std::max<size_t>(1, std::min(need, cap));
+}
+
+extern "C" {
+
+const char* srtb_b200_version(void) { return "srtb_b200 0.1 (sm_100a)"; }
+
+int srtb_b200_ctx_create(int device, void* cuda_stream, srtb_b200_ctx** out) {
+  srtb_b200_ctx* ctx = nullptr;
+  if (!out) return fail(nullptr, SRTB_B200_E_INVALID, "ctx_create: out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, SRTB_B200_E_CUDA,
+                std::string("ctx_create: no CUDA device (") + cudaGetErrorString(e) +
+                    "); libsrtb_b200 has no CPU fallback");
+  if (device < 0 || device >= count) return fail(nullptr, SRTB_B200_E_INVALID, "ctx_create: bad device index");
+  ctx = new srtb_b200_ctx();
+  ctx->device = device;
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->partial, sizeof(double) * 4096);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->ticket, sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(ctx->ticket, 0, sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->mean, sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_res, sizeof(detect_dev_result) * 4);
+  if (e == cudaSuccess) e = cudaMemset(ctx->d_res, 0, sizeof(detect_dev_result) * 4);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_res, sizeof(detect_dev_result) * 4);
+  if (e != cudaSuccess) {
+    const std::string msg = std::string("ctx_create: ") + cudaGetErrorString(e);
+    delete ctx;
+    return fail(nullptr, SRTB_B200_E_CUDA, msg);
+  }
+  *out = ctx;
+  return 0;
+}
+
+int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& p : ctx->tw)
+    if (p) cudaFree(p);
+  for (auto& kv : ctx->bigtw) cudaFree(kv.second);
+  cudaFree(ctx->fft_scratch);
+  cudaFree(ctx->partial);
+  cudaFree(ctx->ticket);
+  cudaFree(ctx->mean);
+  cudaFree(ctx->colsum_partial);
+  for (auto& p : ctx->series) cudaFree(p);
+  cudaFree(ctx->acc);
+  cudaFree(ctx->d_res);
+  cudaFreeHost(ctx->h_res);
+  cudaFree(ctx->d_baseband);
+  for (auto& p : ctx->stream_buf) cudaFree(p);
+  delete ctx;
+  return 0;
+}
+
+int srtb_b200_ctx_set_stream(srtb_b200_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "set_stream: ctx is null");
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  return 0;
+}
+
+int srtb_b200_synchronize(srtb_b200_ctx* ctx) {
+  if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "synchronize: ctx is null");
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+const char* srtb_b200_last_error(const srtb_b200_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_last_error.c_str();
+}
+
+uint64_t srtb_b200_launch_count(const srtb_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------
+// unpack
+// ------------------------------------------------------------------------------------
+template <int BITS>
+static int launch_unpack_simple(srtb_b200_ctx* ctx, const void* d_in, float* out, size_t n, int window) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(d_in) & 15u) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
+  if (!aligned) {
+    unpack_simple_scalar_kernel<BITS><<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(d_in, out, n, window);
+  } else if (window == 0) {
+    unpack_simple_kernel<BITS, false><<<grid_for(ctx, n / 8 + 1, 256), 256, 0, ctx->stream>>>(d_in, out, n, window);
+  } else {
+    unpack_simple_kernel<BITS, true><<<grid_for(ctx, n / 8 + 1, 256), 256, 0, ctx->stream>>>(d_in, out, n, window);
+  }
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int BITS>
+static int launch_unpack_il2(srtb_b200_ctx* ctx, const void* d_in, float* o1, float* o2, size_t n, int window) {
+  unpack_interleaved2_kernel<BITS><<<grid_for(ctx, n / 4 + 1, 256), 256, 0, ctx->stream>>>(d_in, o1, o2, n, window);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srtb_b200_unpack(srtb_b200_ctx* ctx, const void* d_in, size_t in_bytes, int bits,
+                                int format, int window, float* const d_out[4], size_t out_count) {
+  if (!ctx || !d_in || !d_out || !d_out[0]) return fail(ctx, SRTB_B200_E_INVALID, "unpack: null argument");
+  if (window < 0 || window > 2) return fail(ctx, SRTB_B200_E_INVALID, "unpack: unknown window");
+  if (out_count == 0) return 0;
+  const int abits = bits < 0 ? -bits : bits;
+  int streams = 1;
+  if (format == SRTB_B200_FORMAT_INTERLEAVED_2 || format == SRTB_B200_FORMAT_NAOCPSR_SNAP1 ||
+      format == SRTB_B200_FORMAT_GZNUPSR_A1_2)
+    streams = 2;
+  else if (format == SRTB_B200_FORMAT_GZNUPSR_A1_4)
+    streams = 4;
+  else if (format != SRTB_B200_FORMAT_SIMPLE)
+    return fail(ctx, SRTB_B200_E_UNSUPPORTED, "[start_unpack_pipe] Unknown format name: " + std::to_string(format));
+  if (abits == 0 || (size_t)out_count * streams * abits > in_bytes * 8)
+    return fail(ctx, SRTB_B200_E_INVALID, "unpack: in_bytes too small for out_count");
+  for (int s = 0; s < streams; s++)
+    if (!d_out[s]) return fail(ctx, SRTB_B200_E_INVALID, "unpack: null output stream");
+  CK(cudaSetDevice(ctx->device));
+  switch (format) {
+    case SRTB_B200_FORMAT_SIMPLE:
+      switch (bits) {
+        case 1: return launch_unpack_simple<1>(ctx, d_in, d_out[0], out_count, window);
+        case 2: return launch_unpack_simple<2>(ctx, d_in, d_out[0], out_count, window);
+        case 4: return launch_unpack_simple<4>(ctx, d_in, d_out[0], out_count, window);
+        case 8: return launch_unpack_simple<8>(ctx, d_in, d_out[0], out_count, window);
+        case -8: return launch_unpack_simple<-8>(ctx, d_in, d_out[0], out_count, window);
+        case 16: return launch_unpack_simple<16>(ctx, d_in, d_out[0], out_count, window);
+        case -16: return launch_unpack_simple<-16>(ctx, d_in, d_out[0], out_count, window);
+        case 32: return launch_unpack_simple<32>(ctx, d_in, d_out[0], out_count, window);
+        case 64: return launch_unpack_simple<64>(ctx, d_in, d_out[0], out_count, window);
+        default:
+          return fail(ctx, SRTB_B200_E_UNSUPPORTED,
+                      "[unpack pipe] unsupported baseband_input_bits = " + std::to_string(bits));
+      }
+    case SRTB_B200_FORMAT_INTERLEAVED_2:
+      switch (bits) {
+        case 8: return launch_unpack_il2<8>(ctx, d_in, d_out[0], d_out[1], out_count, window);
+        case -8: return launch_unpack_il2<-8>(ctx, d_in, d_out[0], d_out[1], out_count, window);
+        case 16: return launch_unpack_il2<16>(ctx, d_in, d_out[0], d_out[1], out_count, window);
+        case -16: return launch_unpack_il2<-16>(ctx, d_in, d_out[0], d_out[1], out_count, window);
+        case 32: return launch_unpack_il2<32>(ctx, d_in, d_out[0], d_out[1], out_count, window);
+        case 64: return launch_unpack_il2<64>(ctx, d_in, d_out[0], d_out[1], out_count, window);
+        default:
+          return fail(ctx, SRTB_B200_E_UNSUPPORTED,
+                      "[unpack_2pol_interleave_pipe] unsupported baseband_input_bits = " + std::to_string(bits));
+      }
+    case SRTB_B200_FORMAT_NAOCPSR_SNAP1:
+      if (bits != -8)
+        return fail(ctx, SRTB_B200_E_UNSUPPORTED, "naocpsr_snap1 requires baseband_input_bits = -8");
+      unpack_snap1_kernel<<<grid_for(ctx, out_count / 4 + 1, 256), 256, 0, ctx->stream>>>(d_in, d_out[0], d_out[1], out_count, window);
+      break;
+    case SRTB_B200_FORMAT_GZNUPSR_A1_2:
+      unpack_gznupsr_kernel<2><<<grid_for(ctx, out_count / 4 + 1, 256), 256, 0, ctx->stream>>>(
+          d_in, d_out[0], d_out[1], nullptr, nullptr, out_count, window);
+      break;
+    case SRTB_B200_FORMAT_GZNUPSR_A1_4:
+      unpack_gznupsr_kernel<4><<<grid_for(ctx, out_count / 4 + 1, 256), 256, 0, ctx->stream>>>(
+          d_in, d_out[0], d_out[1], d_out[2], d_out[3], out_count, window);
+      break;
+  }
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// FFT planning + launches
+// ------------------------------------------------------------------------------------
+static int get_stage_twiddles(srtb_b200_ctx* ctx, int logl, const float2** out) {
+  if (!ctx->tw[logl]) {
+    const size_t L = (size_t)1 << logl;
+    std::vector<float2> h(L);
+    for (size_t j = 0; j < L; j++) {
+      const double a = -2.0 * M_PI * (double)j / (double)L;
+      h[j] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    CK(cudaMalloc(&ctx->tw[logl], L * sizeof(float2)));
+    CK(cudaMemcpyAsync(ctx->tw[logl], h.data(), L * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  *out = ctx->tw[logl];
+  return 0;
+}
+
+static int get_big_twiddles(srtb_b200_ctx* ctx, int logn, big_twiddle* out) {
+  const int q = (logn + 2) / 3;
+  auto it = ctx->bigtw.find(logn);
+  if (it == ctx->bigtw.end()) {
+    const size_t n = (size_t)1 << logn, m = (size_t)1 << q;
+    std::vector<float2> h(3 * m);
+    for (int level = 0; level < 3; level++)
+      for (size_t j = 0; j < m; j++) {
+        const size_t idx = (j << (level * q)) & (n - 1);
+        const double a = -2.0 * M_PI * (double)idx / (double)n;
+        h[level * m + j] = make_float2((float)std::cos(a), (float)std::sin(a));
+      }
+    float2* d = nullptr;
+    CK(cudaMalloc(&d, h.size() * sizeof(float2)));
+    CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    it = ctx->bigtw.emplace(logn, d).first;
+  }
+  out->tab = it->second;
+  out->q = q;
+  return 0;
+}
+
+template <int LOGL, int T, int MODE, bool FWD, class IO>
+static int launch_pass(srtb_b200_ctx* ctx, const IO& io, unsigned grid, size_t extra_smem) {
+  auto kern = fft_pass_kernel<LOGL, T, MODE, FWD, IO>;
+  const size_t smem = (size_t)tile_layout<LOGL, T, MODE>::ELEMS * sizeof(float2) + extra_smem;
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (smem > 48 * 1024 && !ctx->configured.count(key)) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    ctx->configured.insert(key);
+  }
+  const float2* tw = nullptr;
+  if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+  kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(io, tw);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// rows per CTA in ROW mode: 256 threads up to L = 2048, 512 threads for L = 4096
+template <int LOGL>
+struct row_t {
+  static constexpr int value = (LOGL >= 11) ? 1 : (1 << (11 - LOGL));
+};
+template <int LOGL>
+struct col_t {
+  static constexpr int value = (LOGL <= 8) ? 16 : 8;
+};
+
+template <int LOGL, bool FWD>
+static int launch_row(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t nrows) {
+  constexpr int T = row_t<LOGL>::value;
+  row_io<LOGL, T> io;
+  io.in = in;
+  io.out = out;
+  io.nrows = nrows;
+  io.row0 = 0;
+  const unsigned grid = (unsigned)((nrows + T - 1) / T);
+  return launch_pass<LOGL, T, MODE_ROW, FWD>(ctx, io, grid, 0);
+}
+
+template <int LOGL, bool FWD>
+static int launch_col(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t B) {
+  constexpr int T = col_t<LOGL>::value;
+  col_io<LOGL, T, FWD> io;
+  io.in = in;
+  io.out = out;
+  io.B = B;
+  io.btiles = (uint32_t)(B / T);
+  if (int rc = get_big_twiddles(ctx, LOGL + ilog2(B), &io.btw)) return rc;
+  io.base = 0;
+  io.b0 = 0;
+  io.stw = nullptr;
+  const unsigned grid = (unsigned)(A * (B / T));
+  return launch_pass<LOGL, T, MODE_COL, FWD>(ctx, io, grid, (size_t)(3u << io.btw.q) * sizeof(float2));
+}
+
+template <int LOGL, bool FWD>
+static int launch_trans(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t batch, size_t A,
+                        size_t L1) {
+  constexpr int T = col_t<LOGL>::value;
+  trans_io<LOGL, T> io;
+  io.in = in;
+  io.out = out;
+  io.A = (uint32_t)A;
+  io.S = (uint32_t)(A / L1);
+  io.L1 = (uint32_t)L1;
+  io.k1tiles = (uint32_t)(L1 / T);
+  io.in_row0 = 0;
+  io.out0 = 0;
+  const unsigned grid = (unsigned)(batch * io.S * io.k1tiles);
+  return launch_pass<LOGL, T, MODE_TRANS, FWD>(ctx, io, grid, 0);
+}
+
+#define SRTB_DISPATCH_LOGL(fn, logl, lo, hi, ...)                       \
+  switch (logl) {                                                       \
+    case 3: if (lo <= 3 && 3 <= hi) return fn<(lo <= 3 && 3 <= hi) ? 3 : lo, FWD>(__VA_ARGS__); break;   \
+    case 4: if (lo <= 4 && 4 <= hi) return fn<(lo <= 4 && 4 <= hi) ? 4 : lo, FWD>(__VA_ARGS__); break;   \
+    case 5: if (lo <= 5 && 5 <= hi) return fn<(lo <= 5 && 5 <= hi) ? 5 : lo, FWD>(__VA_ARGS__); break;   \
+    case 6: if (lo <= 6 && 6 <= hi) return fn<(lo <= 6 && 6 <= hi) ? 6 : lo, FWD>(__VA_ARGS__); break;   \
+    case 7: if (lo <= 7 && 7 <= hi) return fn<(lo <= 7 && 7 <= hi) ? 7 : lo, FWD>(__VA_ARGS__); break;   \
+    case 8: if (lo <= 8 && 8 <= hi) return fn<(lo <= 8 && 8 <= hi) ? 8 : lo, FWD>(__VA_ARGS__); break;   \
+    case 9: if (lo <= 9 && 9 <= hi) return fn<(lo <= 9 && 9 <= hi) ? 9 : lo, FWD>(__VA_ARGS__); break;   \
+    case 10: if (lo <= 10 && 10 <= hi) return fn<(lo <= 10 && 10 <= hi) ? 10 : lo, FWD>(__VA_ARGS__); break; \
+    case 11: if (lo <= 11 && 11 <= hi) return fn<(lo <= 11 && 11 <= hi) ? 11 : lo, FWD>(__VA_ARGS__); break; \
+    case 12: if (lo <= 12 && 12 <= hi) return fn<(lo <= 12 && 12 <= hi) ? 12 : lo, FWD>(__VA_ARGS__); break; \
+    default: break;                                                     \
+  }
+
+template <bool FWD>
+static int dispatch_row(srtb_b200_ctx* ctx, int logl, const float2* in, float2* out, size_t nrows) {
+  SRTB_DISPATCH_LOGL(launch_row, logl, 3, 12, ctx, in, out, nrows)
+  return fail(ctx, SRTB_B200_E_SIZE, "fft: unsupported row length 2^" + std::to_string(logl));
+}
+template <bool FWD>
+static int dispatch_col(srtb_b200_ctx* ctx, int logl, const float2* in, float2* out, size_t A, size_t B) {
+  SRTB_DISPATCH_LOGL(launch_col, logl, 6, 10, ctx, in, out, A, B)
+  return fail(ctx, SRTB_B200_E_SIZE, "fft: unsupported column length 2^" + std::to_string(logl));
+}
+template <bool FWD>
+static int dispatch_trans(srtb_b200_ctx* ctx, int logl, const float2* in, float2* out, size_t batch,
+                          size_t A, size_t L1) {
+  SRTB_DISPATCH_LOGL(launch_trans, logl, 6, 10, ctx, in, out, batch, A, L1)
+  return fail(ctx, SRTB_B200_E_SIZE, "fft: unsupported last-pass length 2^" + std::to_string(logl));
+}
+
+// L = 2 or 4: one thread per row
+template <bool FWD>
+__global__ void tiny_fft_kernel(float2* x, int logl, size_t nrows) {
+  const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  if (logl == 1) {
+    float2 a = x[2 * r], b = x[2 * r + 1];
+    dft2<FWD>(a, b);
+    x[2 * r] = a;
+    x[2 * r + 1] = b;
+  } else {
+    float2 a = x[4 * r], b = x[4 * r + 1], c = x[4 * r + 2], d = x[4 * r + 3];
+    dft4<FWD>(a, b, c, d);
+    x[4 * r] = a;
+    x[4 * r + 1] = b;
+    x[4 * r + 2] = c;
+    x[4 * r + 3] = d;
+  }
+}
+
+template <bool FWD>
+static int fft_c2c_impl(srtb_b200_ctx* ctx, float2* x, size_t n, size_t batch) {
+  const int q = ilog2(n);
+  if (q == 0) return 0;
+  if (q <= 2) {
+    tiny_fft_kernel<FWD><<<(unsigned)((batch + 255) / 256), 256, 0, ctx->stream>>>(x, q, batch);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
+  if (q <= 12) return dispatch_row<FWD>(ctx, q, x, x, batch);
+  if (q > 30) return fail(ctx, SRTB_B200_E_SIZE, "fft: length above 2^30 not supported");
+  if (batch * n > ((size_t)1 << 32) * 4)
+    return fail(ctx, SRTB_B200_E_SIZE, "fft: batch * length too large");
+  if (int rc = ensure(ctx, &ctx->fft_scratch, &ctx->fft_scratch_bytes, batch * n * sizeof(float2))) return rc;
+  float2* s = static_cast<float2*>(ctx->fft_scratch);
+  if (q <= 20) {
+    const int l1 = (q + 1) / 2, l2 = q - l1;
+    const size_t L1 = (size_t)1 << l1, L2 = (size_t)1 << l2;
+    if (int rc = dispatch_col<FWD>(ctx, l1, x, s, batch, L2)) return rc;
+    return dispatch_trans<FWD>(ctx, l2, s, x, batch, L1, L1);
+  }
+  const int l1 = (q + 2) / 3, l2 = (q - l1 + 1) / 2, l3 = q - l1 - l2;
+  const size_t L1 = (size_t)1 << l1, L2 = (size_t)1 << l2, L3 = (size_t)1 << l3;
+  if (int rc = dispatch_col<FWD>(ctx, l1, x, s, batch, L2 * L3)) return rc;
+  if (int rc = dispatch_col<FWD>(ctx, l2, s, s, batch * L1, L3)) return rc;
+  return dispatch_trans<FWD>(ctx, l3, s, x, batch, L1 * L2, L1);
+}
+
+extern "C" int srtb_b200_fft_c2c(srtb_b200_ctx* ctx, void* d_x, size_t length, size_t batch, int direction) {
+  if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "fft_c2c: null argument");
+  if (length == 0 || batch == 0) return fail(ctx, SRTB_B200_E_INVALID, "fft_c2c: zero size");
+  if (!is_pow2(length))
+    return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(length));
+  if (direction != 1 && direction != -1) return fail(ctx, SRTB_B200_E_INVALID, "fft_c2c: direction must be +1 / -1");
+  CK(cudaSetDevice(ctx->device));
+  if (direction == 1) return fft_c2c_impl<true>(ctx, static_cast<float2*>(d_x), length, batch);
+  return fft_c2c_impl<false>(ctx, static_cast<float2*>(d_x), length, batch);
+}
+
+extern "C" int srtb_b200_watfft_c2c_backward(srtb_b200_ctx* ctx, void* d_x, size_t length, size_t batch) {
+  return srtb_b200_fft_c2c(ctx, d_x, length, batch, -1);
+}
+
+extern "C" int srtb_b200_fft_r2c_inplace(srtb_b200_ctx* ctx, float* d_inout, size_t n_real) {
+  if (!ctx || !d_inout) return fail(ctx, SRTB_B200_E_INVALID, "fft_r2c: null argument");
+  if (n_real < 2 || !is_pow2(n_real))
+    return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(n_real));
+  CK(cudaSetDevice(ctx->device));
+  const size_t M = n_real / 2;
+  float2* H = reinterpret_cast<float2*>(d_inout);
+  if (int rc = fft_c2c_impl<true>(ctx, H, M, 1)) return rc;
+  r2c_post_kernel<<<grid_for(ctx, M / 2 + 1, 256), 256, 0, ctx->stream>>>(H, M);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// RFI stage 1
+// ------------------------------------------------------------------------------------
+extern "C" float srtb_b200_norm_coefficient(size_t in_count, size_t spectrum_channel_count) {
+  // std::pow(float(Nc) * float(Nc) / float(C), -0.5) evaluated in double, stored as float
+  return static_cast<float>(std::pow(
+      static_cast<float>(in_count) * static_cast<float>(in_count) / static_cast<float>(spectrum_channel_count),
+      -0.5));
+}
+
+// boost::split(..., token_compress_on): adjacent separators merge into one
+static std::vector<std::string> split_compress(const std::string& s, char sep) {
+  std::vector<std::string> out(1);
+  bool prev_sep = false;
+  for (char c : s) {
+    if (c == sep) {
+      if (!prev_sep) out.emplace_back();
+      prev_sep = true;
+    } else {
+      out.back().push_back(c);
+      prev_sep = false;
+    }
+  }
+  return out;
+}
+
+extern "C" size_t srtb_b200_eval_rfi_ranges(const char* freq_list, float* pairs, size_t max_pairs) {
+  // "a-b, c-d" (MHz): split on ',' then on '-'; entries that are not exactly two numbers are
+  // skipped (the reference logs a warning, rfi_mitigation.hpp:76-78)
+  if (!freq_list) return 0;
+  size_t n = 0;
+  for (const std::string& range : split_compress(freq_list, ',')) {
+    const std::vector<std::string> nums = split_compress(range, '-');
+    if (nums.size() != 2) continue;
+    char* end = nullptr;
+    const double f1 = std::strtod(nums[0].c_str(), &end);
+    if (end == nums[0].c_str()) continue;
+    const double f2 = std::strtod(nums[1].c_str(), &end);
+    if (end == nums[1].c_str()) continue;
+    if (pairs && n < max_pairs) {
+      pairs[2 * n] = static_cast<float>(f1);
+      pairs[2 * n + 1] = static_cast<float>(f2);
+    }
+    n++;
+  }
+  return n;
+}
+
+extern "C" int srtb_b200_rfi_range_to_bins(float f1, float f2, float freq_low, float bandwidth,
+                                           size_t in_count, size_t* lo, size_t* hi) {
+  if (std::signbit(bandwidth) != std::signbit(f2 - f1)) std::swap(f1, f2);
+  const float scale = static_cast<float>(in_count - 1);
+  const float a = std::round((f1 - freq_low) / bandwidth * scale);
+  const float b = std::round((f2 - freq_low) / bandwidth * scale);
+  if (!(a >= 0.0f) || !(b >= 0.0f) || a >= 1.8446744e19f || b >= 1.8446744e19f) return 0;
+  const size_t l = static_cast<size_t>(a), h = static_cast<size_t>(b);
+  if (l <= h && h < in_count) {
+    if (lo) *lo = l;
+    if (hi) *hi = h;
+    return 1;
+  }
+  return 0;
+}
+
+extern "C" int srtb_b200_rfi_s1(srtb_b200_ctx* ctx, void* d_x, size_t count, float avg_threshold,
+                                float norm_coef, const size_t* h_bin_ranges, size_t n_ranges,
+                                float* d_mean_out) {
+  if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s1: null argument");
+  if (count == 0) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s1: zero count");
+  if (n_ranges && !h_bin_ranges) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s1: null ranges");
+  CK(cudaSetDevice(ctx->device));
+  float2* x = static_cast<float2*>(d_x);
+  const unsigned grid = std::min<unsigned>(grid_for(ctx, count / 2 + 1, 256), 4096);
+  power_sum_kernel<<<grid, 256, 0, ctx->stream>>>(x, count, ctx->partial, ctx->ticket, ctx->mean);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (d_mean_out) CK(cudaMemcpyAsync(d_mean_out, ctx->mean, sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  rfi_s1_apply_kernel<<<grid_for(ctx, count / 2 + 1, 256), 256, 0, ctx->stream>>>(x, count, ctx->mean, avg_threshold, norm_coef);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  for (size_t r0 = 0; r0 < n_ranges; r0 += 16) {
+    bin_ranges br;
+    const size_t nr = std::min<size_t>(16, n_ranges - r0);
+    size_t longest = 1;
+    for (size_t r = 0; r < nr; r++) {
+      const size_t lo = h_bin_ranges[2 * (r0 + r)], hi = h_bin_ranges[2 * (r0 + r) + 1];
+      if (!(lo <= hi && hi < count)) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s1: bin range out of bounds");
+      br.lo[r] = lo;
+      br.hi[r] = hi;
+      longest = std::max(longest, hi - lo + 1);
+    }
+    dim3 g(grid_for(ctx, longest, 256), (unsigned)nr);
+    rfi_zero_ranges_kernel<<<g, 256, 0, ctx->stream>>>(x, br);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// dedisperse
+// ------------------------------------------------------------------------------------
+extern "C" int srtb_b200_dedisperse(srtb_b200_ctx* ctx, void* d_x, size_t count, float f_min, float f_c,
+                                    float df, float dm) {
+  if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "dedisperse: null argument");
+  if (count == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  constexpr double D = 4.148808e3;  // coherent_dedispersion.hpp:67
+  const double ddm = (D * 1e6) * (double)dm;
+  dedisperse_kernel<<<grid_for(ctx, count / 2 + 1, 256, 16), 256, 0, ctx->stream>>>(
+      static_cast<float2*>(d_x), count, (double)f_min, (double)df, (double)f_c, ddm);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" size_t srtb_b200_nsamps_reserved(size_t baseband_input_count, size_t spectrum_channel_count,
+                                            float freq_low, float bandwidth, float sample_rate, float dm,
+                                            int reserve_sample) {
+  if (!reserve_sample) return 0;
+  constexpr double D = 4.148808e3;
+  const float f = freq_low + bandwidth, f_c = freq_low;
+  const float delay = static_cast<float>(-D * (double)dm * (1.0 / (double)(f * f) - 1.0 / (double)(f_c * f_c)));
+  const float minimal_f = 2 * std::round(delay * sample_rate);
+  const size_t minimal = static_cast<size_t>(minimal_f < 0 ? 0.0f : minimal_f);
+  const size_t per_bin = spectrum_channel_count * 2;
+  const long long keep = static_cast<long long>(baseband_input_count - minimal) / (long long)per_bin * (long long)per_bin;
+  if (keep > 0) return baseband_input_count - (size_t)keep;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// RFI stage 2 (spectral kurtosis)
+// ------------------------------------------------------------------------------------
+extern "C" int srtb_b200_rfi_s2_sk(srtb_b200_ctx* ctx, void* d_x, size_t time_count, size_t chan_count,
+                                   float sk_threshold, float* d_sk_out) {
+  if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s2: null argument");
+  if (time_count == 0 || chan_count == 0) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s2: zero size");
+  CK(cudaSetDevice(ctx->device));
+  const float M_ = static_cast<float>(time_count);
+  float hi = sk_threshold, lo = 2 - sk_threshold;
+  if (lo > hi) std::swap(lo, hi);
+  const float lo_ = lo * ((M_ - 1) / (M_ + 1)) + 1, hi_ = hi * ((M_ - 1) / (M_ + 1)) + 1;
+  sk_kernel<<<(unsigned)chan_count, 256, 0, ctx->stream>>>(static_cast<float2*>(d_x), time_count, lo_, hi_, d_sk_out);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// signal detect
+// ------------------------------------------------------------------------------------
+static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t time_count,
+                          size_t chan_count, size_t time_reserved_count, float snr, float chan_thr,
+                          size_t max_boxcar) {
+  const size_t ts_count = (time_count <= time_reserved_count) ? time_count : time_count - time_reserved_count;
+  // buffers
+  const size_t series_need = (size_t)SRTB_B200_MAX_BOXCARS * time_count;
+  if (ctx->series_elems < series_need) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& p : ctx->series) {
+      if (p) CK(cudaFree(p));
+      p = nullptr;
+    }
+    ctx->series_elems = 0;
+  }
+  if (!ctx->series[slot]) {
+    cudaError_t e = cudaMalloc(&ctx->series[slot], series_need * sizeof(float));
+    if (e != cudaSuccess) return fail(ctx, SRTB_B200_E_NOMEM, "detect: series alloc failed");
+    ctx->series_elems = series_need;
+  }
+  {
+    size_t have = ctx->acc_elems * sizeof(float);
+    if (int rc = ensure(ctx, reinterpret_cast<void**>(&ctx->acc), &have, time_count * sizeof(float))) return rc;
+    ctx->acc_elems = have / sizeof(float);
+  }
+  const size_t ctas_per_chunk = (ts_count + 511) / 512;
+  size_t chunks = std::max<size_t>(1, (size_t)ctx->sm_count * 8 / ctas_per_chunk);
+  chunks = std::min(chunks, std::min<size_t>(128, chan_count));
+  const size_t rows_per_chunk = (chan_count + chunks - 1) / chunks;
+  chunks = (chan_count + rows_per_chunk - 1) / rows_per_chunk;
+  {
+    size_t have = ctx->colsum_partial_elems * sizeof(float);
+    if (int rc = ensure(ctx, reinterpret_cast<void**>(&ctx->colsum_partial), &have, chunks * ts_count * sizeof(float)))
+      return rc;
+    ctx->colsum_partial_elems = have / sizeof(float);
+  }
+  dim3 g((unsigned)ctas_per_chunk, (unsigned)chunks);
+  colsum_partial_kernel<<<g, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, ctx->colsum_partial);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  colsum_final_kernel<<<grid_for(ctx, ts_count, 256), 256, 0, ctx->stream>>>(
+      ctx->colsum_partial, ts_count, chunks, ctx->series[slot], x, time_count, chan_count, ctx->d_res + slot);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  detect_tail_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->series[slot], time_count, ctx->acc, ts_count, chan_count, snr,
+                                                  chan_thr, max_boxcar, ctx->d_res + slot);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  ctx->slot_time_count[slot] = time_count;
+  return 0;
+}
+
+static int detect_collect(srtb_b200_ctx* ctx, int slot, srtb_b200_detect_result* h_result, float* h_series,
+                          int copy_all) {
+  static_assert(sizeof(detect_dev_result) == sizeof(srtb_b200_detect_result), "result layout");
+  std::memcpy(h_result, ctx->h_res + slot, sizeof(srtb_b200_detect_result));
+  if (h_series && h_result->detect_enabled) {
+    const size_t stride = ctx->slot_time_count[slot];
+    bool any = false;
+    for (int b = 0; b < h_result->n_boxcars; b++) {
+      if (copy_all || h_result->signal_count[b] > 0) {
+        CK(cudaMemcpyAsync(h_series + (size_t)b * stride, ctx->series[slot] + (size_t)b * stride,
+                           h_result->series_length[b] * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        any = true;
+      }
+    }
+    if (any) CK(cudaStreamSynchronize(ctx->stream));
+  } else if (h_series && copy_all) {
+    // detection disabled: still hand back the mean-removed time series
+    CK(cudaMemcpyAsync(h_series, ctx->series[slot], h_result->time_series_count * sizeof(float),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+extern "C" int srtb_b200_signal_detect(srtb_b200_ctx* ctx, const void* d_x, size_t time_count,
+                                       size_t chan_count, size_t time_reserved_count, float snr_threshold,
+                                       float channel_threshold, size_t max_boxcar_length,
+                                       srtb_b200_detect_result* h_result, float* h_series, int copy_all) {
+  if (!ctx || !d_x || !h_result) return fail(ctx, SRTB_B200_E_INVALID, "signal_detect: null argument");
+  if (time_count == 0 || chan_count == 0) return fail(ctx, SRTB_B200_E_INVALID, "signal_detect: zero size");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = detect_enqueue(ctx, 0, static_cast<const float2*>(d_x), time_count, chan_count,
+                              time_reserved_count, snr_threshold, channel_threshold, max_boxcar_length))
+    return rc;
+  CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(detect_dev_result), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return detect_collect(ctx, 0, h_result, h_series, copy_all);
+}
+
+// ------------------------------------------------------------------------------------
+// whole block
+// ------------------------------------------------------------------------------------
+static int format_streams(int format) {
+  switch (format) {
+    case SRTB_B200_FORMAT_SIMPLE: return 1;
+    case SRTB_B200_FORMAT_INTERLEAVED_2:
+    case SRTB_B200_FORMAT_NAOCPSR_SNAP1:
+    case SRTB_B200_FORMAT_GZNUPSR_A1_2: return 2;
+    case SRTB_B200_FORMAT_GZNUPSR_A1_4: return 4;
+    default: return 0;
+  }
+}
+
+extern "C" int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                                              const void* d_baseband, size_t baseband_bytes,
+                                              srtb_b200_detect_result* h_results, float* h_series,
+                                              int copy_all) {
+  if (!ctx || !cfg || !d_baseband || !h_results) return fail(ctx, SRTB_B200_E_INVALID, "process_block: null argument");
+  const int streams = format_streams(cfg->baseband_format);
+  if (!streams) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "process_block: unknown format");
+  const size_t N = cfg->baseband_input_count;
+  if (N < 2 || !is_pow2(N)) return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(N));
+  CK(cudaSetDevice(ctx->device));
+  if (ctx->stream_buf_elems < N + 2) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& p : ctx->stream_buf) {
+      if (p) CK(cudaFree(p));
+      p = nullptr;
+    }
+    ctx->stream_buf_elems = 0;
+  }
+  for (int s = 0; s < streams; s++)
+    if (!ctx->stream_buf[s]) {
+      cudaError_t e = cudaMalloc(&ctx->stream_buf[s], (N + 2) * sizeof(float));
+      if (e != cudaSuccess) return fail(ctx, SRTB_B200_E_NOMEM, "process_block: stream buffer alloc failed");
+    }
+  ctx->stream_buf_elems = N + 2;
+  if (int rc = srtb_b200_unpack(ctx, d_baseband, baseband_bytes, cfg->baseband_input_bits, cfg->baseband_format,
+                                cfg->window, ctx->stream_buf, N))
+    return rc;
+  const size_t Nc = N / 2;
+  const size_t batch = std::min<size_t>(cfg->spectrum_channel_count, Nc);  // fft_pipe.hpp:318-320
+  if (batch == 0 || !is_pow2(batch)) return fail(ctx, SRTB_B200_E_SIZE, "spectrum_channel_count must be a power of 2");
+  const size_t L = Nc / batch;
+  // manual zap ranges -> bins (host, rfi_mitigation.hpp:102-143)
+  std::vector<size_t> bins;
+  for (uint64_t r = 0; r < cfg->n_rfi_freq_pairs; r++) {
+    size_t lo, hi;
+    if (srtb_b200_rfi_range_to_bins(cfg->rfi_freq_pairs[2 * r], cfg->rfi_freq_pairs[2 * r + 1],
+                                    cfg->baseband_freq_low, cfg->baseband_bandwidth, Nc, &lo, &hi)) {
+      bins.push_back(lo);
+      bins.push_back(hi);
+    }
+  }
+  const float coef = srtb_b200_norm_coefficient(Nc, cfg->spectrum_channel_count);
+  const float df = cfg->baseband_bandwidth / static_cast<float>(Nc);  // dedisperse_pipe.hpp:34
+  const float f_min = cfg->baseband_freq_low, f_c = f_min + cfg->baseband_bandwidth;
+  const size_t reserved = srtb_b200_nsamps_reserved(N, cfg->spectrum_channel_count, cfg->baseband_freq_low,
+                                                    cfg->baseband_bandwidth, cfg->baseband_sample_rate, cfg->dm,
+                                                    cfg->baseband_reserve_sample) /
+                          batch;
+  for (int s = 0; s < streams; s++) {
+    float* buf = ctx->stream_buf[s];
+    if (int rc = srtb_b200_fft_r2c_inplace(ctx, buf, N)) return rc;
+    if (int rc = srtb_b200_rfi_s1(ctx, buf, Nc, cfg->mitigate_rfi_average_method_threshold, coef,
+                                  bins.empty() ? nullptr : bins.data(), bins.size() / 2, nullptr))
+      return rc;
+    if (int rc = srtb_b200_dedisperse(ctx, buf, Nc, f_min, f_c, df, cfg->dm)) return rc;
+    if (int rc = srtb_b200_watfft_c2c_backward(ctx, buf, L, batch)) return rc;
+    if (int rc = srtb_b200_rfi_s2_sk(ctx, buf, L, batch, cfg->mitigate_rfi_spectral_kurtosis_threshold, nullptr)) return rc;
+    if (int rc = detect_enqueue(ctx, s, reinterpret_cast<const float2*>(buf), L, batch, reserved,
+                                cfg->signal_detect_signal_noise_threshold, cfg->signal_detect_channel_threshold,
+                                cfg->signal_detect_max_boxcar_length))
+      return rc;
+  }
+  CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(detect_dev_result) * streams, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < streams; s++)
+    if (int rc = detect_collect(ctx, s, h_results + s, h_series ? h_series + (size_t)s * SRTB_B200_MAX_BOXCARS * L : nullptr, copy_all))
+      return rc;
+  return streams;
+}
+
+extern "C" int srtb_b200_process_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                                       const void* h_baseband, size_t baseband_bytes,
+                                       srtb_b200_detect_result* h_results, float* h_series, int copy_all) {
+  if (!ctx || !cfg || !h_baseband) return fail(ctx, SRTB_B200_E_INVALID, "process_block: null argument");
+  CK(cudaSetDevice(ctx->device));
+  if (int rc = ensure(ctx, &ctx->d_baseband, &ctx->d_baseband_bytes, baseband_bytes)) return rc;
+  CK(cudaMemcpyAsync(ctx->d_baseband, h_baseband, baseband_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return srtb_b200_process_block_device(ctx, cfg, ctx->d_baseband, baseband_bytes, h_results, h_series, copy_all);
+}
+
+extern "C" const void* srtb_b200_block_spectrum(const srtb_b200_ctx* ctx, int stream) {
+  if (!ctx || stream < 0 || stream >= 4) return nullptr;
+  return ctx->stream_buf[stream];
+}
