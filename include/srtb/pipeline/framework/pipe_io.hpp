@@ -1,0 +1,104 @@
+// srtb/pipeline/framework/pipe_io.hpp — in/out functors connecting pipes to work queues
+// (reference: userspace/include/srtb/pipeline/framework/pipe_io.hpp:28-152): blocking queue in/out
+// that poll every config.thread_query_work_wait_time ns, a try-once "loose" out, a tee, a container
+// splitter and dummies.
+#pragma once
+#include <chrono>
+#include <memory>
+#include <optional>
+#include <stop_token>
+#include <thread>
+#include <tuple>
+
+#include "srtb/config.hpp"
+#include "srtb/work.hpp"
+
+namespace srtb {
+namespace pipeline {
+
+template <typename QueuePtr>
+class queue_in_functor {
+  QueuePtr q_;
+  using Work = typename std::pointer_traits<QueuePtr>::element_type::work_type;
+
+ public:
+  explicit queue_in_functor(QueuePtr q) : q_{q} {}
+  std::optional<Work> operator()(std::stop_token st) {
+    Work w;
+    while (!q_->pop(w)) {
+      if (st.stop_requested()) return std::nullopt;
+      std::this_thread::sleep_for(std::chrono::nanoseconds(srtb::config.thread_query_work_wait_time));
+    }
+    return w;
+  }
+};
+
+template <typename QueuePtr>
+class queue_out_functor {
+  QueuePtr q_;
+  using Work = typename std::pointer_traits<QueuePtr>::element_type::work_type;
+
+ public:
+  explicit queue_out_functor(QueuePtr q) : q_{q} {}
+  void operator()(std::stop_token st, Work w) {
+    while (!q_->push(w)) {
+      if (st.stop_requested()) return;
+      std::this_thread::sleep_for(std::chrono::nanoseconds(srtb::config.thread_query_work_wait_time));
+    }
+  }
+};
+
+/** push once, drop the work if the queue is full (used for the display side branch) */
+template <typename QueuePtr>
+class loose_queue_out_functor {
+  QueuePtr q_;
+  using Work = typename std::pointer_traits<QueuePtr>::element_type::work_type;
+
+ public:
+  explicit loose_queue_out_functor(QueuePtr q) : q_{q} {}
+  void operator()(std::stop_token st, Work w) {
+    if (!st.stop_requested()) q_->push(w);
+  }
+};
+
+/** copy one work to several out functors */
+template <typename... OutFunctors>
+class multiple_out_functors_functor {
+ public:
+  std::tuple<OutFunctors...> out_functors;
+  explicit multiple_out_functors_functor(OutFunctors... f) : out_functors{f...} {}
+  template <typename Work>
+  void operator()(std::stop_token st, Work w) {
+    std::apply([&](auto&... f) { (f(st, w), ...); }, out_functors);
+  }
+};
+
+/** a pipe that returns a container of works (1 in, S out): forward each element */
+template <typename OutFunctor>
+class multiple_works_out_functor {
+ public:
+  OutFunctor out_functor;
+  explicit multiple_works_out_functor(OutFunctor f) : out_functor{f} {}
+  template <typename WorkContainer>
+  void operator()(std::stop_token st, WorkContainer works) {
+    for (auto&& w : works) {
+      if (st.stop_requested()) return;
+      out_functor(st, w);
+    }
+  }
+};
+
+template <typename T = srtb::work::dummy_work>
+class dummy_in_functor {
+ public:
+  std::optional<T> operator()(std::stop_token) { return T{}; }
+};
+
+template <typename T = srtb::work::dummy_work>
+class dummy_out_functor {
+ public:
+  void operator()(std::stop_token, T) {}
+};
+
+}  // namespace pipeline
+}  // namespace srtb

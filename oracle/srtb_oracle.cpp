@@ -701,6 +701,14 @@ int srtb_oracle_chain(const void* baseband, const srtb_oracle_chain_config* cfg,
   return 0;
 }
 
+void srtb_oracle_set_threads(int n) {
+#if defined(_OPENMP)
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int srtb_oracle_num_threads(void) {
 #if defined(_OPENMP)
   return omp_get_max_threads();

@@ -1,0 +1,160 @@
+// pipeline_main.cpp — the reference's main.cpp wiring (userspace/src/main.cpp:125-228) on the
+// re-hosted pipes: one thread per pipe, work queues between them, one cuda_queue per GPU:
+//   copy_to_device -> unpack -> fft_1d_r2c -> rfi_mitigation_s1 -> dedisperse -> watfft_1d_c2c
+//                  -> rfi_mitigation_s2 -> signal_detect_pipe_2 -> (sink: prints one JSON line per work)
+// Input: a raw baseband file (--input) cut into blocks of baseband_input_count samples per stream.
+// Used by tests/test_gpu_pipeline.py, which compares the printed results with the CPU oracle.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "srtb/config.hpp"
+#include "srtb/cuda_queue.hpp"
+#include "srtb/memory.hpp"
+#include "srtb/pipeline/copy_to_device_pipe.hpp"
+#include "srtb/pipeline/dedisperse_pipe.hpp"
+#include "srtb/pipeline/fft_pipe.hpp"
+#include "srtb/pipeline/framework/composite_pipe.hpp"
+#include "srtb/pipeline/framework/pipe.hpp"
+#include "srtb/pipeline/framework/pipe_io.hpp"
+#include "srtb/pipeline/rfi_mitigation_pipe.hpp"
+#include "srtb/pipeline/signal_detect_pipe.hpp"
+#include "srtb/pipeline/unpack_pipe.hpp"
+#include "srtb/work.hpp"
+
+namespace {
+
+struct sink_out_functor {
+  std::shared_ptr<std::atomic<int>> done;
+  std::string dump_prefix;
+  void operator()(std::stop_token, srtb::work::write_signal_work w) {
+    std::string line = "{\"stream\": " + std::to_string(w.data_stream_id) + ", \"block\": " +
+                       std::to_string(w.udp_packet_counter) + ", \"count\": " + std::to_string(w.count) +
+                       ", \"batch_size\": " + std::to_string(w.batch_size) + ", \"zero_count\": " +
+                       std::to_string(w.zero_count) + ", \"series\": [";
+    for (size_t i = 0; i < w.time_series.size(); i++) {
+      const auto& h = w.time_series[i];
+      double peak = 0;
+      for (size_t j = 0; j < h.time_series_length; j++) peak = std::max<double>(peak, h.h_time_series.get()[j]);
+      line += std::string(i ? ", " : "") + "{\"boxcar\": " + std::to_string(h.boxcar_length) + ", \"length\": " +
+              std::to_string(h.time_series_length) + ", \"count\": " + std::to_string(h.signal_count) +
+              ", \"peak\": " + std::to_string(peak) + "}";
+    }
+    line += "]}";
+    if (!dump_prefix.empty()) {  // dynamic spectrum [C][L] complex64, like the reference's .npy payload
+      std::vector<char> host(w.count * w.batch_size * sizeof(srtb::complex<srtb::real>));
+      srtb::cuda_check(cudaMemcpy(host.data(), w.ptr.get(), host.size(), cudaMemcpyDeviceToHost), "D2H spectrum");
+      std::ofstream f(dump_prefix + std::to_string(w.udp_packet_counter) + "." + std::to_string(w.data_stream_id) + ".bin",
+                      std::ios::binary);
+      f.write(host.data(), (std::streamsize)host.size());
+    }
+    std::cout << line << std::endl;
+    (*done)++;
+  }
+};
+
+const char* arg(int argc, char** argv, const char* name, const char* def) {
+  for (int i = 1; i + 1 < argc; i++)
+    if (!std::strcmp(argv[i], name)) return argv[i + 1];
+  return def;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+  using namespace srtb::pipeline;
+  auto& cfg = srtb::config;
+  cfg.baseband_input_count = size_t{1} << std::atoi(arg(argc, argv, "--log2n", "20"));
+  cfg.baseband_input_bits = std::atoi(arg(argc, argv, "--bits", "-8"));
+  cfg.baseband_format_type = arg(argc, argv, "--format", "simple");
+  cfg.baseband_freq_low = std::atof(arg(argc, argv, "--freq-low", "1000"));
+  cfg.baseband_bandwidth = std::atof(arg(argc, argv, "--bandwidth", "500"));
+  cfg.baseband_sample_rate = std::atof(arg(argc, argv, "--sample-rate", "1e9"));
+  cfg.baseband_reserve_sample = std::atoi(arg(argc, argv, "--reserve", "0")) != 0;
+  cfg.dm = std::atof(arg(argc, argv, "--dm", "0"));
+  cfg.spectrum_channel_count = std::strtoull(arg(argc, argv, "--channels", "256"), nullptr, 10);
+  cfg.mitigate_rfi_average_method_threshold = std::atof(arg(argc, argv, "--avg-thr", "10"));
+  cfg.mitigate_rfi_spectral_kurtosis_threshold = std::atof(arg(argc, argv, "--sk-thr", "1.1"));
+  cfg.mitigate_rfi_freq_list = arg(argc, argv, "--freq-list", "");
+  cfg.signal_detect_signal_noise_threshold = std::atof(arg(argc, argv, "--snr", "6"));
+  cfg.signal_detect_max_boxcar_length = std::strtoull(arg(argc, argv, "--max-boxcar", "64"), nullptr, 10);
+  const std::string input = arg(argc, argv, "--input", "");
+  const std::string dump = arg(argc, argv, "--dump-prefix", "");
+  const bool composite = std::atoi(arg(argc, argv, "--composite", "0")) != 0;
+  if (input.empty()) {
+    std::fprintf(stderr, "usage: pipeline_main --input <file> [--log2n 20 --bits -8 --format simple ...]\n");
+    return 2;
+  }
+  size_t streams = 1;
+  if (cfg.baseband_format_type == "naocpsr_snap1" || cfg.baseband_format_type == "interleaved_samples_2" ||
+      cfg.baseband_format_type == "gznupsr_a1")
+    streams = 2;
+  const size_t block_bytes =
+      cfg.baseband_input_count * static_cast<size_t>(std::abs(cfg.baseband_input_bits)) / 8 * streams;
+
+  srtb::cuda_queue q{std::atoi(arg(argc, argv, "--device", "0"))};
+
+  using namespace srtb::work;
+  auto copy_q = std::make_shared<srtb::work_queue<copy_to_device_work, false>>();
+  auto unpack_q = std::make_shared<srtb::work_queue<unpack_work, false>>();
+  auto r2c_q = std::make_shared<srtb::work_queue<fft_1d_r2c_work>>();
+  auto s1_q = std::make_shared<srtb::work_queue<rfi_mitigation_s1_work>>();
+  auto dd_q = std::make_shared<srtb::work_queue<dedisperse_work>>();
+  auto wat_q = std::make_shared<srtb::work_queue<watfft_1d_c2c_work>>();
+  auto s2_q = std::make_shared<srtb::work_queue<rfi_mitigation_s2_work>>();
+  auto det_q = std::make_shared<srtb::work_queue<signal_detect_work>>();
+  auto done = std::make_shared<std::atomic<int>>(0);
+  sink_out_functor sink{done, dump};
+
+  std::vector<std::jthread> threads;
+  threads.push_back(start_pipe<copy_to_device_pipe>(queue_in_functor{copy_q}, queue_out_functor{unpack_q}, q));
+  threads.push_back(start_unpack_pipe(cfg.baseband_format_type, queue_in_functor{unpack_q}, queue_out_functor{r2c_q}, q));
+  if (!composite) {
+    threads.push_back(start_pipe<fft_1d_r2c_pipe>(queue_in_functor{r2c_q}, queue_out_functor{s1_q}, q));
+    threads.push_back(start_pipe<rfi_mitigation_s1_pipe>(queue_in_functor{s1_q}, queue_out_functor{dd_q}, q));
+    threads.push_back(start_pipe<dedisperse_pipe>(queue_in_functor{dd_q}, queue_out_functor{wat_q}, q));
+    threads.push_back(start_pipe<watfft_1d_c2c_pipe>(queue_in_functor{wat_q}, queue_out_functor{s2_q}, q));
+    threads.push_back(start_pipe<rfi_mitigation_s2_pipe>(queue_in_functor{s2_q}, queue_out_functor{det_q}, q));
+    threads.push_back(start_pipe<signal_detect_pipe_2>(queue_in_functor{det_q}, sink, q));
+  } else {
+    // stream-ordered fast mode: the six device stages as one composite pipe on one thread, no
+    // per-stage host wait (all share q's stream; signal_detect synchronises once)
+    pipe_sync_mode = sync_mode::stream_ordered;
+    using chain = composite_pipe<fft_1d_r2c_pipe, rfi_mitigation_s1_pipe, dedisperse_pipe, watfft_1d_c2c_pipe,
+                                 rfi_mitigation_s2_pipe, signal_detect_pipe_2>;
+    threads.push_back(start_pipe<chain>(queue_in_functor{r2c_q}, sink, q));
+  }
+
+  // source: the reference's read_file_pipe in miniature (pinned host block, zero padded tail)
+  std::ifstream f(input, std::ios::binary);
+  if (!f) {
+    std::fprintf(stderr, "cannot open %s\n", input.c_str());
+    return 2;
+  }
+  int blocks = 0;
+  while (true) {
+    auto h = srtb::host_allocator.allocate_shared<std::byte>(block_bytes);
+    std::memset(h.get(), 0, block_bytes);
+    f.read(reinterpret_cast<char*>(h.get()), (std::streamsize)block_bytes);
+    if (f.gcount() <= 0) break;
+    copy_to_device_work w;
+    w.count = block_bytes;
+    w.udp_packet_counter = (uint64_t)blocks;
+    w.data_stream_id = 0;
+    w.baseband_data = {h, block_bytes};
+    copy_q->push(w);
+    blocks++;
+    if ((size_t)f.gcount() < block_bytes) break;
+  }
+  while (done->load() < blocks * (int)streams) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  for (auto& t : threads) t.request_stop();
+  threads.clear();
+  srtb::device_allocator.deallocate_all_free_ptrs();
+  srtb::host_allocator.deallocate_all_free_ptrs();
+  return 0;
+}

@@ -224,6 +224,9 @@ class Oracle:
         assert rc == 0
         return work, res, series, stage_s
 
+    def set_threads(self, n: int):
+        self.lib.srtb_oracle_set_threads(int(n))
+
     def num_threads(self):
         return int(self.lib.srtb_oracle_num_threads())
 

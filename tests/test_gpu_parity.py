@@ -1,0 +1,564 @@
+"""GPU parity tests: every stage of the path, through the C ABI (libsrtb_b200.so), against
+the CPU oracle and float64 truth on the same seeded inputs.
+
+Parity policy:
+  * unpack / indexing / layouts / zero_count / bin ranges: bit-exact;
+  * FFT / dedisperse / normalise values: rel-L2 <= 1e-5 vs float64 truth (the reference's own
+    FFT tolerance is clamp(eps*n/2, 1e-5, 0.05) per element, test-fft_wrappers.cpp:109-110);
+  * masks (s1 zap, SK zap) and detection counts: identical except for elements whose statistic
+    lies within a relative 1e-4 of the threshold.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import srtb_b200  # noqa: E402
+
+REL_L2 = 1e-5
+BORDER = 1e-4
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel_l2(a, b):
+    a = np.asarray(a).astype(np.complex128).ravel()
+    b = np.asarray(b).astype(np.complex128).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+# ----------------------------------------------------------------------------- unpack
+KAT = np.array([0b01100011, 0b10110110, 0b00001000, 0b10011101], np.uint8)
+KAT_EXPECTED = {
+    1: [0, 1, 1, 0, 0, 0, 1, 1, 1, 0, 1, 1, 0, 1, 1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1, 1, 1, 0, 1],
+    2: [1, 2, 0, 3, 2, 3, 1, 2, 0, 0, 2, 0, 2, 1, 3, 1],
+    4: [6, 3, 11, 6, 0, 8, 9, 13],
+    8: [99, 182, 8, 157],
+}
+
+
+@pytest.mark.parametrize("bits", [1, 2, 4, 8])
+def test_unpack_reference_kat(ctx, bits):
+    # userspace/tests/test-unpack.cpp:142-210, bytes {0x63,0xB6,0x08,0x9D}
+    d_in = dev(KAT)
+    n = 32 // bits
+    out = torch.zeros(n + 2, dtype=torch.float32, device="cuda")
+    ctx.unpack(d_in, 4, bits, srtb_b200.FORMAT_SIMPLE, 0, [out], n)
+    torch.cuda.synchronize()
+    assert out[:n].cpu().tolist() == [float(v) for v in KAT_EXPECTED[bits]]
+
+
+@pytest.mark.parametrize("bits", [1, 2, 4, 8, -8, 16, -16, 32, 64])
+@pytest.mark.parametrize("nbytes", [1 << 16, (1 << 12) + 24])
+def test_unpack_simple_bit_exact(ctx, oracle, bits, nbytes):
+    rng = np.random.default_rng(abs(bits) * 7 + nbytes)
+    if bits == 32:
+        raw = rng.standard_normal(nbytes // 4).astype(np.float32).view(np.uint8)
+    elif bits == 64:
+        raw = rng.standard_normal(nbytes // 8).astype(np.float64).view(np.uint8)
+    else:
+        raw = rng.integers(0, 256, nbytes, dtype=np.uint8)
+    n = nbytes * 8 // abs(bits)
+    expect = oracle.unpack(raw, n, bits)
+    out = torch.zeros(n + 2, dtype=torch.float32, device="cuda")
+    ctx.unpack(dev(raw), nbytes, bits, srtb_b200.FORMAT_SIMPLE, 0, [out], n)
+    torch.cuda.synchronize()
+    assert np.array_equal(out[:n].cpu().numpy(), expect)
+    assert out[n:].cpu().tolist() == [0.0, 0.0]  # the +2 pad is not touched
+
+
+def test_unpack_tail_and_unaligned(ctx, oracle):
+    rng = np.random.default_rng(5)
+    raw = rng.integers(0, 256, 1003, dtype=np.uint8)
+    # ragged length (n % 8 != 0)
+    out = torch.zeros(1003, dtype=torch.float32, device="cuda")
+    ctx.unpack(dev(raw), 1003, 8, 0, 0, [out], 1003)
+    assert np.array_equal(out.cpu().numpy(), oracle.unpack(raw, 1003, 8))
+    # input pointer off 16-byte alignment -> scalar path, same answer
+    d = dev(np.concatenate([np.zeros(3, np.uint8), raw]))
+    out2 = torch.zeros(1000, dtype=torch.float32, device="cuda")
+    ctx.unpack(d.data_ptr() + 3, 1000, -8, 0, 0, [out2], 1000)
+    assert np.array_equal(out2.cpu().numpy(), oracle.unpack(raw[:1000], 1000, -8))
+
+
+@pytest.mark.parametrize("window", [1, 2])
+def test_unpack_window(ctx, oracle, window):
+    # test-fft_window.cpp:98-121: window fused into unpack<1> of all-ones bytes
+    raw = np.full(2, 0xFF, np.uint8)
+    out = torch.zeros(16, dtype=torch.float32, device="cuda")
+    ctx.unpack(dev(raw), 2, 1, 0, window, [out], 16)
+    assert np.allclose(out.cpu().numpy(), oracle.unpack(raw, 16, 1, window), atol=1e-6)
+    rng = np.random.default_rng(2)
+    raw = rng.integers(0, 256, 4096, dtype=np.uint8)
+    out = torch.zeros(4096, dtype=torch.float32, device="cuda")
+    ctx.unpack(dev(raw), 4096, -8, 0, window, [out], 4096)
+    assert np.allclose(out.cpu().numpy(), oracle.unpack(raw, 4096, -8, window), rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.parametrize("bits", [8, -8, 16, -16, 32])
+def test_unpack_interleaved_2(ctx, oracle, bits):
+    rng = np.random.default_rng(11)
+    n = 4096 + 2
+    nbytes = 2 * n * abs(bits) // 8
+    raw = (rng.standard_normal(2 * n).astype(np.float32).view(np.uint8) if bits == 32
+           else rng.integers(0, 256, nbytes, dtype=np.uint8))
+    e1, e2 = oracle.unpack_interleaved_2(raw, n, bits)
+    o1 = torch.zeros(n, dtype=torch.float32, device="cuda")
+    o2 = torch.zeros(n, dtype=torch.float32, device="cuda")
+    ctx.unpack(dev(raw), nbytes, bits, srtb_b200.FORMAT_INTERLEAVED_2, 0, [o1, o2], n)
+    assert np.array_equal(o1.cpu().numpy(), e1) and np.array_equal(o2.cpu().numpy(), e2)
+
+
+def test_unpack_board_formats(ctx, oracle):
+    rng = np.random.default_rng(12)
+    n = 8192
+    raw = rng.integers(0, 256, 4 * n, dtype=np.uint8)
+    # naocpsr_snap1 "1 1 2 2"
+    e1, e2 = oracle.unpack_snap1(raw[:2 * n], n)
+    o = [torch.zeros(n, dtype=torch.float32, device="cuda") for _ in range(4)]
+    ctx.unpack(dev(raw[:2 * n]), 2 * n, -8, srtb_b200.FORMAT_NAOCPSR_SNAP1, 0, o[:2], n)
+    assert np.array_equal(o[0].cpu().numpy(), e1) and np.array_equal(o[1].cpu().numpy(), e2)
+    # gznupsr_a1 v2.1 (2 streams, no xor) and the 4-stream variant (xor 0x80 after promotion)
+    e = oracle.unpack_gznupsr_a1(raw[:2 * n], n, 2)
+    ctx.unpack(dev(raw[:2 * n]), 2 * n, 8, srtb_b200.FORMAT_GZNUPSR_A1_2, 0, o[:2], n)
+    assert all(np.array_equal(o[i].cpu().numpy(), e[i]) for i in range(2))
+    e = oracle.unpack_gznupsr_a1(raw, n, 4)
+    ctx.unpack(dev(raw), 4 * n, 8, srtb_b200.FORMAT_GZNUPSR_A1_4, 0, o, n)
+    assert all(np.array_equal(o[i].cpu().numpy(), e[i]) for i in range(4))
+
+
+def test_unpack_errors(ctx):
+    d = torch.zeros(64, dtype=torch.uint8, device="cuda")
+    out = torch.zeros(64, dtype=torch.float32, device="cuda")
+    with pytest.raises(srtb_b200.SrtbError) as e:
+        ctx.unpack(d, 64, 3, 0, 0, [out], 16)
+    assert e.value.code == -3 and "unsupported baseband_input_bits" in e.value.message
+    with pytest.raises(srtb_b200.SrtbError) as e:
+        ctx.unpack(d, 64, 8, 99, 0, [out], 16)
+    assert e.value.code == -3 and "Unknown format" in e.value.message
+    with pytest.raises(srtb_b200.SrtbError):
+        ctx.unpack(d, 4, 8, 0, 0, [out], 64)  # in_bytes too small
+
+
+# ----------------------------------------------------------------------------- FFT
+@pytest.mark.parametrize("k,batch", [(1, 5), (2, 7), (3, 300), (4, 33), (5, 9), (6, 64), (7, 3), (8, 16),
+                                     (9, 5), (10, 4), (11, 3), (12, 5), (13, 3), (14, 2), (16, 2), (20, 1),
+                                     (21, 1), (23, 1)])
+@pytest.mark.parametrize("direction", [1, -1])
+def test_fft_c2c_vs_float64(ctx, k, batch, direction):
+    rng = np.random.default_rng(k * 31 + batch)
+    n = 1 << k
+    x = (rng.uniform(-1, 1, (batch, n)) + 1j * rng.uniform(-1, 1, (batch, n))).astype(np.complex64)
+    d = dev(x)
+    ctx.fft_c2c(d, n, batch, direction)
+    torch.cuda.synchronize()
+    got = d.cpu().numpy()
+    x64 = x.astype(np.complex128)
+    truth = np.fft.fft(x64, axis=1) if direction == 1 else np.fft.ifft(x64, axis=1) * n
+    err = rel_l2(got, truth)
+    assert err < REL_L2, f"n=2^{k} batch={batch} dir={direction}: rel-L2 {err:.3e}"
+    # per-element bound of the reference's own FFT test (test-fft_wrappers.cpp:109-110)
+    tol = float(np.clip(np.finfo(np.float32).eps * n / 2, 1e-5, 0.05))
+    assert np.abs(got - truth).max() / np.abs(truth).max() < tol
+
+
+def test_fft_c2c_matches_oracle_small(ctx, oracle):
+    rng = np.random.default_rng(99)
+    x = (rng.uniform(-1, 1, 1024) + 1j * rng.uniform(-1, 1, 1024)).astype(np.complex64)
+    for direction in (1, -1):
+        d = dev(x)
+        ctx.fft_c2c(d, 1024, 1, direction)
+        assert rel_l2(d.cpu().numpy(), oracle.fft_c2c(x, direction)) < REL_L2
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 12, 13, 14, 17, 21, 22, 24])
+def test_fft_r2c_inplace_vs_float64(ctx, k):
+    # input of test-fft_wrappers.cpp:127-131: uniform [-1, 1]
+    rng = np.random.default_rng(233 + k)
+    n = 1 << k
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    buf = torch.zeros(n + 2, dtype=torch.float32, device="cuda")
+    buf[:n] = dev(x)
+    ctx.fft_r2c_inplace(buf, n)
+    torch.cuda.synchronize()
+    got = buf.cpu().numpy().view(np.complex64)
+    truth = np.fft.rfft(x.astype(np.float64))
+    assert got.size == n // 2 + 1
+    err = rel_l2(got, truth)
+    assert err < REL_L2, f"N=2^{k}: rel-L2 {err:.3e}"
+
+
+def test_fft_r2c_matches_oracle(ctx, oracle):
+    rng = np.random.default_rng(4)
+    n = 1 << 12
+    x = rng.integers(-128, 128, n).astype(np.float32)
+    buf = torch.zeros(n + 2, dtype=torch.float32, device="cuda")
+    buf[:n] = dev(x)
+    ctx.fft_r2c_inplace(buf, n)
+    assert rel_l2(buf.cpu().numpy().view(np.complex64), oracle.fft_r2c(x)) < REL_L2
+
+
+def test_fft_size_errors(ctx):
+    d = torch.zeros(4096, dtype=torch.complex64, device="cuda")
+    with pytest.raises(srtb_b200.SrtbError) as e:
+        ctx.fft_c2c(d, 1000, 1, 1)
+    assert e.value.code == -2 and "power of 2" in e.value.message  # naive_fft_wrapper.hpp:52-56
+    with pytest.raises(srtb_b200.SrtbError):
+        ctx.fft_r2c_inplace(d, 3000)
+    with pytest.raises(srtb_b200.SrtbError):
+        ctx.fft_c2c(d, 1024, 1, 0)
+
+
+def test_fft_linearity_and_roundtrip_full_size(ctx):
+    # size-independent properties at BASELINE.json's full block size (2^24 real -> 2^23 complex)
+    n = 1 << 23
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(n, dtype=torch.complex64, device="cuda", generator=g)
+    b = torch.randn(n, dtype=torch.complex64, device="cuda", generator=g)
+    s = (a + 2 * b).clone()
+    fa, fb = a.clone(), b.clone()
+    ctx.fft_c2c(fa, n, 1, 1)
+    ctx.fft_c2c(fb, n, 1, 1)
+    ctx.fft_c2c(s, n, 1, 1)
+    lin = (s - (fa + 2 * fb)).abs().pow(2).sum().sqrt() / s.abs().pow(2).sum().sqrt()
+    assert float(lin) < 1e-6
+    ctx.fft_c2c(fa, n, 1, -1)       # forward then backward = n * identity
+    rt = (fa / n - a).abs().pow(2).sum().sqrt() / a.abs().pow(2).sum().sqrt()
+    assert float(rt) < 2e-6
+    # Parseval
+    e_t = float(b.abs().pow(2).double().sum())
+    e_f = float(fb.abs().pow(2).double().sum()) / n
+    assert abs(e_t - e_f) / e_t < 1e-5
+
+
+# ----------------------------------------------------------------------------- RFI stage 1
+def _spectrum(rng, nc, rfi_bins=()):
+    x = (rng.standard_normal(nc) + 1j * rng.standard_normal(nc)).astype(np.complex64) * 100
+    for b in rfi_bins:
+        x[b] *= 30
+    return x
+
+
+@pytest.mark.parametrize("nc", [1 << 10, (1 << 16) + 1, 1 << 20])
+def test_rfi_s1_vs_oracle(ctx, oracle, nc):
+    rng = np.random.default_rng(nc)
+    rfi = rng.integers(0, nc, 20)
+    x = _spectrum(rng, nc, rfi)
+    thr, C_ = 1.5, 1 << 4
+    coef = srtb_b200.norm_coefficient(nc, C_)
+    assert coef == oracle.norm_coefficient(nc, C_)
+    ey, emean, emask = oracle.rfi_s1_average(x, thr, C_)
+    d = dev(x)
+    dmean = torch.zeros(1, dtype=torch.float32, device="cuda")
+    ctx.rfi_s1(d, nc, thr, coef, [], dmean)
+    torch.cuda.synchronize()
+    mean = float(dmean.cpu()[0])
+    truth_mean = float(np.mean(np.abs(x.astype(np.complex128)) ** 2))
+    assert abs(mean - truth_mean) / truth_mean < 1e-6
+    assert abs(emean - truth_mean) / truth_mean < 1e-5
+    got = d.cpu().numpy()
+    p = np.abs(x.astype(np.complex128)) ** 2
+    border = np.abs(p / (thr * truth_mean) - 1) < BORDER
+    gmask = (got == 0) & (x != 0)
+    assert np.array_equal(gmask[~border], emask[~border].astype(bool)), "zap mask differs off the border"
+    keep = ~gmask & ~emask.astype(bool)
+    assert rel_l2(got[keep], ey[keep]) < 1e-6
+    assert int(emask.sum()) >= 15  # the injected RFI was zapped
+
+
+def test_rfi_s1_manual_ranges(ctx, oracle):
+    # test-rfi_mitigation.cpp:21-71 through the GPU path
+    n = 1500
+    ranges = srtb_b200.eval_rfi_ranges("11-12, 15-90, 233-235, 1176-1177")
+    assert ranges == oracle.eval_rfi_ranges("11-12, 15-90, 233-235, 1176-1177")
+    bins = [srtb_b200.rfi_range_to_bins(a, b, 0.0, float(n - 1), n) for a, b in ranges]
+    assert bins == [(11, 12), (15, 90), (233, 235), (1176, 1177)]
+    x = np.ones(n, np.complex64)
+    d = dev(x)
+    ctx.rfi_s1(d, n, 1e9, 1.0, bins)        # threshold high, coef 1: only the manual zap acts
+    expected = oracle.rfi_manual(x, 0.0, float(n - 1), ranges)
+    assert np.array_equal(d.cpu().numpy(), expected)
+    # inverted band (J1644 cfg) + out-of-band ranges agree with the oracle
+    for args in [(1418.0, 1422.0, 1437.0, -64.0, 1 << 12), (100.0, 200.0, 1000.0, 500.0, 4096),
+                 (1400.0, 1600.0, 1000.0, 500.0, 4096), (1422.0, 1418.0, 1437.0, -64.0, 1 << 20)]:
+        assert srtb_b200.rfi_range_to_bins(*args) == oracle.rfi_range_to_bins(*args)
+    with pytest.raises(srtb_b200.SrtbError):
+        ctx.rfi_s1(d, n, 1.0, 1.0, [(10, 5000)])
+
+
+# ----------------------------------------------------------------------------- dedisperse
+@pytest.mark.parametrize("nc,f_low,bw,dm", [(1 << 14, 1000.0, 500.0, 56.778), ((1 << 16) + 1, 1000.0, 400.0, 562.05),
+                                            (1 << 18, 1437.0, -64.0, -478.80), (1 << 12, 1000.0, 500.0, 0.0)])
+def test_dedisperse_vs_oracle_and_truth(ctx, oracle, nc, f_low, bw, dm):
+    rng = np.random.default_rng(nc)
+    x = (rng.standard_normal(nc) + 1j * rng.standard_normal(nc)).astype(np.complex64)
+    f_min, f_c = np.float32(f_low), np.float32(np.float32(f_low) + np.float32(bw))
+    df = np.float32(np.float32(bw) / np.float32(nc))       # dedisperse_pipe.hpp:33-41, f32
+    d = dev(x)
+    ctx.dedisperse(d, nc, float(f_min), float(f_c), float(df), dm)
+    got = d.cpu().numpy()
+    expect = oracle.dedisperse(x, float(f_min), float(f_c), float(df), dm)
+    # truth in extended precision, from the same f32-rounded scalars
+    i = np.arange(nc, dtype=np.longdouble)
+    f = np.longdouble(f_min) + np.longdouble(df) * i
+    k = np.longdouble(4.148808e3) * 1e6 * np.longdouble(np.float32(dm)) / f * ((f - np.longdouble(f_c)) / np.longdouble(f_c)) ** 2
+    truth = x.astype(np.complex128) * np.exp(-2j * np.pi * (k - np.trunc(k)).astype(np.float64))
+    kmax = float(np.abs(k).max())
+    tol = max(REL_L2, 2 * np.pi * kmax * 2.3e-16 * 4)      # fp64 rounding of k scales with |k|
+    assert rel_l2(got, truth) < tol, (rel_l2(got, truth), tol)
+    assert rel_l2(expect, truth) < tol
+    assert rel_l2(got, expect) < 2 * tol
+
+
+# ----------------------------------------------------------------------------- waterfall FFT
+@pytest.mark.parametrize("C_,L", [(16, 64), (2048, 8), (8, 4096), (4, 1 << 14), (64, 1), (3, 2)])
+def test_watfft_layout(ctx, C_, L):
+    rng = np.random.default_rng(C_ + L)
+    x = (rng.standard_normal((C_, L)) + 1j * rng.standard_normal((C_, L))).astype(np.complex64)
+    d = dev(x)
+    ctx.watfft_c2c_backward(d, L, C_)
+    truth = np.fft.ifft(x.astype(np.complex128), axis=1) * L   # backward, unnormalised, rows = sub-bands
+    got = d.cpu().numpy()
+    if L == 1:
+        assert np.array_equal(got, x)
+    else:
+        assert rel_l2(got, truth) < REL_L2
+
+
+# ----------------------------------------------------------------------------- spectral kurtosis
+def test_rfi_s2_sk_vs_oracle(ctx, oracle):
+    rng = np.random.default_rng(21)
+    C_, L = 64, 2048
+    x = (rng.standard_normal((C_, L)) + 1j * rng.standard_normal((C_, L))).astype(np.complex64)
+    x[5, :] = (3 + 0j)                       # CW tone: sk -> 1, zapped
+    x[9, ::8] *= 9                           # impulsive: sk >> 2, zapped
+    x[11, :] = 0                             # already-zapped channel: sk = NaN, left alone (q5)
+    thr = 1.05
+    ey, esk, ezap = oracle.rfi_s2(x.reshape(-1), L, C_, thr)
+    d = dev(x.reshape(-1))
+    dsk = torch.zeros(C_, dtype=torch.float32, device="cuda")
+    ctx.rfi_s2_sk(d, L, C_, thr, dsk)
+    got = d.cpu().numpy().reshape(C_, L)
+    sk = dsk.cpu().numpy()
+    fin = np.isfinite(esk)
+    assert np.array_equal(np.isnan(sk), np.isnan(esk))
+    assert np.allclose(sk[fin], esk[fin], rtol=1e-5)
+    lo, hi = oracle.sk_thresholds(L, thr)
+    border = np.zeros(C_, bool)
+    border[fin] = (np.abs(esk[fin] / hi - 1) < BORDER) | (np.abs(esk[fin] / lo - 1) < BORDER)
+    gzap = np.all(got == 0, axis=1) & ~np.all(x == 0, axis=1)
+    assert np.array_equal(gzap[~border], ezap[~border].astype(bool))
+    assert ezap[5] == 1 and ezap[9] == 1 and ezap[11] == 0
+    same = gzap == ezap.astype(bool)
+    assert np.array_equal(got[same], ey.reshape(C_, L)[same])  # untouched rows are bit-identical
+
+
+# ----------------------------------------------------------------------------- signal detect
+def _dynspec(rng, C_, L, pulse_at=None, amp=10.0):
+    x = (rng.standard_normal((C_, L)) + 1j * rng.standard_normal((C_, L))).astype(np.complex64)
+    if pulse_at is not None:
+        x[:, pulse_at:pulse_at + 8] *= amp
+    return x
+
+
+def _compare_detect(res, eres, series, eseries, snr):
+    assert res.zero_count == eres.zero_count
+    assert res.time_series_count == eres.time_series_count
+    assert res.detect_enabled == eres.detect_enabled
+    assert res.n_boxcars == eres.n_boxcars
+    for b in range(res.n_boxcars):
+        assert res.boxcar_length[b] == eres.boxcar_length[b]
+        assert res.series_length[b] == eres.series_length[b]
+        n = int(res.series_length[b])
+        assert res.threshold[b] == pytest.approx(eres.threshold[b], rel=1e-4)
+        ev = eseries[b, :n].astype(np.float64)
+        scale = np.sqrt(np.mean(ev ** 2))
+        if series is not None:
+            assert np.abs(series[b, :n] - ev).max() < 2e-4 * max(scale, 1.0) * np.sqrt(res.boxcar_length[b])
+        borderline = int((np.abs(ev - eres.threshold[b]) < BORDER * max(eres.threshold[b], 1e-30) * 10).sum())
+        assert abs(int(res.signal_count[b]) - int(eres.signal_count[b])) <= borderline
+
+
+@pytest.mark.parametrize("C_,L,reserved,maxbox", [(16, 256, 0, 16), (64, 4096, 0, 256), (33, 1001, 100, 1024),
+                                                  (2048, 512, 0, 64)])
+def test_signal_detect_vs_oracle(ctx, oracle, C_, L, reserved, maxbox):
+    rng = np.random.default_rng(C_ * L)
+    x = _dynspec(rng, C_, L, pulse_at=L // 3)
+    x[1, :] = 0
+    snr, chan_thr = 6.0, 0.9
+    eres, eseries = oracle.signal_detect(x.reshape(-1), L, C_, reserved, snr, chan_thr, maxbox)
+    h_series = np.zeros((srtb_b200.MAX_BOXCARS, L), np.float32)
+    res = ctx.signal_detect(dev(x.reshape(-1)), L, C_, reserved, snr, chan_thr, maxbox, h_series, copy_all=True)
+    _compare_detect(res, eres, h_series, eseries, snr)
+    assert res.signal_count[0] > 0           # the injected pulse is found
+    # only positive series are copied when copy_all is off
+    h2 = np.zeros_like(h_series)
+    res2 = ctx.signal_detect(dev(x.reshape(-1)), L, C_, reserved, snr, chan_thr, maxbox, h2, copy_all=False)
+    for b in range(res2.n_boxcars):
+        if res2.signal_count[b] == 0:
+            assert not h2[b].any()
+        else:
+            assert np.array_equal(h2[b], h_series[b])
+
+
+def test_signal_detect_disabled_when_mostly_zapped(ctx, oracle):
+    rng = np.random.default_rng(8)
+    C_, L = 16, 256
+    x = _dynspec(rng, C_, L, pulse_at=50)
+    x[:15, :] = 0
+    res = ctx.signal_detect(dev(x.reshape(-1)), L, C_, 0, 6.0, 0.9, 16)
+    eres, _ = oracle.signal_detect(x.reshape(-1), L, C_, 0, 6.0, 0.9, 16)
+    assert res.zero_count == 15 == eres.zero_count
+    assert res.detect_enabled == 0 and res.n_boxcars == 0
+
+
+# ----------------------------------------------------------------------------- whole chain
+def make_block_config(n, bits, fmt, C_, dm, f_low=1000.0, bw=500.0, fs=1e9, avg_thr=10.0, sk_thr=1.1,
+                      snr=6.0, chan_thr=0.9, maxbox=64, pairs=()):
+    import ctypes as CT
+    cfg = srtb_b200.BlockConfig()
+    cfg.baseband_input_count = n
+    cfg.baseband_input_bits = bits
+    cfg.baseband_format = fmt
+    cfg.window = 0
+    cfg.baseband_reserve_sample = 0
+    cfg.baseband_freq_low, cfg.baseband_bandwidth, cfg.baseband_sample_rate, cfg.dm = f_low, bw, fs, dm
+    cfg.mitigate_rfi_average_method_threshold = avg_thr
+    cfg.mitigate_rfi_spectral_kurtosis_threshold = sk_thr
+    cfg.spectrum_channel_count = C_
+    cfg.signal_detect_signal_noise_threshold = snr
+    cfg.signal_detect_channel_threshold = chan_thr
+    cfg.signal_detect_max_boxcar_length = maxbox
+    flat = [v for p in pairs for v in p]
+    arr = (CT.c_float * max(1, len(flat)))(*flat)
+    cfg._keep = arr
+    cfg.rfi_freq_pairs = CT.cast(arr, CT.POINTER(CT.c_float))
+    cfg.n_rfi_freq_pairs = len(pairs)
+    return cfg
+
+
+def oracle_chain_config(cfg):
+    import ctypes as CT
+    import oracle_lib
+    oc = oracle_lib.ChainConfig()
+    oc.baseband_input_count = cfg.baseband_input_count
+    oc.baseband_input_bits = cfg.baseband_input_bits
+    oc.window = cfg.window
+    oc.baseband_freq_low, oc.baseband_bandwidth = cfg.baseband_freq_low, cfg.baseband_bandwidth
+    oc.baseband_sample_rate, oc.dm = cfg.baseband_sample_rate, cfg.dm
+    oc.baseband_reserve_sample = cfg.baseband_reserve_sample
+    oc.rfi_average_threshold = cfg.mitigate_rfi_average_method_threshold
+    oc.rfi_sk_threshold = cfg.mitigate_rfi_spectral_kurtosis_threshold
+    oc.spectrum_channel_count = cfg.spectrum_channel_count
+    oc.snr_threshold = cfg.signal_detect_signal_noise_threshold
+    oc.channel_threshold = cfg.signal_detect_channel_threshold
+    oc.max_boxcar_length = cfg.signal_detect_max_boxcar_length
+    oc.rfi_pairs = cfg.rfi_freq_pairs
+    oc.n_rfi_pairs = cfg.n_rfi_freq_pairs
+    return oc
+
+
+def synth_baseband(n, seed, tone=True, pulse=True):
+    """V2/V3-style synthetic voltage: noise sigma 20 + CW tone + a short burst"""
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(n) * 20
+    t = np.arange(n)
+    if tone:
+        v += 40 * np.cos(2 * np.pi * 0.237 / 2 * t)
+    if pulse:
+        v[n // 2:n // 2 + 64] += rng.standard_normal(64) * 120
+    return np.clip(np.round(v), -127, 127).astype(np.int8)
+
+
+@pytest.mark.parametrize("logn,C_,dm", [(16, 16, 0.0), (20, 256, 10.0)])
+def test_chain_vs_oracle(ctx, oracle, logn, C_, dm):
+    n = 1 << logn
+    bb = synth_baseband(n, seed=logn)
+    cfg = make_block_config(n, -8, srtb_b200.FORMAT_SIMPLE, C_, dm, avg_thr=5.0, sk_thr=1.3, snr=6.0,
+                            pairs=[(1200.0, 1201.0)])
+    work, eres, eseries, _ = oracle.chain(bb.view(np.uint8), oracle_chain_config(cfg))
+    L = n // 2 // C_
+    h_series = np.zeros((srtb_b200.MAX_BOXCARS, L), np.float32)
+    pinned = torch.from_numpy(bb.view(np.uint8).copy()).pin_memory()
+    res = ctx.process_block(cfg, pinned, n, h_series, copy_all=True)
+    assert len(res) == 1
+    torch.cuda.synchronize()
+    src = ctx.block_spectrum_ptr(0)
+    got = _from_device_ptr(src, n // 2)
+    espec = work[:n].view(np.complex64)
+    ezap = np.all(espec.reshape(C_, L) == 0, axis=1)
+    gspec = got.reshape(C_, L)
+    gzap = np.all(gspec == 0, axis=1)
+    assert (gzap != ezap).sum() <= 1, "SK zap decisions differ on more than a borderline channel"
+    same = gzap == ezap
+    assert rel_l2(gspec[same], espec.reshape(C_, L)[same]) < 5 * REL_L2
+    if np.array_equal(gzap, ezap):
+        _compare_detect(res[0], eres, h_series, eseries, 6.0)
+    assert res[0].detect_enabled == 1
+    if dm == 0.0:   # an undispersed burst stays sharp only when no chirp is applied
+        assert sum(res[0].signal_count[b] for b in range(res[0].n_boxcars)) > 0
+
+
+def _from_device_ptr(ptr, n_complex):
+    """copy n complex64 from a raw device pointer to numpy (test helper)"""
+    import ctypes as CT
+    out = np.empty(n_complex, np.complex64)
+    cudart = CT.CDLL("libcudart.so")
+    cudart.cudaMemcpy.argtypes = [CT.c_void_p, CT.c_void_p, CT.c_size_t, CT.c_int]
+    rc = cudart.cudaMemcpy(out.ctypes.data, ptr, out.nbytes, 2)
+    assert rc == 0
+    return out
+
+
+def test_chain_dual_pol_snap1(ctx, oracle):
+    # config #3 shape at reduced size: 2 streams, naocpsr_snap1 layout, DM 562.05, full RFI + detect
+    n = 1 << 18
+    a, b = synth_baseband(n, 1), synth_baseband(n, 2, tone=False)
+    raw = np.empty(2 * n, np.int8)
+    raw.reshape(-1, 4)[:, 0:2] = a.reshape(-1, 2)
+    raw.reshape(-1, 4)[:, 2:4] = b.reshape(-1, 2)
+    cfg = make_block_config(n, -8, srtb_b200.FORMAT_NAOCPSR_SNAP1, 64, 562.05, bw=400.0, fs=8e8,
+                            avg_thr=1.5 * 4, sk_thr=1.3, snr=8.0, maxbox=256)
+    res = ctx.process_block(cfg, torch.from_numpy(raw.view(np.uint8)).pin_memory(), 2 * n, None)
+    assert len(res) == 2
+    for s, bb in enumerate((a, b)):
+        cfg1 = make_block_config(n, -8, srtb_b200.FORMAT_SIMPLE, 64, 562.05, bw=400.0, fs=8e8,
+                                 avg_thr=1.5 * 4, sk_thr=1.3, snr=8.0, maxbox=256)
+        _, eres, eseries, _ = oracle.chain(bb.view(np.uint8), oracle_chain_config(cfg1))
+        assert res[s].zero_count == eres.zero_count or abs(int(res[s].zero_count) - int(eres.zero_count)) <= 1
+        assert res[s].n_boxcars == eres.n_boxcars
+        if res[s].zero_count == eres.zero_count:
+            _compare_detect(res[s], eres, None, eseries, 8.0)
+
+
+def test_chain_full_size_properties(ctx):
+    """BASELINE config #2 at full size (2^24 samples, 8-bit, C = 2^11): size-independent checks —
+    white noise of variance s^2 gives E|y|^2 = 2 s^2 per dynamic-spectrum sample (SURVEY §8 anchors),
+    SK ~ 2 so (almost) nothing is zapped and nothing is detected; a long weak burst (16 time bins,
+    +50% amplitude: too smooth for SK, obvious to the boxcars) is detected."""
+    n = 1 << 24
+    C_ = 1 << 11
+    L = n // 2 // C_
+    g = torch.Generator().manual_seed(3)
+    v = (torch.randn(n, generator=g) * 20)
+    cfg = make_block_config(n, -8, srtb_b200.FORMAT_SIMPLE, C_, 0.0, avg_thr=10.0, sk_thr=1.2, snr=8.0,
+                            maxbox=1024)
+    bb = v.round().clamp(-127, 127).to(torch.int8)
+    s2 = float(bb.float().var())
+    res = ctx.process_block(cfg, bb.view(torch.uint8).pin_memory(), n, None)
+    spec = _from_device_ptr(ctx.block_spectrum_ptr(0), n // 2).reshape(C_, L)
+    zapped = np.all(spec == 0, axis=1)
+    assert zapped.sum() <= C_ // 100 and res[0].zero_count == zapped.sum()
+    p = float(np.mean(np.abs(spec[~zapped].astype(np.complex128)) ** 2))
+    assert abs(p / (2 * s2) - 1) < 0.01
+    assert res[0].detect_enabled == 1 and res[0].n_boxcars == 11
+    assert list(res[0].boxcar_length[:11]) == [1 << i for i in range(11)]
+    assert sum(res[0].signal_count[b] for b in range(11)) == 0          # pure noise at 8 sigma
+    v[n // 2:n // 2 + 16 * 2 * C_] *= 1.5
+    bb = v.round().clamp(-127, 127).to(torch.int8)
+    res = ctx.process_block(cfg, bb.view(torch.uint8).pin_memory(), n, None)
+    assert res[0].zero_count <= C_ // 100
+    assert res[0].signal_count[4] > 0                                    # boxcar 16 sees it
