@@ -1,0 +1,110 @@
+"""The reference's main.cpp wiring on the re-hosted pipes (tests/cpp/pipeline_main.cpp): one thread per
+pipe + work queues (drop-in mode), and the same stages as one stream-ordered composite_pipe. Results
+are compared with the CPU oracle block by block."""
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "tests" / "cpp" / "pipeline_main"
+
+
+def _build():
+    subprocess.run(["make", "-C", str(BIN.parent), "pipeline_main"], check=True, capture_output=True)
+    assert BIN.exists(), "pipeline_main was not built (libsrtb_b200.so missing?)"
+
+
+def _block(n, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(n) * 20
+    v += 40 * np.cos(2 * np.pi * 0.1185 * np.arange(n))
+    v[n // 2:n // 2 + 256] += rng.standard_normal(256) * 110
+    return np.clip(np.round(v), -127, 127).astype(np.int8)
+
+
+def _oracle_cfg(n, C_, dm, freq_pairs):
+    import ctypes as CT
+    import oracle_lib
+    oc = oracle_lib.ChainConfig()
+    oc.baseband_input_count, oc.baseband_input_bits, oc.window = n, -8, 0
+    oc.baseband_freq_low, oc.baseband_bandwidth, oc.baseband_sample_rate, oc.dm = 1000.0, 500.0, 1e9, dm
+    oc.baseband_reserve_sample = 0
+    oc.rfi_average_threshold, oc.rfi_sk_threshold = 5.0, 1.3
+    oc.spectrum_channel_count = C_
+    oc.snr_threshold, oc.channel_threshold, oc.max_boxcar_length = 6.0, 0.9, 64
+    flat = [v for p in freq_pairs for v in p]
+    arr = (CT.c_float * max(1, len(flat)))(*flat)
+    oc._keep = arr
+    oc.rfi_pairs = CT.cast(arr, CT.POINTER(CT.c_float))
+    oc.n_rfi_pairs = len(freq_pairs)
+    return oc
+
+
+def _run(tmp_path, fmt, raw, logn, C_, dm, composite, freq_list="1200-1201"):
+    inp = tmp_path / f"bb_{fmt}_{composite}.bin"
+    raw.tofile(inp)
+    prefix = tmp_path / f"dump_{fmt}_{composite}_"
+    cmd = [str(BIN), "--input", str(inp), "--log2n", str(logn), "--bits", "-8", "--format", fmt, "--channels",
+           str(C_), "--dm", str(dm), "--avg-thr", "5", "--sk-thr", "1.3", "--snr", "6", "--max-boxcar", "64",
+           "--freq-list", freq_list, "--dump-prefix", str(prefix), "--composite", str(composite)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    works = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    return works, prefix
+
+
+def _check_work(w, prefix, bb, oracle, n, C_, dm):
+    work, eres, eseries, _ = oracle.chain(bb.view(np.uint8), _oracle_cfg(n, C_, dm, [(1200.0, 1201.0)]))
+    L = n // 2 // C_
+    assert w["count"] == L and w["batch_size"] == C_
+    spec = np.fromfile(f"{prefix}{w['block']}.{w['stream']}.bin", dtype=np.complex64).reshape(C_, L)
+    espec = work[:n].view(np.complex64).reshape(C_, L)
+    gz, ez = np.all(spec == 0, axis=1), np.all(espec == 0, axis=1)
+    assert (gz != ez).sum() <= 1
+    same = gz == ez
+    err = np.linalg.norm(spec[same].astype(np.complex128) - espec[same]) / np.linalg.norm(espec[same].astype(np.complex128))
+    assert err < 5e-5
+    if np.array_equal(gz, ez):
+        assert w["zero_count"] == eres.zero_count
+        got = {s["boxcar"]: s["count"] for s in w["series"]}
+        exp = {int(eres.boxcar_length[b]): int(eres.signal_count[b]) for b in range(eres.n_boxcars)
+               if eres.signal_count[b] > 0}
+        assert set(got) ^ set(exp) <= {b for b in set(got) | set(exp) if abs(got.get(b, 0) - exp.get(b, 0)) <= 1}
+        for b in set(got) & set(exp):
+            assert abs(got[b] - exp[b]) <= 1
+    return len(w["series"])
+
+
+@pytest.mark.parametrize("composite", [0, 1])
+def test_pipeline_simple_three_blocks(tmp_path, oracle, composite):
+    _build()
+    logn, C_, dm = 18, 64, 0.0
+    n = 1 << logn
+    blocks = [_block(n, s) for s in (1, 2, 3)]
+    works, prefix = _run(tmp_path, "simple", np.concatenate(blocks), logn, C_, dm, composite)
+    assert sorted(w["block"] for w in works) == [0, 1, 2]          # every block came out, once
+    detected = 0
+    for w in works:
+        assert w["stream"] == 0
+        detected += _check_work(w, prefix, blocks[w["block"]], oracle, n, C_, dm)
+    assert detected > 0                                             # the injected bursts were found
+
+
+def test_pipeline_dual_pol_fanout(tmp_path, oracle):
+    """naocpsr_snap1: one unpack work fans out into two fft works with data_stream_id 2*id + s
+    (unpack_pipe.hpp:249-258)"""
+    _build()
+    logn, C_, dm = 16, 16, 0.0
+    n = 1 << logn
+    a, b = _block(n, 11), _block(n, 12)
+    raw = np.empty(2 * n, np.int8)
+    raw.reshape(-1, 4)[:, 0:2] = a.reshape(-1, 2)
+    raw.reshape(-1, 4)[:, 2:4] = b.reshape(-1, 2)
+    works, prefix = _run(tmp_path, "naocpsr_snap1", raw, logn, C_, dm, 0)
+    assert sorted((w["block"], w["stream"]) for w in works) == [(0, 0), (0, 1)]
+    for w in works:
+        _check_work(w, prefix, (a, b)[w["stream"]], oracle, n, C_, dm)
