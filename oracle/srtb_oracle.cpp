@@ -17,8 +17,9 @@
 //                    FFT only against FFTW, tests/test-naive_fft.cpp:148-157)
 // and, when /root/reference is present, against the reference headers themselves
 // compiled through a host SYCL shim (oracle/ref_shim -> oracle/_ref/libsrtb_ref.so).
-// Stages the reference never tests (s1, SK, chirp values, waterfall layout, detect)
-// are pinned only by that shim build; see DESIGN.md "Oracle".
+// tests/test_oracle_vs_ref.py: bit-exact for unpack / window / FFT / chirp / s1 values / SK rows,
+// masks and counts identical off the threshold border). Stages the reference never tests
+// (s1, SK, chirp values, waterfall layout, detect) are pinned by that build; see DESIGN.md section 4.
 //
 // Build: make -C oracle   (g++ -O2 -fopenmp -ffp-contract=off: the reference is built
 // with -fno-fast-math and contraction only inside one expression,

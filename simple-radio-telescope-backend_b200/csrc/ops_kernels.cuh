@@ -25,8 +25,8 @@ __device__ __forceinline__ float window_value(int window, size_t i, float n_minu
 }
 
 // ------------------------------------------------------------------------------
-// K1 unpack "simple" (S/unpack.hpp:43-156,171-197): eight output samples per thread
-// per iteration (two float4 stores, 32 B contiguous per thread, 1 KiB per warp).
+// K1 unpack "simple" (S/unpack.hpp:43-156,171-197). unpack_src<> (8 samples at a time) serves
+// the de-interleaving kernels; unpack_quad<> (one float4) serves the simple kernel.
 // ------------------------------------------------------------------------------
 template <int BITS>
 struct unpack_src {};  // loads the bytes of 8 consecutive samples starting at sample 8*g
@@ -146,28 +146,77 @@ __device__ __forceinline__ float unpack_one(const void* in, size_t i) {
   return (float)static_cast<const double*>(in)[i];
 }
 
+// one float4 of output (samples 4q .. 4q+3) from the 4*|BITS| input bits it needs
+template <int BITS>
+__device__ __forceinline__ float4 unpack_quad(const void* __restrict__ in, size_t q) {
+  if (BITS == 1) {
+    const unsigned v = static_cast<const uint8_t*>(in)[q >> 1];
+    const unsigned nib = (q & 1) ? (v & 0xfu) : (v >> 4);
+    return make_float4((float)((nib >> 3) & 1u), (float)((nib >> 2) & 1u), (float)((nib >> 1) & 1u), (float)(nib & 1u));
+  } else if (BITS == 2) {
+    const unsigned v = static_cast<const uint8_t*>(in)[q];
+    return make_float4((float)(v >> 6), (float)((v >> 4) & 3u), (float)((v >> 2) & 3u), (float)(v & 3u));
+  } else if (BITS == 4) {
+    const unsigned v = static_cast<const uint16_t*>(in)[q];  // little endian: byte 0 first
+    return make_float4((float)((v >> 4) & 0xfu), (float)(v & 0xfu), (float)(v >> 12), (float)((v >> 8) & 0xfu));
+  } else if (BITS == 8) {
+    const unsigned v = static_cast<const uint32_t*>(in)[q];
+    return make_float4((float)(v & 0xffu), (float)((v >> 8) & 0xffu), (float)((v >> 16) & 0xffu), (float)(v >> 24));
+  } else if (BITS == -8) {
+    const unsigned v = static_cast<const uint32_t*>(in)[q];
+    return make_float4((float)(int)(int8_t)(v & 0xffu), (float)(int)(int8_t)((v >> 8) & 0xffu),
+                       (float)(int)(int8_t)((v >> 16) & 0xffu), (float)(int)(int8_t)(v >> 24));
+  } else if (BITS == 16) {
+    const uint2 v = static_cast<const uint2*>(in)[q];
+    return make_float4((float)(v.x & 0xffffu), (float)(v.x >> 16), (float)(v.y & 0xffffu), (float)(v.y >> 16));
+  } else if (BITS == -16) {
+    const uint2 v = static_cast<const uint2*>(in)[q];
+    return make_float4((float)(int)(int16_t)(v.x & 0xffffu), (float)(int)(int16_t)(v.x >> 16),
+                       (float)(int)(int16_t)(v.y & 0xffffu), (float)(int)(int16_t)(v.y >> 16));
+  } else if (BITS == 32) {
+    return static_cast<const float4*>(in)[q];
+  } else {
+    const double2 a = static_cast<const double2*>(in)[2 * q], b2 = static_cast<const double2*>(in)[2 * q + 1];
+    return make_float4((float)a.x, (float)a.y, (float)b2.x, (float)b2.y);
+  }
+}
+
+// K1: every warp-level access is contiguous (32 lanes x 16 B stores = 512 B; loads 32 x |BITS|/2 B);
+// four independent quads per thread per iteration keep 4 loads + 4 stores in flight.
 template <int BITS, bool WIN>
 __global__ void __launch_bounds__(256) unpack_simple_kernel(const void* __restrict__ in,
                                                             float* __restrict__ out, size_t n,
                                                             int window) {
-  const size_t groups = n / 8;
+  constexpr int K = 4;
+  const size_t quads = n / 4;
   const float nm1 = (float)(n - 1);
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
-    float o[8];
-    unpack_src<BITS>::get(in, g, o);
-    if (WIN) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * K;
+  float4* __restrict__ dst = reinterpret_cast<float4*>(out);
+  for (size_t q0 = (size_t)blockIdx.x * blockDim.x * K + threadIdx.x; q0 < quads; q0 += stride) {
+    float4 v[K];
 #pragma unroll
-      for (int i = 0; i < 8; i++) o[i] *= window_value(window, 8 * g + i, nm1);
+    for (int j = 0; j < K; j++) {
+      const size_t q = q0 + (size_t)j * blockDim.x;
+      if (q < quads) v[j] = unpack_quad<BITS>(in, q);
     }
-    float4* dst = reinterpret_cast<float4*>(out) + 2 * g;
-    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const size_t q = q0 + (size_t)j * blockDim.x;
+      if (q < quads) {
+        if (WIN) {
+          v[j].x *= window_value(window, 4 * q, nm1);
+          v[j].y *= window_value(window, 4 * q + 1, nm1);
+          v[j].z *= window_value(window, 4 * q + 2, nm1);
+          v[j].w *= window_value(window, 4 * q + 3, nm1);
+        }
+        dst[q] = v[j];
+      }
+    }
   }
-  // tail (n % 8 samples) by the first threads of block 0
+  // tail (n % 4 samples) by the first threads of block 0
   if (blockIdx.x == 0) {
-    const size_t i = groups * 8 + threadIdx.x;
-    if (threadIdx.x < 8 && i < n) {
+    const size_t i = quads * 4 + threadIdx.x;
+    if (threadIdx.x < 4 && i < n) {
       float v = unpack_one<BITS>(in, i);
       if (WIN) v *= window_value(window, i, nm1);
       out[i] = v;
@@ -372,7 +421,15 @@ __global__ void __launch_bounds__(256) power_sum_kernel(const float2* __restrict
   const size_t pairs = count / 2;
   float acc0 = 0.f, acc1 = 0.f;
   const float4* x4 = reinterpret_cast<const float4*>(x);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < pairs; i += 4 * stride) {   // four loads in flight per thread
+    const float4 a = x4[i], b = x4[i + stride], c = x4[i + 2 * stride], d = x4[i + 3 * stride];
+    acc0 += (a.x * a.x + a.y * a.y) + (b.x * b.x + b.y * b.y);
+    acc1 += (a.z * a.z + a.w * a.w) + (b.z * b.z + b.w * b.w);
+    acc0 += (c.x * c.x + c.y * c.y) + (d.x * d.x + d.y * d.y);
+    acc1 += (c.z * c.z + c.w * c.w) + (d.z * d.z + d.w * d.w);
+  }
+  for (; i < pairs; i += stride) {
     const float4 v = x4[i];
     acc0 += v.x * v.x + v.y * v.y;
     acc1 += v.z * v.z + v.w * v.w;
@@ -440,12 +497,13 @@ __global__ void __launch_bounds__(256) rfi_zero_ranges_kernel(float2* __restrict
 // f = f_min + df*i in fp64 (f32 inputs promoted), k = (D*1e6*dm)/f * ((f-f_c)/f_c)^2,
 // phi = -2 pi frac(k); the sincos is taken as sincospi(-2 frac) in fp32.
 // ------------------------------------------------------------------------------
-__device__ __forceinline__ float2 chirp_factor(double f_min, double df, double f_c, double ddm,
-                                               size_t i) {
-  const double f = f_min + df * (double)i;
-  const double delta_f = f - f_c;
-  const double q = delta_f / f_c;
-  const double k = ddm / f * (q * q);
+__device__ __forceinline__ float2 chirp_factor(double f_min, double df, double inv_fc, double f_c,
+                                               double ddm, unsigned i) {
+  // 1/f by __drcp_rn (correctly rounded) and (f - f_c) * (1/f_c): each differs from the reference's
+  // true divisions by <= 1 ulp of fp64, i.e. <= |k| * 2.2e-16 cycles of phase
+  const double f = fma(df, (double)i, f_min);
+  const double q = (f - f_c) * inv_fc;
+  const double k = (ddm * __drcp_rn(f)) * (q * q);
   const float frac = (float)(k - trunc(k));
   float s, c;
   sincospif(-2.0f * frac, &s, &c);
@@ -457,18 +515,19 @@ __global__ void __launch_bounds__(256) dedisperse_kernel(float2* __restrict__ x,
                                                          double ddm) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t pairs = count / 2;
+  const double inv_fc = 1.0 / f_c;
   float4* x4 = reinterpret_cast<float4*>(x);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
     float4 v = x4[i];
-    const float2 w0 = chirp_factor(f_min, df, f_c, ddm, 2 * i);
-    const float2 w1 = chirp_factor(f_min, df, f_c, ddm, 2 * i + 1);
+    const float2 w0 = chirp_factor(f_min, df, inv_fc, f_c, ddm, (unsigned)(2 * i));
+    const float2 w1 = chirp_factor(f_min, df, inv_fc, f_c, ddm, (unsigned)(2 * i + 1));
     const float4 o = make_float4(v.x * w0.x - v.y * w0.y, v.x * w0.y + v.y * w0.x,
                                  v.z * w1.x - v.w * w1.y, v.z * w1.y + v.w * w1.x);
     x4[i] = o;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && (count & 1)) {
     const float2 v = x[count - 1];
-    const float2 w = chirp_factor(f_min, df, f_c, ddm, count - 1);
+    const float2 w = chirp_factor(f_min, df, inv_fc, f_c, ddm, (unsigned)(count - 1));
     x[count - 1] = make_float2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
   }
 }
@@ -488,7 +547,18 @@ __global__ void __launch_bounds__(256) sk_kernel(float2* __restrict__ x, size_t 
   const float4* r4 = reinterpret_cast<const float4*>(row);
   const bool vec = ((((size_t)blockIdx.x * time_count) & 1) == 0);
   if (vec) {
-    for (size_t i = threadIdx.x; i < pairs; i += blockDim.x) {
+    size_t i = threadIdx.x;
+    const size_t bd = blockDim.x;
+    for (; i + 3 * bd < pairs; i += 4 * bd) {   // four loads in flight per thread
+      const float4 a = r4[i], b = r4[i + bd], c = r4[i + 2 * bd], d = r4[i + 3 * bd];
+      const float pa0 = a.x * a.x + a.y * a.y, pa1 = a.z * a.z + a.w * a.w;
+      const float pb0 = b.x * b.x + b.y * b.y, pb1 = b.z * b.z + b.w * b.w;
+      const float pc0 = c.x * c.x + c.y * c.y, pc1 = c.z * c.z + c.w * c.w;
+      const float pd0 = d.x * d.x + d.y * d.y, pd1 = d.z * d.z + d.w * d.w;
+      s2 += (pa0 + pa1) + (pb0 + pb1) + (pc0 + pc1) + (pd0 + pd1);
+      s4 += (pa0 * pa0 + pa1 * pa1) + (pb0 * pb0 + pb1 * pb1) + (pc0 * pc0 + pc1 * pc1) + (pd0 * pd0 + pd1 * pd1);
+    }
+    for (; i < pairs; i += bd) {
       const float4 v = r4[i];
       const float p0 = v.x * v.x + v.y * v.y, p1 = v.z * v.z + v.w * v.w;
       s2 += p0 + p1;
@@ -550,7 +620,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float2* __res
   const bool two = (j2 + 1 < ts_count);
   const bool vec = ((time_count & 1) == 0);
   if (vec && two) {
-#pragma unroll 4
+#pragma unroll 8
     for (size_t c = c0; c < c1; c++) {
       const float4 v = *reinterpret_cast<const float4*>(x + c * time_count + j2);
       a0 += v.x * v.x + v.y * v.y;
@@ -571,118 +641,146 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float2* __res
   if (two) p[1] = a1;
 }
 
-// K17 stage 2 + K16: ts[j] = sum over chunks (ascending), zero_count
+// K17 stage 2 + K16: ts[j] = sum over chunks (fixed order), zero_count.
+// CTA = 32 columns x 8 chunk groups: coalesced along time, tree over the groups in shared memory.
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial,
                                                            size_t ts_count, size_t chunks,
                                                            float* __restrict__ ts,
                                                            const float2* __restrict__ x,
                                                            size_t time_count, size_t chan_count,
                                                            detect_dev_result* __restrict__ res) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < ts_count; j += stride) {
-    float a = 0.f;
-    for (size_t c = 0; c < chunks; c++) a += partial[c * ts_count + j];
-    ts[j] = a;
+  __shared__ float sm[8][33];
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const size_t j = (size_t)blockIdx.x * 32 + lx;
+  float a = 0.f;
+  if (j < ts_count) {
+    const size_t per = (chunks + 7) / 8;
+    const size_t c0 = (size_t)ly * per, c1 = min(c0 + per, chunks);
+    for (size_t c = c0; c < c1; c++) a += partial[c * ts_count + j];
+  }
+  sm[ly][lx] = a;
+  __syncthreads();
+  if (ly == 0 && j < ts_count) {
+    float t = sm[0][lx];
+#pragma unroll
+    for (int g = 1; g < 8; g++) t += sm[g][lx];
+    ts[j] = t;
   }
   if (blockIdx.x == 0) {
-    __shared__ float sm[32];
+    __shared__ float smz[32];
     float z = 0.f;
     for (size_t c = threadIdx.x; c < chan_count; c += blockDim.x) {
       const float2 v = x[c * time_count];
       if (v.x * v.x + v.y * v.y == 0.f) z += 1.f;
     }
-    z = block_sum<float>(z, sm);
+    z = block_sum<float>(z, smz);
     if (threadIdx.x == 0) res->zero_count = (unsigned long long)z;
   }
 }
 
-// K18-K21 in one CTA: mean removal, count_signal, inclusive scan, boxcar ladder.
-// series layout: row b (stride row_stride) = series of entry b. acc = scan buffer.
-__global__ void __launch_bounds__(1024) detect_tail_kernel(float* __restrict__ series,
-                                                           size_t row_stride, float* __restrict__ acc,
+// K18 + K20 in one CTA: mean removal, inclusive scan (fp64 chunk offsets), result header.
+__global__ void __launch_bounds__(1024) detect_scan_kernel(float* __restrict__ ts, float* __restrict__ acc,
                                                            size_t ts_count, size_t chan_count,
-                                                           float snr, float chan_thr,
-                                                           size_t max_boxcar,
+                                                           float chan_thr, size_t max_boxcar,
                                                            detect_dev_result* __restrict__ res) {
   __shared__ double smd[32];
   __shared__ double chunk_off[1024];
-  __shared__ float s_thr;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  float* ts = series;
-  // mean removal (:324-334)
-  double a = 0.0;
-  for (size_t i = tid; i < ts_count; i += nt) a += (double)ts[i];
-  a = block_sum<double>(a, smd);
   __shared__ float s_mean;
-  if (tid == 0) s_mean = (float)a / (float)ts_count;
-  __syncthreads();
-  const float mean = s_mean;
-  for (size_t i = tid; i < ts_count; i += nt) ts[i] -= mean;
-  __syncthreads();
-  if (tid == 0) {
-    res->time_series_count = ts_count;
-    res->detect_enabled = ((float)res->zero_count < chan_thr * (float)chan_count) ? 1 : 0;
-    res->n_boxcars = 0;
-  }
-  __syncthreads();
-  if (!res->detect_enabled) return;
-
-  // inclusive scan of ts -> acc: per-thread contiguous chunk, chunk offsets in fp64
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // each thread owns a contiguous chunk: one pass for the mean, one for the scan
   const size_t per = (ts_count + nt - 1) / nt;
   const size_t lo = min((size_t)tid * per, ts_count), hi = min(lo + per, ts_count);
   double local = 0.0;
   for (size_t i = lo; i < hi; i++) local += (double)ts[i];
-  chunk_off[tid] = local;
+  const double total = block_sum<double>(local, smd);
+  if (tid == 0) s_mean = (float)total / (float)ts_count;   // map_average: sum / float(count)
   __syncthreads();
-  if (tid == 0) {
+  const float mean = s_mean;
+  // chunk sums of the mean-removed series
+  double lsum = 0.0;
+  for (size_t i = lo; i < hi; i++) {
+    const float v = ts[i] - mean;
+    ts[i] = v;
+    lsum += (double)v;
+  }
+  chunk_off[tid] = lsum;
+  __syncthreads();
+  // exclusive scan of the 1024 chunk sums by warp 0 (32 values per lane, then a shuffle scan)
+  if (tid < 32) {
     double run = 0.0;
-    for (int i = 0; i < nt; i++) {
-      const double t = chunk_off[i];
-      chunk_off[i] = run;
-      run += t;
+    const int per_lane = nt / 32;
+    for (int i = 0; i < per_lane; i++) run += chunk_off[tid * per_lane + i];
+    double incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += t;
+    }
+    double base = incl - run;
+    for (int i = 0; i < per_lane; i++) {
+      const double t = chunk_off[tid * per_lane + i];
+      chunk_off[tid * per_lane + i] = base;
+      base += t;
     }
   }
   __syncthreads();
-  {
-    double run = chunk_off[tid];
-    for (size_t i = lo; i < hi; i++) {
-      run += (double)ts[i];
-      acc[i] = (float)run;
-    }
+  double run = chunk_off[tid];
+  for (size_t i = lo; i < hi; i++) {
+    run += (double)ts[i];
+    acc[i] = (float)run;
   }
-  __syncthreads();
+  if (tid == 0) {
+    res->time_series_count = ts_count;
+    const int enabled = ((float)res->zero_count < chan_thr * (float)chan_count) ? 1 : 0;
+    res->detect_enabled = enabled;
+    int nb = 0;
+    if (enabled) {
+      nb = 1;
+      for (size_t b = 2; b <= max_boxcar && b < ts_count && nb < 32; b *= 2) nb++;
+    }
+    res->n_boxcars = nb;
+  }
+}
 
-  int nb = 0;
-  for (size_t b = 1; (b == 1) || (b <= max_boxcar && b < ts_count); b *= 2) {
-    if (nb >= 32) break;
-    float* v = series + (size_t)nb * row_stride;
-    const size_t n = (b == 1) ? ts_count : ts_count - b;
-    if (b > 1) {
-      for (size_t i = tid; i < n; i += nt) v[i] = acc[i + b] - acc[i];
-      __syncthreads();
-    }
-    double sq = 0.0;
+// K19 + K21: one CTA per boxcar length 2^blockIdx.x: series, variance, threshold, count.
+__global__ void __launch_bounds__(1024) detect_boxcar_kernel(float* __restrict__ series, size_t row_stride,
+                                                             const float* __restrict__ acc,
+                                                             size_t ts_count, float snr,
+                                                             detect_dev_result* __restrict__ res) {
+  __shared__ double smd[32];
+  __shared__ float s_thr;
+  const int nb = blockIdx.x;
+  if (nb >= res->n_boxcars) return;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const size_t b = (size_t)1 << nb;
+  float* v = series + (size_t)nb * row_stride;
+  const size_t n = (nb == 0) ? ts_count : ts_count - b;
+  double sq = 0.0;
+  if (nb == 0) {
     for (size_t i = tid; i < n; i += nt) sq += (double)v[i] * (double)v[i];
-    sq = block_sum<double>(sq, smd);
-    if (tid == 0) {
-      const float var = (float)sq / (float)n;
-      s_thr = snr * sqrtf(var);
-      res->variance[nb] = var;
-      res->threshold[nb] = s_thr;
-      res->boxcar_length[nb] = b;
-      res->series_length[nb] = n;
+  } else {
+    for (size_t i = tid; i < n; i += nt) {
+      const float d = acc[i + b] - acc[i];
+      v[i] = d;
+      sq += (double)d * (double)d;
     }
-    __syncthreads();
-    const float thr = s_thr;
-    double cnt = 0.0;
-    for (size_t i = tid; i < n; i += nt)
-      if (v[i] > thr) cnt += 1.0;
-    cnt = block_sum<double>(cnt, smd);
-    if (tid == 0) res->signal_count[nb] = (unsigned long long)cnt;
-    __syncthreads();
-    nb++;
   }
-  if (tid == 0) res->n_boxcars = nb;
+  sq = block_sum<double>(sq, smd);
+  if (tid == 0) {
+    const float var = (float)sq / (float)n;
+    s_thr = snr * sqrtf(var);
+    res->variance[nb] = var;
+    res->threshold[nb] = s_thr;
+    res->boxcar_length[nb] = b;
+    res->series_length[nb] = n;
+  }
+  __syncthreads();
+  const float thr = s_thr;
+  double cnt = 0.0;
+  for (size_t i = tid; i < n; i += nt)
+    if (v[i] > thr) cnt += 1.0;
+  cnt = block_sum<double>(cnt, smd);
+  if (tid == 0) res->signal_count[nb] = (unsigned long long)cnt;
 }
 
 }  // namespace srtb_b200

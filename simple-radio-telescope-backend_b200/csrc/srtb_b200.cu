@@ -184,9 +184,9 @@ static int launch_unpack_simple(srtb_b200_ctx* ctx, const void* d_in, float* out
   if (!aligned) {
     unpack_simple_scalar_kernel<BITS><<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(d_in, out, n, window);
   } else if (window == 0) {
-    unpack_simple_kernel<BITS, false><<<grid_for(ctx, n / 8 + 1, 256), 256, 0, ctx->stream>>>(d_in, out, n, window);
+    unpack_simple_kernel<BITS, false><<<grid_for(ctx, n / 16 + 1, 256), 256, 0, ctx->stream>>>(d_in, out, n, window);
   } else {
-    unpack_simple_kernel<BITS, true><<<grid_for(ctx, n / 8 + 1, 256), 256, 0, ctx->stream>>>(d_in, out, n, window);
+    unpack_simple_kernel<BITS, true><<<grid_for(ctx, n / 16 + 1, 256), 256, 0, ctx->stream>>>(d_in, out, n, window);
   }
   ctx->launches++;
   CK(cudaGetLastError());
@@ -682,12 +682,19 @@ static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t 
   colsum_partial_kernel<<<g, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, ctx->colsum_partial);
   ctx->launches++;
   CK(cudaGetLastError());
-  colsum_final_kernel<<<grid_for(ctx, ts_count, 256), 256, 0, ctx->stream>>>(
+  colsum_final_kernel<<<(unsigned)((ts_count + 31) / 32), 256, 0, ctx->stream>>>(
       ctx->colsum_partial, ts_count, chunks, ctx->series[slot], x, time_count, chan_count, ctx->d_res + slot);
   ctx->launches++;
   CK(cudaGetLastError());
-  detect_tail_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->series[slot], time_count, ctx->acc, ts_count, chan_count, snr,
-                                                  chan_thr, max_boxcar, ctx->d_res + slot);
+  detect_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->series[slot], ctx->acc, ts_count, chan_count, chan_thr,
+                                                  max_boxcar, ctx->d_res + slot);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  // one CTA per possible boxcar; CTAs beyond n_boxcars (known only on the device) exit at once
+  unsigned max_nb = 1;
+  for (size_t b = 2; b <= max_boxcar && b < ts_count && max_nb < SRTB_B200_MAX_BOXCARS; b *= 2) max_nb++;
+  detect_boxcar_kernel<<<max_nb, 1024, 0, ctx->stream>>>(ctx->series[slot], time_count, ctx->acc, ts_count, snr,
+                                                         ctx->d_res + slot);
   ctx->launches++;
   CK(cudaGetLastError());
   ctx->slot_time_count[slot] = time_count;

@@ -66,8 +66,11 @@ def _check_work(w, prefix, bb, oracle, n, C_, dm):
     gz, ez = np.all(spec == 0, axis=1), np.all(espec == 0, axis=1)
     assert (gz != ez).sum() <= 1
     same = gz == ez
-    err = np.linalg.norm(spec[same].astype(np.complex128) - espec[same]) / np.linalg.norm(espec[same].astype(np.complex128))
-    assert err < 5e-5
+    den = np.linalg.norm(espec[same].astype(np.complex128))
+    if den == 0:        # everything zapped in both
+        assert not spec[same].any()
+    else:
+        assert np.linalg.norm(spec[same].astype(np.complex128) - espec[same]) / den < 5e-5
     if np.array_equal(gz, ez):
         assert w["zero_count"] == eres.zero_count
         got = {s["boxcar"]: s["count"] for s in w["series"]}
