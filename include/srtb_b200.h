@@ -166,6 +166,15 @@ int srtb_b200_process_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cf
 int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
                                    const void* d_baseband, size_t baseband_bytes,
                                    srtb_b200_detect_result* h_results, float* h_series, int copy_all);
+/* pipelined ingest (the pinned-host ring of SURVEY section 8e): submit copies the block on a
+ * dedicated copy stream while the previous block computes and returns a ticket (>= 0);
+ * collect waits for that block and fills h_results[stream] (returns the stream count).
+ * Up to SRTB_B200_RING_SLOTS blocks may be in flight; h_baseband must stay valid (and should be
+ * pinned) until its block is collected. Time series are not returned on this path. */
+#define SRTB_B200_RING_SLOTS 3
+int srtb_b200_submit_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                           const void* h_baseband, size_t baseband_bytes);
+int srtb_b200_collect_block(srtb_b200_ctx* ctx, int ticket, srtb_b200_detect_result* h_results);
 /* device pointer of stream s's dynamic spectrum after process_block (valid until next call) */
 const void* srtb_b200_block_spectrum(const srtb_b200_ctx* ctx, int stream);
 

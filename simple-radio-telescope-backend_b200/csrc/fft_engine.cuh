@@ -94,7 +94,14 @@ struct sched {
 // slots as NB = 8/r butterflies: butterfly m uses slots m + i*NB (i < r) and is butterfly
 // number u + m*U of the L/r butterflies in the sequence. Twiddle (DIT) W_{Ns*r}^{k*i},
 // k = butterfly % Ns; outputs go to (b / Ns)*Ns*r + k + i*Ns.
-template <int LOGL, int LOGR, int LOGNS, bool FWD>
+// TABLE = true reads every power W^{k i} from the table (cheap when the lanes of a warp share k, i.e.
+// in the column-mode mappings); TABLE = false reads W^k and forms the powers by multiplication
+// (lanes run along k: one gather instead of seven).
+// TWSHIFT: table index of W_{Ns*R}^j is j << TWSHIFT (LOGL - LOGNS - LOGR for a length-L table, 0 for
+// a per-stage compact table). TWLDG: the table is in global memory (read through the read-only path)
+// rather than in shared memory.
+template <int LOGL, int LOGR, int LOGNS, bool FWD, bool TABLE = false, int TWSHIFT = LOGL - LOGNS - LOGR,
+          bool TWLDG = true>
 __device__ __forceinline__ void stage_compute(float2 (&v)[8], int u, const float2* __restrict__ tw,
                                               int (&oidx)[8]) {
   constexpr int L = 1 << LOGL, U = L / 8, R = 1 << LOGR, NB = 8 / R, NS = 1 << LOGNS;
@@ -104,9 +111,16 @@ __device__ __forceinline__ void stage_compute(float2 (&v)[8], int u, const float
     const int k = b & (NS - 1);
     if constexpr (LOGNS > 0) {
       // w1 = W_{Ns*R}^k from the length-L forward table; higher powers by multiplication
-      const float2 w1 = c_dir<FWD>(__ldg(&tw[k << (LOGL - LOGNS - LOGR)]));
+      constexpr int SH = (TWSHIFT < 0) ? 0 : TWSHIFT;
+      const float2 w1 = c_dir<FWD>(TWLDG ? __ldg(&tw[k << SH]) : tw[k << SH]);
       if (R == 2) {
         v[m + NB] = c_mul(v[m + NB], w1);
+      } else if (TABLE) {
+#pragma unroll
+        for (int i = 1; i < R; i++) {
+          const float2 wi = (i == 1) ? w1 : c_dir<FWD>(TWLDG ? __ldg(&tw[(k * i) << SH]) : tw[(k * i) << SH]);
+          v[m + i * NB] = c_mul(v[m + i * NB], wi);
+        }
       } else if (R == 4) {
         const float2 w2 = c_sqr(w1), w3 = c_mul(w2, w1);
         v[m + NB] = c_mul(v[m + NB], w1);
@@ -153,6 +167,8 @@ struct tile_layout {
 template <int LOGL, int T>
 struct pass_threads {
   static constexpr int value = ((1 << LOGL) / 8) * T;
+  // resident CTAs per SM the persistent TMA kernels aim for (register budget via __launch_bounds__)
+  static constexpr int min_blocks = (value >= 1024) ? 1 : ((value >= 512) ? 3 : ((value >= 256) ? 5 : 8));
 };
 
 // IO concept:
@@ -200,7 +216,7 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value)
 #pragma unroll
     for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u1 + e * U, t1)];
     __syncthreads();
-    stage_compute<LOGL, SC::logr(1), SC::logns(1), FWD>(v, u1, tw, oidx);
+    stage_compute<LOGL, SC::logr(1), SC::logns(1), FWD, MODE != MODE_ROW>(v, u1, tw, oidx);
 #pragma unroll
     for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t1)] = v[e];
     __syncthreads();
@@ -209,7 +225,7 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value)
 #pragma unroll
     for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u1 + e * U, t1)];
     __syncthreads();
-    stage_compute<LOGL, SC::logr(2), SC::logns(2), FWD>(v, u1, tw, oidx);
+    stage_compute<LOGL, SC::logr(2), SC::logns(2), FWD, MODE != MODE_ROW>(v, u1, tw, oidx);
 #pragma unroll
     for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t1)] = v[e];
     __syncthreads();
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value)
   // last stage
 #pragma unroll
   for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u1 + e * U, t1)];
-  stage_compute<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD>(v, u1, tw, oidx);
+  stage_compute<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD, MODE != MODE_ROW>(v, u1, tw, oidx);
   if (io.tile_valid(t1)) io.store8(t1, u1, U, v);
   }
 }
@@ -338,5 +354,382 @@ struct trans_io {
     for (int e = 0; e < 8; e++) o[(size_t)A * e * U] = v[e];
   }
 };
+
+
+// ---------------------------------------------------------------------------------
+// TMA (cp.async.bulk) + mbarrier helpers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a TMA that never completes (bad tensor map) traps after ~2 s instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ROW-mode transform as a persistent kernel: each CTA walks tiles of T contiguous rows; the next
+// tile's rows are fetched by ONE cp.async.bulk (TMA) into the other shared-memory buffer while the
+// current tile is transformed, so no thread ever waits on a global load in its critical path.
+// Buffers: raw layout [T][L] as it arrives, then the padded exchange layout in place.
+template <int LOGL, int T>
+struct row_tma_smem {
+  static constexpr int L = 1 << LOGL;
+  static constexpr int BUF = T * (L + (L >> 4));  // elements per buffer (padded layout is the larger)
+  // compact stage tables: stage s >= 1 needs W_{8^s * R}^k for k < 8^s  (8 + 64 + 512 entries at most)
+  static constexpr int TW = (LOGL > 9) ? 584 : ((LOGL > 6) ? 72 : ((LOGL > 3) ? 8 : 0));
+  static constexpr size_t bytes = 2 * (size_t)BUF * sizeof(float2) + 128 + (size_t)(TW + 8) * sizeof(float2);
+};
+
+template <int LOGL, int T, bool FWD>
+__global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOGL, T>::min_blocks)
+    fft_row_tma_kernel(const float2* __restrict__ in, float2* __restrict__ out, size_t nrows,
+                       const float2* __restrict__ tw) {
+  using SC = sched<LOGL>;
+  using LAY = tile_layout<LOGL, T, MODE_ROW>;
+  constexpr int L = 1 << LOGL, U = L / 8, S = SC::S, BUF = row_tma_smem<LOGL, T>::BUF;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  float2* const buf0 = reinterpret_cast<float2*>(smraw);
+  float2* const buf1 = buf0 + BUF;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  float2* const ctw = reinterpret_cast<float2*>(smraw + 2 * (size_t)BUF * sizeof(float2) + 128);
+  const int tid = threadIdx.x;
+  const int t = tid / U, u = tid % U;
+  const unsigned ntiles = (unsigned)((nrows + T - 1) / T);
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  // compact stage twiddles: table of stage s (>= 1) starts at offset (8^s - 8) / 7 and holds
+  // W_{Ns*R}^k = W_L^{k << (LOGL - 3s - logr(s))} for k < Ns = 8^s
+  for (int s = 1; s < S; s++) {
+    const int ns = 1 << (3 * s), off = (ns - 8) / 7, sh = LOGL - 3 * s - SC::logr(s);
+    for (int k = tid; k < ns; k += blockDim.x) ctw[off + k] = __ldg(&tw[k << sh]);
+  }
+  __syncthreads();
+  auto issue = [&](unsigned tl, int b) {  // one thread: fetch tile tl into buffer b
+    const size_t row0 = (size_t)tl * T;
+    const size_t rows = (nrows - row0 < (size_t)T) ? nrows - row0 : (size_t)T;
+    const uint32_t bytes = (uint32_t)(rows << LOGL) * (uint32_t)sizeof(float2);
+    fence_proxy_async();  // earlier generic-proxy accesses to this buffer are ordered before the async write
+    mbar_expect_tx(&mbar[b], bytes);
+    bulk_g2s(b ? buf1 : buf0, in + (row0 << LOGL), bytes, &mbar[b]);
+  };
+  unsigned tile = blockIdx.x;
+  if (tile < ntiles && tid == 0) issue(tile, 0);
+  for (unsigned it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int b = it & 1;
+    float2* const sm = b ? buf1 : buf0;
+    const unsigned nxt = tile + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue(nxt, b ^ 1);
+    mbar_wait(&mbar[b], (it >> 1) & 1);
+    const size_t row = (size_t)tile * T + t;
+    const bool valid = row < nrows;
+    float2 v[8];
+    int oidx[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = valid ? sm[t * L + u + e * U] : make_float2(0.f, 0.f);
+    stage_compute<LOGL, SC::logr(0), 0, FWD>(v, u, tw, oidx);
+    if constexpr (S == 1) {
+      if (valid) {
+        float2* o = out + (row << LOGL) + u;
+#pragma unroll
+        for (int e = 0; e < 8; e++) o[e * U] = v[e];
+      }
+      __syncthreads();  // buffer b may be refilled from the next iteration on
+    } else {
+      __syncthreads();  // every raw read done before the padded layout overwrites the buffer
+#pragma unroll
+      for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t)] = v[e];
+      __syncthreads();
+      if constexpr (S >= 3) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u + e * U, t)];
+        __syncthreads();
+        stage_compute<LOGL, SC::logr(1), SC::logns(1), FWD, false, 0, false>(v, u, ctw + 0, oidx);
+#pragma unroll
+        for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t)] = v[e];
+        __syncthreads();
+      }
+      if constexpr (S >= 4) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u + e * U, t)];
+        __syncthreads();
+        stage_compute<LOGL, SC::logr(2), SC::logns(2), FWD, false, 0, false>(v, u, ctw + 8, oidx);
+#pragma unroll
+        for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t)] = v[e];
+        __syncthreads();
+      }
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u + e * U, t)];
+      stage_compute<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD, false, 0, false>(v, u, ctw + ((1 << (3 * (S - 1))) - 8) / 7, oidx);
+      if (valid) {
+        float2* o = out + (row << LOGL) + u;
+#pragma unroll
+        for (int e = 0; e < 8; e++) o[e * U] = v[e];
+      }
+      __syncthreads();  // all reads of buffer b done: it may be refilled from the next iteration on
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------
+// COL and TRANS passes fed by tensor-map TMA (cp.async.bulk.tensor, SASS: UTMALDG)
+// ---------------------------------------------------------------------------------
+struct alignas(64) tensor_map_blob {
+  unsigned char bytes[128];  // a CUtensorMap, passed by value as a __grid_constant__ parameter
+};
+
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const tensor_map_blob* tmap, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const tensor_map_blob* tmap, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <int LOGL, int T>
+struct tile_tma_smem {
+  static constexpr int L = 1 << LOGL;
+  static constexpr int BUF = T * L;  // elements per buffer (COL / TRANS layouts are dense)
+  static constexpr size_t data_bytes = 2 * (size_t)BUF * sizeof(float2);
+  // [2 tile buffers][128 B: mbarriers][stage twiddles W_L^j, L entries][3 << q inter-pass twiddles]
+  static constexpr size_t bytes(int q) { return data_bytes + 128 + (size_t)(L + (3 << q)) * sizeof(float2); }
+};
+
+// Column pass, persistent: view [A][L][B] (B = elements between consecutive FFT points). A tile is the
+// L x T box at (row a*L, column b0) of the 2-D tensor [A*L][B]; ONE TMA box load (per 256 rows) brings
+// it into shared memory in exactly the column-mode layout [idx][t], double buffered across tiles.
+// Stores go straight from registers with the inter-pass twiddle W_{L*B}^{k b} applied.
+template <int LOGL, int T, bool FWD>
+__global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOGL, T>::min_blocks)
+    fft_col_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, size_t B,
+                       uint32_t btiles, uint32_t ntiles, big_twiddle btw, const float2* __restrict__ tw) {
+  using SC = sched<LOGL>;
+  constexpr int L = 1 << LOGL, U = L / 8, S = SC::S, BUF = tile_tma_smem<LOGL, T>::BUF;
+  constexpr int ROWS_PER_BOX = (L < 256) ? L : 256;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  float2* const buf0 = reinterpret_cast<float2*>(smraw);
+  float2* const buf1 = buf0 + BUF;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  float2* const ltw = reinterpret_cast<float2*>(smraw + tile_tma_smem<LOGL, T>::data_bytes + 128);
+  float2* const stw = ltw + L;
+  const int tid = threadIdx.x;
+  const int t = tid % T, u = tid / T;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < (3 << btw.q); i += blockDim.x) stw[i] = __ldg(&btw.tab[i]);
+  for (int i = tid; i < L; i += blockDim.x) ltw[i] = __ldg(&tw[i]);
+  __syncthreads();
+  auto issue = [&](uint32_t tl, int b) {
+    const uint32_t a = tl / btiles, b0 = (tl % btiles) * T;
+    float2* dst = b ? buf1 : buf0;
+    fence_proxy_async();
+    mbar_expect_tx(&mbar[b], (uint32_t)(BUF * sizeof(float2)));
+#pragma unroll
+    for (int r = 0; r < L; r += ROWS_PER_BOX)
+      tma_load_2d(dst + r * T, &tmap, (int)b0, (int)(a * L + r), &mbar[b]);
+  };
+  uint32_t tile = blockIdx.x;
+  if (tile < ntiles && tid == 0) issue(tile, 0);
+  for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int b = it & 1;
+    float2* const sm = b ? buf1 : buf0;
+    const uint32_t nxt = tile + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue(nxt, b ^ 1);
+    mbar_wait(&mbar[b], (it >> 1) & 1);
+    float2 v[8];
+    int oidx[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = sm[(u + e * U) * T + t];
+    stage_compute<LOGL, SC::logr(0), 0, FWD>(v, u, tw, oidx);
+    if constexpr (S > 1) {
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 8; e++) sm[oidx[e] * T + t] = v[e];
+      __syncthreads();
+      if constexpr (S >= 3) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = sm[(u + e * U) * T + t];
+        __syncthreads();
+        stage_compute<LOGL, SC::logr(1), SC::logns(1), FWD, true, LOGL - SC::logns(1) - SC::logr(1), false>(v, u, ltw, oidx);
+#pragma unroll
+        for (int e = 0; e < 8; e++) sm[oidx[e] * T + t] = v[e];
+        __syncthreads();
+      }
+      if constexpr (S >= 4) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = sm[(u + e * U) * T + t];
+        __syncthreads();
+        stage_compute<LOGL, SC::logr(2), SC::logns(2), FWD, true, LOGL - SC::logns(2) - SC::logr(2), false>(v, u, ltw, oidx);
+#pragma unroll
+        for (int e = 0; e < 8; e++) sm[oidx[e] * T + t] = v[e];
+        __syncthreads();
+      }
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[e] = sm[(u + e * U) * T + t];
+      stage_compute<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD, true, LOGL - SC::logns(S - 1) - SC::logr(S - 1), false>(v, u, ltw, oidx);
+    }
+    {
+      // store k = u + e*U of column b0 + t, times W_{L*B}^{k (b0 + t)}
+      const uint32_t a = tile / btiles, b0 = (tile % btiles) * T;
+      const uint32_t bb = b0 + t;
+      float2 wb = big_tw_lookup(stw, btw.q, (uint32_t)u * bb);
+      float2 r1 = big_tw_lookup(stw, btw.q, (uint32_t)U * bb);
+      if (!FWD) {
+        wb.y = -wb.y;
+        r1.y = -r1.y;
+      }
+      const float2 r2 = c_sqr(r1), r4 = c_sqr(r2);
+      float2 w[8];
+      w[0] = wb;
+      w[1] = c_mul(wb, r1);
+      w[2] = c_mul(wb, r2);
+      w[3] = c_mul(w[1], r2);
+      w[4] = c_mul(wb, r4);
+      w[5] = c_mul(w[1], r4);
+      w[6] = c_mul(w[2], r4);
+      w[7] = c_mul(w[3], r4);
+      float2* o = out + ((size_t)a << LOGL) * B + b0 + (size_t)u * B + t;
+#pragma unroll
+      for (int e = 0; e < 8; e++) o[(size_t)e * U * B] = c_mul(v[e], w[e]);
+    }
+    __syncthreads();  // buffer b may be refilled from the next iteration on
+  }
+}
+
+// Transposing last pass, persistent: input rows [beta][k1][rest][L] as a 3-D tensor (L, S, L1*batch);
+// a tile = T consecutive k1 at fixed (beta, rest) = ONE 3-D TMA box (L, 1, T) landing as [t][L].
+// Stage 0 runs in the row mapping on that buffer, then the rotated column layout takes over and the
+// results leave in natural order: out[beta*n + k1 + L1*rest + A*k].
+template <int LOGL, int T, bool FWD>
+__global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOGL, T>::min_blocks)
+    fft_trans_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, uint32_t A,
+                         uint32_t S_, uint32_t L1, uint32_t k1tiles, uint32_t ntiles,
+                         const float2* __restrict__ tw) {
+  using SC = sched<LOGL>;
+  using LAY = tile_layout<LOGL, T, MODE_TRANS>;
+  constexpr int L = 1 << LOGL, U = L / 8, S = SC::S, BUF = tile_tma_smem<LOGL, T>::BUF;
+  static_assert(L <= 256 || true, "");
+  extern __shared__ __align__(128) unsigned char smraw[];
+  float2* const buf0 = reinterpret_cast<float2*>(smraw);
+  float2* const buf1 = buf0 + BUF;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  float2* const ltw = reinterpret_cast<float2*>(smraw + tile_tma_smem<LOGL, T>::data_bytes + 128);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < L; i += blockDim.x) ltw[i] = __ldg(&tw[i]);
+  const int t0 = tid / U, u0 = tid % U;  // stage 0: lanes along the FFT index (rows are contiguous)
+  const int t1 = tid % T, u1 = tid / T;  // later stages and the store: lanes along t
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  constexpr int COLS_PER_BOX = (L < 256) ? L : 256;
+  auto issue = [&](uint32_t tl, int b) {
+    const uint32_t k1t = tl % k1tiles, r = tl / k1tiles;
+    const uint32_t rest = r % S_, beta = r / S_;
+    float2* dst = b ? buf1 : buf0;
+    fence_proxy_async();
+    mbar_expect_tx(&mbar[b], (uint32_t)(BUF * sizeof(float2)));
+    if (L <= 256) {
+      tma_load_3d(dst, &tmap, 0, (int)rest, (int)(beta * L1 + k1t * T), &mbar[b]);
+    } else {
+      // box inner dimension is capped at 256 elements: one box per 256-column slab and per row
+      for (int tt = 0; tt < T; tt++)
+        for (int c = 0; c < L; c += COLS_PER_BOX)
+          tma_load_3d(dst + tt * L + c, &tmap, c, (int)rest, (int)(beta * L1 + k1t * T + tt), &mbar[b]);
+    }
+  };
+  uint32_t tile = blockIdx.x;
+  if (tile < ntiles && tid == 0) issue(tile, 0);
+  for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int b = it & 1;
+    float2* const sm = b ? buf1 : buf0;
+    const uint32_t nxt = tile + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue(nxt, b ^ 1);
+    mbar_wait(&mbar[b], (it >> 1) & 1);
+    float2 v[8];
+    int oidx[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = sm[t0 * L + u0 + e * U];
+    stage_compute<LOGL, SC::logr(0), 0, FWD>(v, u0, tw, oidx);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t0)] = v[e];
+    __syncthreads();
+    if constexpr (S >= 3) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u1 + e * U, t1)];
+      __syncthreads();
+      stage_compute<LOGL, SC::logr(1), SC::logns(1), FWD, true, LOGL - SC::logns(1) - SC::logr(1), false>(v, u1, ltw, oidx);
+#pragma unroll
+      for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t1)] = v[e];
+      __syncthreads();
+    }
+    if constexpr (S >= 4) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u1 + e * U, t1)];
+      __syncthreads();
+      stage_compute<LOGL, SC::logr(2), SC::logns(2), FWD, true, LOGL - SC::logns(2) - SC::logr(2), false>(v, u1, ltw, oidx);
+#pragma unroll
+      for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t1)] = v[e];
+      __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u1 + e * U, t1)];
+    stage_compute<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD, true, LOGL - SC::logns(S - 1) - SC::logr(S - 1), false>(v, u1, ltw, oidx);
+    {
+      const uint32_t k1t = tile % k1tiles, r = tile / k1tiles;
+      const uint32_t rest = r % S_, beta = r / S_;
+      float2* o = out + (((size_t)beta * A) << LOGL) + (size_t)k1t * T + (size_t)L1 * rest + t1 + (size_t)A * u1;
+#pragma unroll
+      for (int e = 0; e < 8; e++) o[(size_t)A * e * U] = v[e];
+    }
+    __syncthreads();
+  }
+}
 
 }  // namespace srtb_b200

@@ -364,23 +364,6 @@ __device__ __forceinline__ float2 r2c_twiddle(size_t k, size_t M) {
   return make_float2(c1 * c2 - s1 * s2, c1 * s2 + s1 * c2);
 }
 
-__global__ void __launch_bounds__(256) r2c_post_kernel(float2* __restrict__ H, size_t M) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k <= M / 2; k += stride) {
-    const float2 hk = H[k];
-    const float2 hm = (k == 0) ? hk : H[M - k];
-    const float2 F = make_float2(0.5f * (hk.x + hm.x), 0.5f * (hk.y - hm.y));
-    // d = hk - conj(hm) = (hk.x - hm.x, hk.y + hm.y);  G = -i/2 * d = (d.y/2, -d.x/2)
-    const float2 G = make_float2(0.5f * (hk.y + hm.y), -0.5f * (hk.x - hm.x));
-    const float2 w = r2c_twiddle(k, M);
-    const float2 gw = make_float2(G.x * w.x - G.y * w.y, G.x * w.y + G.y * w.x);
-    const float2 xk = make_float2(F.x + gw.x, F.y + gw.y);
-    const float2 xm = make_float2(F.x - gw.x, -(F.y - gw.y));
-    H[k] = xk;
-    H[M - k] = xm;  // k == M/2 writes the same bin twice; the reference keeps this one (:257-258)
-  }
-}
-
 // ------------------------------------------------------------------------------
 // reductions
 // ------------------------------------------------------------------------------
@@ -406,6 +389,66 @@ __device__ __forceinline__ T block_sum(T v, T* sm) {
   T r = (threadIdx.x < nw) ? sm[threadIdx.x] : T(0);
   if (wid == 0) r = warp_sum(r);
   return r;
+}
+
+// SUM = true additionally produces the mean of |X_k|^2 over k < M (the s1 statistic, K9) while the
+// bins are in registers: per-CTA fp64 partials + last-CTA ticket, exactly as power_sum_kernel.
+template <bool SUM>
+__global__ void __launch_bounds__(256) r2c_post_kernel(float2* __restrict__ H, size_t M,
+                                                       double* __restrict__ partial,
+                                                       unsigned* __restrict__ ticket,
+                                                       float* __restrict__ mean_out) {
+  __shared__ double sm[32];
+  __shared__ bool last;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float acc = 0.f;
+  auto split = [&](size_t k, float2 hk, float2 hm) {
+    const float2 F = make_float2(0.5f * (hk.x + hm.x), 0.5f * (hk.y - hm.y));
+    // d = hk - conj(hm) = (hk.x - hm.x, hk.y + hm.y);  G = -i/2 * d = (d.y/2, -d.x/2)
+    const float2 G = make_float2(0.5f * (hk.y + hm.y), -0.5f * (hk.x - hm.x));
+    const float2 w = r2c_twiddle(k, M);
+    const float2 gw = make_float2(G.x * w.x - G.y * w.y, G.x * w.y + G.y * w.x);
+    const float2 xk = make_float2(F.x + gw.x, F.y + gw.y);
+    const float2 xm = make_float2(F.x - gw.x, -(F.y - gw.y));
+    H[k] = xk;
+    H[M - k] = xm;  // k == M/2 writes the same bin twice; the reference keeps this one (:257-258)
+    if (SUM) {
+      // bins 0 .. M-1 count (the Nyquist bin M is dropped by the pipe); bin M/2 counted once
+      const float wm = (k == 0 || 2 * k == M) ? 0.f : 1.f;
+      acc += (xk.x * xk.x + xk.y * xk.y) + wm * (xm.x * xm.x + xm.y * xm.y);
+    }
+  };
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; k + stride <= M / 2; k += 2 * stride) {   // two independent pairs: four loads in flight
+    const size_t k2 = k + stride;
+    const float2 a0 = H[k], a1 = (k == 0) ? a0 : H[M - k];
+    const float2 b0 = H[k2], b1 = H[M - k2];
+    split(k, a0, a1);
+    split(k2, b0, b1);
+  }
+  if (k <= M / 2) {
+    const float2 a0 = H[k], a1 = (k == 0) ? a0 : H[M - k];
+    split(k, a0, a1);
+  }
+  if (SUM) {
+    const double s = block_sum<double>((double)acc, sm);
+    if (threadIdx.x == 0) {
+      partial[blockIdx.x] = s;
+      __threadfence();
+      last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      double a = 0.0;
+      for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) a += partial[i];
+      a = block_sum<double>(a, sm);
+      if (threadIdx.x == 0) {
+        *mean_out = (float)a / (float)M;
+        *ticket = 0;
+      }
+    }
+  }
 }
 
 // K9 mean of |X|^2 (S/algorithm/map_reduce.hpp:84-91 over rfi_mitigation_pipe.hpp:53-60).
@@ -510,15 +553,25 @@ __device__ __forceinline__ float2 chirp_factor(double f_min, double df, double i
   return make_float2(c, s);
 }
 
+// S1 = true fuses K10 (zap + normalise, rfi_mitigation_pipe.hpp:66-79) in front of the chirp: used by
+// srtb_b200_process_block, where the s1 and dedisperse pipes run back to back on one stream.
+template <bool S1>
 __global__ void __launch_bounds__(256) dedisperse_kernel(float2* __restrict__ x, size_t count,
                                                          double f_min, double df, double f_c,
-                                                         double ddm) {
+                                                         double ddm, const float* __restrict__ mean,
+                                                         float threshold, float coef) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t pairs = count / 2;
   const double inv_fc = 1.0 / f_c;
+  const float limit = S1 ? threshold * (*mean) : 0.f;
   float4* x4 = reinterpret_cast<float4*>(x);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
     float4 v = x4[i];
+    if (S1) {
+      const float p0 = v.x * v.x + v.y * v.y, p1 = v.z * v.z + v.w * v.w;
+      if (p0 > limit) { v.x = 0.f; v.y = 0.f; } else { v.x *= coef; v.y *= coef; }
+      if (p1 > limit) { v.z = 0.f; v.w = 0.f; } else { v.z *= coef; v.w *= coef; }
+    }
     const float2 w0 = chirp_factor(f_min, df, inv_fc, f_c, ddm, (unsigned)(2 * i));
     const float2 w1 = chirp_factor(f_min, df, inv_fc, f_c, ddm, (unsigned)(2 * i + 1));
     const float4 o = make_float4(v.x * w0.x - v.y * w0.y, v.x * w0.y + v.y * w0.x,
@@ -526,7 +579,11 @@ __global__ void __launch_bounds__(256) dedisperse_kernel(float2* __restrict__ x,
     x4[i] = o;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && (count & 1)) {
-    const float2 v = x[count - 1];
+    float2 v = x[count - 1];
+    if (S1) {
+      if (v.x * v.x + v.y * v.y > limit) v = make_float2(0.f, 0.f);
+      else { v.x *= coef; v.y *= coef; }
+    }
     const float2 w = chirp_factor(f_min, df, inv_fc, f_c, ddm, (unsigned)(count - 1));
     x[count - 1] = make_float2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);
   }
@@ -641,6 +698,74 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float2* __res
   if (two) p[1] = a1;
 }
 
+// K14 + K15 + K17 stage 1 fused (process_block only): one sweep over the dynamic spectrum computes
+// every row's spectral kurtosis, zeroes the flagged rows AND accumulates the partial column sums
+// of the surviving rows, so the detector does not read the spectrum again.
+// CTA = rows_per_chunk consecutive channel rows; thread owns NJ float4 (2*NJ time samples) per row.
+template <int NJ>
+__global__ void __launch_bounds__(256) sk_colsum_kernel(float2* __restrict__ x, size_t time_count,
+                                                        size_t chan_count, size_t ts_count,
+                                                        size_t rows_per_chunk, float thr_lo, float thr_hi,
+                                                        float* __restrict__ partial) {
+  __shared__ float sm2[8], sm4[8];
+  __shared__ int s_zap;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const size_t c0 = (size_t)blockIdx.x * rows_per_chunk;
+  const size_t c1 = min(c0 + rows_per_chunk, chan_count);
+  float acc[2 * NJ];
+#pragma unroll
+  for (int j = 0; j < 2 * NJ; j++) acc[j] = 0.f;
+  for (size_t c = c0; c < c1; c++) {
+    float4* row4 = reinterpret_cast<float4*>(x + c * time_count);
+    float4 v[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) v[j] = row4[tid + 256 * j];
+    float p[2 * NJ];
+    float s2 = 0.f, s4 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      p[2 * j] = v[j].x * v[j].x + v[j].y * v[j].y;
+      p[2 * j + 1] = v[j].z * v[j].z + v[j].w * v[j].w;
+      s2 += p[2 * j] + p[2 * j + 1];
+      s4 += p[2 * j] * p[2 * j] + p[2 * j + 1] * p[2 * j + 1];
+    }
+    s2 = warp_sum(s2);
+    s4 = warp_sum(s4);
+    if (lane == 0) {
+      sm2[wid] = s2;
+      sm4[wid] = s4;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      float a = (lane < 8) ? sm2[lane] : 0.f, b = (lane < 8) ? sm4[lane] : 0.f;
+      a = warp_sum(a);
+      b = warp_sum(b);
+      if (lane == 0) {
+        const float sk = (float)time_count * (b / (a * a));
+        s_zap = (sk > thr_hi || sk < thr_lo) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    if (s_zap) {
+#pragma unroll
+      for (int j = 0; j < NJ; j++) row4[tid + 256 * j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2 * NJ; j++) acc[j] += p[j];
+    }
+  }
+  float* out = partial + (size_t)blockIdx.x * ts_count;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const size_t col = 2 * ((size_t)tid + 256 * j);
+    if (col + 1 < ts_count) {
+      *reinterpret_cast<float2*>(out + col) = make_float2(acc[2 * j], acc[2 * j + 1]);
+    } else if (col < ts_count) {
+      out[col] = acc[2 * j];
+    }
+  }
+}
+
 // K17 stage 2 + K16: ts[j] = sum over chunks (fixed order), zero_count.
 // CTA = 32 columns x 8 chunk groups: coalesced along time, tree over the groups in shared memory.
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial,
@@ -666,15 +791,21 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
     for (int g = 1; g < 8; g++) t += sm[g][lx];
     ts[j] = t;
   }
-  if (blockIdx.x == 0) {
-    __shared__ float smz[32];
-    float z = 0.f;
-    for (size_t c = threadIdx.x; c < chan_count; c += blockDim.x) {
+  // K16: channels whose first sample is zero; every CTA takes a slice, integer atomics (exact)
+  {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int z = 0;
+    if (c < chan_count) {
       const float2 v = x[c * time_count];
-      if (v.x * v.x + v.y * v.y == 0.f) z += 1.f;
+      z = (v.x * v.x + v.y * v.y == 0.f) ? 1 : 0;
     }
-    z = block_sum<float>(z, smz);
-    if (threadIdx.x == 0) res->zero_count = (unsigned long long)z;
+    const unsigned m = __ballot_sync(0xffffffffu, z);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&res->zero_count, (unsigned long long)__popc(m));
+    // channels beyond gridDim.x * blockDim.x (more channels than columns/32*256): strided tail
+    for (size_t cc = c + (size_t)gridDim.x * blockDim.x; cc < chan_count; cc += (size_t)gridDim.x * blockDim.x) {
+      const float2 v = x[cc * time_count];
+      if (v.x * v.x + v.y * v.y == 0.f) atomicAdd(&res->zero_count, 1ull);
+    }
   }
 }
 

@@ -2,6 +2,7 @@
 // kernel launches. Host logic only mirrors the reference's host-side arithmetic; every
 // data-path byte is touched by the CUDA kernels in fft_engine.cuh / ops_kernels.cuh.
 // There is no CPU fallback.
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -28,6 +29,7 @@ struct srtb_b200_ctx {
   std::string err;
   uint64_t launches = 0;
   std::set<const void*> configured;  // kernels whose smem attribute is set on this device
+  std::map<const void*, int> occupancy;  // resident CTAs per SM of the persistent kernels
   // FFT
   float2* tw[13] = {nullptr};
   std::map<int, float2*> bigtw;  // log2(n_i) -> [3 << q]
@@ -47,6 +49,15 @@ struct srtb_b200_ctx {
   detect_dev_result* d_res = nullptr;
   detect_dev_result* h_res = nullptr;  // pinned, 4 slots
   size_t slot_time_count[4] = {0, 0, 0, 0};
+  // pipelined ingest ring
+  cudaStream_t copy_stream = nullptr;
+  void* slot_baseband[SRTB_B200_RING_SLOTS] = {nullptr};
+  size_t slot_baseband_bytes[SRTB_B200_RING_SLOTS] = {0};
+  cudaEvent_t slot_h2d[SRTB_B200_RING_SLOTS] = {nullptr}, slot_done[SRTB_B200_RING_SLOTS] = {nullptr};
+  int slot_streams[SRTB_B200_RING_SLOTS] = {0};
+  size_t slot_L[SRTB_B200_RING_SLOTS] = {0};
+  bool slot_busy[SRTB_B200_RING_SLOTS] = {false};
+  uint64_t submit_count = 0;
   // process_block
   void* d_baseband = nullptr;
   size_t d_baseband_bytes = 0;
@@ -122,7 +133,7 @@ int srtb_b200_ctx_create(int device, void* cuda_stream, srtb_b200_ctx** out) {
   if (e == cudaSuccess) e = cudaMalloc(&ctx->mean, sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_res, sizeof(detect_dev_result) * 4);
   if (e == cudaSuccess) e = cudaMemset(ctx->d_res, 0, sizeof(detect_dev_result) * 4);
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_res, sizeof(detect_dev_result) * 4);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_res, sizeof(detect_dev_result) * 4 * (1 + SRTB_B200_RING_SLOTS));
   if (e != cudaSuccess) {
     const std::string msg = std::string("ctx_create: ") + cudaGetErrorString(e);
     delete ctx;
@@ -149,6 +160,12 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   cudaFree(ctx->d_res);
   cudaFreeHost(ctx->h_res);
   cudaFree(ctx->d_baseband);
+  for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) {
+    cudaFree(ctx->slot_baseband[i]);
+    if (ctx->slot_h2d[i]) cudaEventDestroy(ctx->slot_h2d[i]);
+    if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& p : ctx->stream_buf) cudaFree(p);
   delete ctx;
   return 0;
@@ -339,6 +356,27 @@ struct col_t {
 template <int LOGL, bool FWD>
 static int launch_row(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t nrows) {
   constexpr int T = row_t<LOGL>::value;
+  if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
+    // persistent TMA-fed kernel (cp.async.bulk needs 16-byte aligned rows)
+    auto kern = fft_row_tma_kernel<LOGL, T, FWD>;
+    constexpr size_t smem = row_tma_smem<LOGL, T>::bytes;
+    const void* key = reinterpret_cast<const void*>(kern);
+    if (!ctx->configured.count(key)) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 1;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pass_threads<LOGL, T>::value, smem));
+      ctx->occupancy[key] = std::max(1, per_sm);
+      ctx->configured.insert(key);
+    }
+    const float2* tw = nullptr;
+    if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+    const size_t ntiles = (nrows + T - 1) / T;
+    const unsigned grid = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * ctx->occupancy[key]);
+    kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(in, out, nrows, tw);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+  }
   row_io<LOGL, T> io;
   io.in = in;
   io.out = out;
@@ -348,9 +386,118 @@ static int launch_row(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t 
   return launch_pass<LOGL, T, MODE_ROW, FWD>(ctx, io, grid, 0);
 }
 
+// ---- tensor maps for the TMA-fed passes --------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  }
+  return fn;
+}
+
+// complex64 elements are described to TMA as 8-byte integers; dims/box are innermost first
+static bool make_tensor_map(tensor_map_blob* out, const void* base, int rank, const cuuint64_t* dims,
+                            const cuuint64_t* strides_bytes /* rank-1 */, const cuuint32_t* box) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return false;
+  static_assert(sizeof(CUtensorMap) <= sizeof(tensor_map_blob), "tensor map size");
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_INT64, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                         box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return false;
+  std::memcpy(out->bytes, &m, sizeof(m));
+  return true;
+}
+
+template <class K>
+static int persistent_grid(srtb_b200_ctx* ctx, K kern, int threads, size_t smem, size_t smem_max, size_t ntiles,
+                           unsigned* grid) {
+  const void* key = reinterpret_cast<const void*>(kern);
+  if (!ctx->configured.count(key)) {
+    // the attribute is set once per kernel: use the largest size any later launch can ask for
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_max));
+    ctx->occupancy[key] = std::max(1, per_sm);
+    ctx->configured.insert(key);
+  }
+  *grid = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * ctx->occupancy[key]);
+  return 0;
+}
+
+template <int LOGL, bool FWD>
+static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t B, bool* done) {
+  constexpr int T = col_t<LOGL>::value, L = 1 << LOGL;
+  *done = false;
+  if ((reinterpret_cast<uintptr_t>(in) & 15u) || A * L >= ((size_t)1 << 31) || B >= ((size_t)1 << 31)) return 0;
+  tensor_map_blob tm;
+  const cuuint64_t dims[2] = {(cuuint64_t)B, (cuuint64_t)(A * L)};
+  const cuuint64_t strides[1] = {(cuuint64_t)B * sizeof(float2)};
+  const cuuint32_t box[2] = {(cuuint32_t)T, (cuuint32_t)std::min(L, 256)};
+  if (!make_tensor_map(&tm, in, 2, dims, strides, box)) return 0;  // fall back to the LDG kernel
+  big_twiddle btw;
+  if (int rc = get_big_twiddles(ctx, LOGL + ilog2(B), &btw)) return rc;
+  const float2* tw = nullptr;
+  if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+  auto kern = fft_col_tma_kernel<LOGL, T, FWD>;
+  const size_t smem = tile_tma_smem<LOGL, T>::bytes(btw.q);
+  const size_t ntiles = A * (B / T);
+  unsigned grid = 1;
+  if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
+  kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  *done = true;
+  return 0;
+}
+
+template <int LOGL, bool FWD>
+static int launch_trans_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t batch, size_t A, size_t L1,
+                            bool* done) {
+  constexpr int T = col_t<LOGL>::value, L = 1 << LOGL;
+  *done = false;
+  const size_t S = A / L1;
+  if ((reinterpret_cast<uintptr_t>(in) & 15u) || batch * L1 >= ((size_t)1 << 31)) return 0;
+  tensor_map_blob tm;
+  // rows [beta*L1 + k1][rest][L]  ->  dims (L, S, batch*L1)
+  const cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)S, (cuuint64_t)(batch * L1)};
+  const cuuint64_t strides[2] = {(cuuint64_t)L * sizeof(float2), (cuuint64_t)S * L * sizeof(float2)};
+  const cuuint32_t box[3] = {(cuuint32_t)std::min(L, 256), 1u, (cuuint32_t)((L <= 256) ? T : 1)};
+  if (!make_tensor_map(&tm, in, 3, dims, strides, box)) return 0;
+  const float2* tw = nullptr;
+  if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+  auto kern = fft_trans_tma_kernel<LOGL, T, FWD>;
+  const size_t smem = tile_tma_smem<LOGL, T>::bytes(0);
+  const size_t k1tiles = L1 / T, ntiles = batch * S * k1tiles;
+  unsigned grid = 1;
+  if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, smem, ntiles, &grid)) return rc;
+  kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
+                                                                  (uint32_t)k1tiles, (uint32_t)ntiles, tw);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  *done = true;
+  return 0;
+}
+
 template <int LOGL, bool FWD>
 static int launch_col(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t B) {
   constexpr int T = col_t<LOGL>::value;
+  {
+    bool done = false;
+    if (int rc = launch_col_tma<LOGL, FWD>(ctx, in, out, A, B, &done)) return rc;
+    if (done) return 0;
+  }
   col_io<LOGL, T, FWD> io;
   io.in = in;
   io.out = out;
@@ -368,6 +515,11 @@ template <int LOGL, bool FWD>
 static int launch_trans(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t batch, size_t A,
                         size_t L1) {
   constexpr int T = col_t<LOGL>::value;
+  {
+    bool done = false;
+    if (int rc = launch_trans_tma<LOGL, FWD>(ctx, in, out, batch, A, L1, &done)) return rc;
+    if (done) return 0;
+  }
   trans_io<LOGL, T> io;
   io.in = in;
   io.out = out;
@@ -485,7 +637,20 @@ extern "C" int srtb_b200_fft_r2c_inplace(srtb_b200_ctx* ctx, float* d_inout, siz
   const size_t M = n_real / 2;
   float2* H = reinterpret_cast<float2*>(d_inout);
   if (int rc = fft_c2c_impl<true>(ctx, H, M, 1)) return rc;
-  r2c_post_kernel<<<grid_for(ctx, M / 2 + 1, 256), 256, 0, ctx->stream>>>(H, M);
+  r2c_post_kernel<false><<<grid_for(ctx, M / 2 + 1, 256), 256, 0, ctx->stream>>>(H, M, nullptr, nullptr, nullptr);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// R2C whose split pass also leaves mean(|X_k|^2, k < N/2) in ctx->mean (used by process_block:
+// the s1 statistic costs no extra sweep)
+static int fft_r2c_with_power_mean(srtb_b200_ctx* ctx, float* d_inout, size_t n_real) {
+  const size_t M = n_real / 2;
+  float2* H = reinterpret_cast<float2*>(d_inout);
+  if (int rc = fft_c2c_impl<true>(ctx, H, M, 1)) return rc;
+  const unsigned grid = std::min<unsigned>(grid_for(ctx, M / 2 + 1, 256), 4096);
+  r2c_post_kernel<true><<<grid, 256, 0, ctx->stream>>>(H, M, ctx->partial, ctx->ticket, ctx->mean);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -600,10 +765,44 @@ extern "C" int srtb_b200_dedisperse(srtb_b200_ctx* ctx, void* d_x, size_t count,
   CK(cudaSetDevice(ctx->device));
   constexpr double D = 4.148808e3;  // coherent_dedispersion.hpp:67
   const double ddm = (D * 1e6) * (double)dm;
-  dedisperse_kernel<<<grid_for(ctx, count / 2 + 1, 256, 16), 256, 0, ctx->stream>>>(
-      static_cast<float2*>(d_x), count, (double)f_min, (double)df, (double)f_c, ddm);
+  dedisperse_kernel<false><<<grid_for(ctx, count / 2 + 1, 256, 16), 256, 0, ctx->stream>>>(
+      static_cast<float2*>(d_x), count, (double)f_min, (double)df, (double)f_c, ddm, nullptr, 0.f, 1.f);
   ctx->launches++;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// s1 (mean -> zap/normalise) and the chirp in two kernels instead of three: power sum, then one
+// fused apply + chirp sweep, then the manual zap (zero * chirp = zero, so the order is equivalent)
+static int rfi_s1_dedisperse_fused(srtb_b200_ctx* ctx, float2* x, size_t count, float avg_threshold, float coef,
+                                   const std::vector<size_t>& bins, float f_min, float f_c, float df, float dm,
+                                   bool mean_ready) {
+  if (!mean_ready) {
+    const unsigned grid = std::min<unsigned>(grid_for(ctx, count / 2 + 1, 256), 4096);
+    power_sum_kernel<<<grid, 256, 0, ctx->stream>>>(x, count, ctx->partial, ctx->ticket, ctx->mean);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  constexpr double D = 4.148808e3;
+  const double ddm = (D * 1e6) * (double)dm;
+  dedisperse_kernel<true><<<grid_for(ctx, count / 2 + 1, 256, 16), 256, 0, ctx->stream>>>(
+      x, count, (double)f_min, (double)df, (double)f_c, ddm, ctx->mean, avg_threshold, coef);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  for (size_t r0 = 0; r0 < bins.size() / 2; r0 += 16) {
+    bin_ranges br;
+    const size_t nr = std::min<size_t>(16, bins.size() / 2 - r0);
+    size_t longest = 1;
+    for (size_t r = 0; r < nr; r++) {
+      br.lo[r] = bins[2 * (r0 + r)];
+      br.hi[r] = bins[2 * (r0 + r) + 1];
+      longest = std::max<size_t>(longest, br.hi[r] - br.lo[r] + 1);
+    }
+    dim3 g(grid_for(ctx, longest, 256), (unsigned)nr);
+    rfi_zero_ranges_kernel<<<g, 256, 0, ctx->stream>>>(x, br);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -643,11 +842,7 @@ extern "C" int srtb_b200_rfi_s2_sk(srtb_b200_ctx* ctx, void* d_x, size_t time_co
 // ------------------------------------------------------------------------------------
 // signal detect
 // ------------------------------------------------------------------------------------
-static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t time_count,
-                          size_t chan_count, size_t time_reserved_count, float snr, float chan_thr,
-                          size_t max_boxcar) {
-  const size_t ts_count = (time_count <= time_reserved_count) ? time_count : time_count - time_reserved_count;
-  // buffers
+static int detect_prepare(srtb_b200_ctx* ctx, int slot, size_t time_count, size_t need_partial_elems) {
   const size_t series_need = (size_t)SRTB_B200_MAX_BOXCARS * time_count;
   if (ctx->series_elems < series_need) {
     CK(cudaStreamSynchronize(ctx->stream));
@@ -667,21 +862,18 @@ static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t 
     if (int rc = ensure(ctx, reinterpret_cast<void**>(&ctx->acc), &have, time_count * sizeof(float))) return rc;
     ctx->acc_elems = have / sizeof(float);
   }
-  const size_t ctas_per_chunk = (ts_count + 511) / 512;
-  size_t chunks = std::max<size_t>(1, (size_t)ctx->sm_count * 8 / ctas_per_chunk);
-  chunks = std::min(chunks, std::min<size_t>(128, chan_count));
-  const size_t rows_per_chunk = (chan_count + chunks - 1) / chunks;
-  chunks = (chan_count + rows_per_chunk - 1) / rows_per_chunk;
   {
     size_t have = ctx->colsum_partial_elems * sizeof(float);
-    if (int rc = ensure(ctx, reinterpret_cast<void**>(&ctx->colsum_partial), &have, chunks * ts_count * sizeof(float)))
+    if (int rc = ensure(ctx, reinterpret_cast<void**>(&ctx->colsum_partial), &have, need_partial_elems * sizeof(float)))
       return rc;
     ctx->colsum_partial_elems = have / sizeof(float);
   }
-  dim3 g((unsigned)ctas_per_chunk, (unsigned)chunks);
-  colsum_partial_kernel<<<g, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, ctx->colsum_partial);
-  ctx->launches++;
-  CK(cudaGetLastError());
+  return 0;
+}
+
+// column-sum reduction over `chunks` partial rows, zero count, scan, boxcar ladder
+static int detect_tail(srtb_b200_ctx* ctx, int slot, const float2* x, size_t time_count, size_t chan_count,
+                       size_t ts_count, size_t chunks, float snr, float chan_thr, size_t max_boxcar) {
   colsum_final_kernel<<<(unsigned)((ts_count + 31) / 32), 256, 0, ctx->stream>>>(
       ctx->colsum_partial, ts_count, chunks, ctx->series[slot], x, time_count, chan_count, ctx->d_res + slot);
   ctx->launches++;
@@ -699,6 +891,52 @@ static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t 
   CK(cudaGetLastError());
   ctx->slot_time_count[slot] = time_count;
   return 0;
+}
+
+static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t time_count,
+                          size_t chan_count, size_t time_reserved_count, float snr, float chan_thr,
+                          size_t max_boxcar) {
+  const size_t ts_count = (time_count <= time_reserved_count) ? time_count : time_count - time_reserved_count;
+  const size_t ctas_per_chunk = (ts_count + 511) / 512;
+  size_t chunks = std::max<size_t>(1, (size_t)ctx->sm_count * 8 / ctas_per_chunk);
+  chunks = std::min(chunks, std::min<size_t>(128, chan_count));
+  const size_t rows_per_chunk = (chan_count + chunks - 1) / chunks;
+  chunks = (chan_count + rows_per_chunk - 1) / rows_per_chunk;
+  if (int rc = detect_prepare(ctx, slot, time_count, chunks * ts_count)) return rc;
+  CK(cudaMemsetAsync(ctx->d_res + slot, 0, sizeof(detect_dev_result), ctx->stream));
+  dim3 g((unsigned)ctas_per_chunk, (unsigned)chunks);
+  colsum_partial_kernel<<<g, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, ctx->colsum_partial);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
+}
+
+// s2 (spectral kurtosis) + the detector's first column-sum stage in one sweep; used by process_block
+// when a row fits the per-thread register tile (L = 512 .. 4096)
+static bool sk_detect_fusable(size_t time_count) {
+  return time_count == 512 || time_count == 1024 || time_count == 2048 || time_count == 4096;
+}
+static int sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_t time_count, size_t chan_count,
+                           size_t time_reserved_count, float sk_threshold, float snr, float chan_thr,
+                           size_t max_boxcar) {
+  const size_t ts_count = (time_count <= time_reserved_count) ? time_count : time_count - time_reserved_count;
+  const size_t rows_per_chunk = std::max<size_t>(1, chan_count / ((size_t)ctx->sm_count * 4));
+  const size_t chunks = (chan_count + rows_per_chunk - 1) / rows_per_chunk;
+  if (int rc = detect_prepare(ctx, slot, time_count, chunks * ts_count)) return rc;
+  CK(cudaMemsetAsync(ctx->d_res + slot, 0, sizeof(detect_dev_result), ctx->stream));
+  const float M_ = static_cast<float>(time_count);
+  float hi = sk_threshold, lo = 2 - sk_threshold;
+  if (lo > hi) std::swap(lo, hi);
+  const float lo_ = lo * ((M_ - 1) / (M_ + 1)) + 1, hi_ = hi * ((M_ - 1) / (M_ + 1)) + 1;
+  switch (time_count / 512) {
+    case 1: sk_colsum_kernel<1><<<(unsigned)chunks, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, lo_, hi_, ctx->colsum_partial); break;
+    case 2: sk_colsum_kernel<2><<<(unsigned)chunks, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, lo_, hi_, ctx->colsum_partial); break;
+    case 4: sk_colsum_kernel<4><<<(unsigned)chunks, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, lo_, hi_, ctx->colsum_partial); break;
+    default: sk_colsum_kernel<8><<<(unsigned)chunks, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, lo_, hi_, ctx->colsum_partial); break;
+  }
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
 }
 
 static int detect_collect(srtb_b200_ctx* ctx, int slot, srtb_b200_detect_result* h_result, float* h_series,
@@ -754,16 +992,14 @@ static int format_streams(int format) {
   }
 }
 
-extern "C" int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
-                                              const void* d_baseband, size_t baseband_bytes,
-                                              srtb_b200_detect_result* h_results, float* h_series,
-                                              int copy_all) {
-  if (!ctx || !cfg || !d_baseband || !h_results) return fail(ctx, SRTB_B200_E_INVALID, "process_block: null argument");
+// enqueue every stage of one block on ctx->stream (no host sync); results land in
+// ctx->h_res[res_base .. res_base + streams) once the stream reaches the final D2H copy
+static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, const void* d_baseband,
+                         size_t baseband_bytes, int res_base, int* streams_out, size_t* L_out) {
   const int streams = format_streams(cfg->baseband_format);
   if (!streams) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "process_block: unknown format");
   const size_t N = cfg->baseband_input_count;
   if (N < 2 || !is_pow2(N)) return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(N));
-  CK(cudaSetDevice(ctx->device));
   if (ctx->stream_buf_elems < N + 2) {
     CK(cudaStreamSynchronize(ctx->stream));
     for (auto& p : ctx->stream_buf) {
@@ -804,19 +1040,42 @@ extern "C" int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b20
                           batch;
   for (int s = 0; s < streams; s++) {
     float* buf = ctx->stream_buf[s];
-    if (int rc = srtb_b200_fft_r2c_inplace(ctx, buf, N)) return rc;
-    if (int rc = srtb_b200_rfi_s1(ctx, buf, Nc, cfg->mitigate_rfi_average_method_threshold, coef,
-                                  bins.empty() ? nullptr : bins.data(), bins.size() / 2, nullptr))
+    if (int rc = fft_r2c_with_power_mean(ctx, buf, N)) return rc;
+    if (int rc = rfi_s1_dedisperse_fused(ctx, reinterpret_cast<float2*>(buf), Nc,
+                                         cfg->mitigate_rfi_average_method_threshold, coef, bins, f_min, f_c, df, cfg->dm,
+                                         /*mean_ready=*/true))
       return rc;
-    if (int rc = srtb_b200_dedisperse(ctx, buf, Nc, f_min, f_c, df, cfg->dm)) return rc;
     if (int rc = srtb_b200_watfft_c2c_backward(ctx, buf, L, batch)) return rc;
-    if (int rc = srtb_b200_rfi_s2_sk(ctx, buf, L, batch, cfg->mitigate_rfi_spectral_kurtosis_threshold, nullptr)) return rc;
-    if (int rc = detect_enqueue(ctx, s, reinterpret_cast<const float2*>(buf), L, batch, reserved,
-                                cfg->signal_detect_signal_noise_threshold, cfg->signal_detect_channel_threshold,
-                                cfg->signal_detect_max_boxcar_length))
-      return rc;
+    if (sk_detect_fusable(L)) {
+      if (int rc = sk_detect_fused(ctx, s, reinterpret_cast<float2*>(buf), L, batch, reserved,
+                                   cfg->mitigate_rfi_spectral_kurtosis_threshold,
+                                   cfg->signal_detect_signal_noise_threshold, cfg->signal_detect_channel_threshold,
+                                   cfg->signal_detect_max_boxcar_length))
+        return rc;
+    } else {
+      if (int rc = srtb_b200_rfi_s2_sk(ctx, buf, L, batch, cfg->mitigate_rfi_spectral_kurtosis_threshold, nullptr)) return rc;
+      if (int rc = detect_enqueue(ctx, s, reinterpret_cast<const float2*>(buf), L, batch, reserved,
+                                  cfg->signal_detect_signal_noise_threshold, cfg->signal_detect_channel_threshold,
+                                  cfg->signal_detect_max_boxcar_length))
+        return rc;
+    }
   }
-  CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(detect_dev_result) * streams, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->h_res + res_base, ctx->d_res, sizeof(detect_dev_result) * streams, cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  *streams_out = streams;
+  *L_out = L;
+  return 0;
+}
+
+extern "C" int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                                              const void* d_baseband, size_t baseband_bytes,
+                                              srtb_b200_detect_result* h_results, float* h_series,
+                                              int copy_all) {
+  if (!ctx || !cfg || !d_baseband || !h_results) return fail(ctx, SRTB_B200_E_INVALID, "process_block: null argument");
+  CK(cudaSetDevice(ctx->device));
+  int streams = 0;
+  size_t L = 0;
+  if (int rc = block_enqueue(ctx, cfg, d_baseband, baseband_bytes, 0, &streams, &L)) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   for (int s = 0; s < streams; s++)
     if (int rc = detect_collect(ctx, s, h_results + s, h_series ? h_series + (size_t)s * SRTB_B200_MAX_BOXCARS * L : nullptr, copy_all))
@@ -832,6 +1091,48 @@ extern "C" int srtb_b200_process_block(srtb_b200_ctx* ctx, const srtb_b200_block
   if (int rc = ensure(ctx, &ctx->d_baseband, &ctx->d_baseband_bytes, baseband_bytes)) return rc;
   CK(cudaMemcpyAsync(ctx->d_baseband, h_baseband, baseband_bytes, cudaMemcpyHostToDevice, ctx->stream));
   return srtb_b200_process_block_device(ctx, cfg, ctx->d_baseband, baseband_bytes, h_results, h_series, copy_all);
+}
+
+// ---- pipelined ingest: the pinned-host ring of SURVEY section 8e -------------------------------
+// submit() copies block k on a dedicated copy stream while block k-1 computes; collect() waits for
+// one block's results. Up to SRTB_B200_RING_SLOTS blocks may be in flight.
+extern "C" int srtb_b200_submit_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                                      const void* h_baseband, size_t baseband_bytes) {
+  if (!ctx || !cfg || !h_baseband) return fail(ctx, SRTB_B200_E_INVALID, "submit_block: null argument");
+  CK(cudaSetDevice(ctx->device));
+  const int slot = (int)(ctx->submit_count % SRTB_B200_RING_SLOTS);
+  if (ctx->slot_busy[slot]) return fail(ctx, SRTB_B200_E_INVALID, "submit_block: ring full, collect a block first");
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) {
+      CK(cudaEventCreateWithFlags(&ctx->slot_h2d[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
+    }
+  }
+  if (int rc = ensure(ctx, &ctx->slot_baseband[slot], &ctx->slot_baseband_bytes[slot], baseband_bytes)) return rc;
+  CK(cudaMemcpyAsync(ctx->slot_baseband[slot], h_baseband, baseband_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CK(cudaEventRecord(ctx->slot_h2d[slot], ctx->copy_stream));
+  CK(cudaStreamWaitEvent(ctx->stream, ctx->slot_h2d[slot], 0));
+  if (int rc = block_enqueue(ctx, cfg, ctx->slot_baseband[slot], baseband_bytes, 4 * (1 + slot), &ctx->slot_streams[slot],
+                             &ctx->slot_L[slot]))
+    return rc;
+  CK(cudaEventRecord(ctx->slot_done[slot], ctx->stream));
+  ctx->slot_busy[slot] = true;
+  const int ticket = (int)(ctx->submit_count & 0x3fffffff);
+  ctx->submit_count++;
+  return ticket;
+}
+
+extern "C" int srtb_b200_collect_block(srtb_b200_ctx* ctx, int ticket, srtb_b200_detect_result* h_results) {
+  if (!ctx || !h_results || ticket < 0) return fail(ctx, SRTB_B200_E_INVALID, "collect_block: bad argument");
+  const int slot = ticket % SRTB_B200_RING_SLOTS;
+  if (!ctx->slot_busy[slot]) return fail(ctx, SRTB_B200_E_INVALID, "collect_block: nothing submitted under this ticket");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->slot_done[slot]));
+  const int streams = ctx->slot_streams[slot];
+  std::memcpy(h_results, ctx->h_res + 4 * (1 + slot), sizeof(srtb_b200_detect_result) * streams);
+  ctx->slot_busy[slot] = false;
+  return streams;
 }
 
 extern "C" const void* srtb_b200_block_spectrum(const srtb_b200_ctx* ctx, int stream) {

@@ -97,6 +97,8 @@ SYMBOLS = {
     "srtb_b200_signal_detect": (_I, [_P, _P, _SZ, _SZ, _SZ, _F, _F, _SZ, C.POINTER(DetectResult), _P, _I]),
     "srtb_b200_process_block": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, C.POINTER(DetectResult), _P, _I]),
     "srtb_b200_process_block_device": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, C.POINTER(DetectResult), _P, _I]),
+    "srtb_b200_submit_block": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ]),
+    "srtb_b200_collect_block": (_I, [_P, _I, C.POINTER(DetectResult)]),
     "srtb_b200_block_spectrum": (_P, [_P, _I]),
 }
 
@@ -215,6 +217,15 @@ class Context:
         res = (DetectResult * 4)()
         fn = self.lib.srtb_b200_process_block_device if on_device else self.lib.srtb_b200_process_block
         n = self._ck(fn(self.h, C.byref(cfg), _ptr(baseband), nbytes, res, _ptr(h_series), int(copy_all)))
+        return [res[i] for i in range(n)]
+
+    def submit_block(self, cfg: BlockConfig, h_baseband, nbytes: int) -> int:
+        """pipelined ingest: H2D on the copy stream overlaps the previous block's compute"""
+        return self._ck(self.lib.srtb_b200_submit_block(self.h, C.byref(cfg), _ptr(h_baseband), nbytes))
+
+    def collect_block(self, ticket: int):
+        res = (DetectResult * 4)()
+        n = self._ck(self.lib.srtb_b200_collect_block(self.h, ticket, res))
         return [res[i] for i in range(n)]
 
     def block_spectrum_ptr(self, stream: int) -> int:

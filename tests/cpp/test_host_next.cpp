@@ -1,0 +1,122 @@
+// CPU-only tests of the SURVEY section 8(f) host pieces: the config loader with its expression grammar
+// (include/srtb/program_options.hpp), the NPY writer, and the file reader's block/overlap arithmetic.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <filesystem>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "srtb/io/npy.hpp"
+#include "srtb/program_options.hpp"
+
+#define CHECK(...)                                                                     \
+  do {                                                                                 \
+    if (!(__VA_ARGS__)) {                                                              \
+      std::fprintf(stderr, "CHECK failed: %s (%s:%d)\n", #__VA_ARGS__, __FILE__, __LINE__); \
+      return 1;                                                                        \
+    }                                                                                  \
+  } while (0)
+
+int main(int argc, char** argv) {
+  using srtb::program_options::parse;
+  // expressions that appear in the shipped cfg files (srtb_config.cfg:2-8, srtb_config_1644-4559.cfg:2-3,26-28)
+  CHECK(parse("2 ** 30") == 1073741824.0);
+  CHECK(parse("2 ** 11") == 2048.0);
+  CHECK(parse("1405 + (64 / 2)") == 1437.0);
+  CHECK(parse("1000 * 1e6") == 1e9);
+  CHECK(parse("128 * 1e6") == 128e6);
+  CHECK(parse("-478.80") == -478.80);
+  CHECK(parse("-64") == -64.0);
+  // grammar: precedence, right-associative **, unary signs, functions, constants, case-insensitive
+  CHECK(parse("1 + 2 * 3") == 7.0);
+  CHECK(parse("(1 + 2) * 3") == 9.0);
+  CHECK(parse("2 ** 3 ** 2") == 512.0);
+  CHECK(parse("-2 ** 2") == 4.0);  // unary minus is a primary: (-2) ** 2
+  CHECK(parse("2 * -3") == -6.0);
+  CHECK(parse("10 / 4") == 2.5);
+  CHECK(std::abs(parse("pi") - M_PI) < 1e-15 && std::abs(parse("PI * 2") - 2 * M_PI) < 1e-15);
+  CHECK(std::abs(parse("e") - M_E) < 1e-15);
+  CHECK(parse("sqrt(16) + abs(-2)") == 6.0);
+  CHECK(parse("max(2, 3) + min(2, 3) + pow(2, 10)") == 1029.0);
+  CHECK(std::abs(parse("atan2(1, 1)") - M_PI / 4) < 1e-15);
+  CHECK(parse("floor(2.7) + ceil(2.1) + log10(1000)") == 8.0);
+  CHECK(parse(" 1.5e3 ") == 1500.0);
+  for (const char* bad : {"", "2 **", "1 +", "(1", "foo", "2 2", "sqrt 4", "max(1)"}) {
+    bool threw = false;
+    try {
+      parse(bad);
+    } catch (const std::invalid_argument&) {
+      threw = true;
+    }
+    CHECK(threw);
+  }
+  // config text with the same keys and expression styles as the J1644 cfg
+  const std::string cfg_text =
+      "# example\n"
+      "baseband_input_count = 2 ** 30\n"
+      "spectrum_channel_count = 2 ** 11\n"
+      "baseband_output_file_prefix = /dev/shm/\n"
+      "log_level = 4\n"
+      "mitigate_rfi_average_method_threshold = 1.5\n"
+      "mitigate_rfi_spectral_kurtosis_threshold = 1.05\n"
+      "signal_detect_signal_noise_threshold = 8\n"
+      "signal_detect_max_boxcar_length = 256\n"
+      "gui_enable = 1\n"
+      "input_file_path = /tmp/buf3.bin   # comment\n"
+      "baseband_input_bits = 2\n"
+      "dm = -478.80\n"
+      "baseband_reserve_sample = 0\n"
+      "baseband_freq_low = 1405 + (64 / 2)\n"
+      "baseband_bandwidth = -64\n"
+      "baseband_sample_rate = 128 * 1e6\n"
+      "mitigate_rfi_freq_list = 1418-1422\n"
+      "udp_receiver_port = 12004, 12005\n"
+      "udp_receiver_address = 10.0.1.2,10.0.1.3\n";
+  auto m = srtb::program_options::parse_config_text(cfg_text);
+  srtb::configs c;
+  srtb::program_options::apply_changed_configs(m, c);
+  CHECK(c.baseband_input_count == (size_t{1} << 30) && c.spectrum_channel_count == 2048);
+  CHECK(c.baseband_input_bits == 2 && c.baseband_freq_low == 1437.0f && c.baseband_bandwidth == -64.0f);
+  CHECK(c.baseband_sample_rate == 128e6f && c.dm == -478.80f && c.baseband_reserve_sample == false);
+  CHECK(c.mitigate_rfi_average_method_threshold == 1.5f && c.mitigate_rfi_spectral_kurtosis_threshold == 1.05f);
+  CHECK(c.signal_detect_signal_noise_threshold == 8.0f && c.signal_detect_max_boxcar_length == 256);
+  CHECK(c.mitigate_rfi_freq_list == "1418-1422" && c.input_file_path == "/tmp/buf3.bin");
+  CHECK(c.baseband_output_file_prefix == "/dev/shm/" && c.gui_enable == true);
+  CHECK(c.udp_receiver_port.size() == 2 && c.udp_receiver_port[1] == 12005);
+  CHECK(c.udp_receiver_address.size() == 2 && c.udp_receiver_address[1] == "10.0.1.3");
+  CHECK(srtb::log::current_level == srtb::log::levels::DEBUG);
+  srtb::log::current_level = srtb::log::levels::WARNING;
+  // command line beats the file; unknown keys are rejected
+  const std::string dir = (argc > 1) ? argv[1] : "/tmp";
+  const std::string cfg_path = dir + "/srtb_test.cfg";
+  {
+    std::ofstream f(cfg_path);
+    f << "dm = 10\nspectrum_channel_count = 2 ** 15\n";
+  }
+  std::string a0 = "prog", a1 = "--config_file_name", a2 = cfg_path, a3 = "--dm=56.778", a4 = "--baseband_input_bits", a5 = "-8";
+  char* av[] = {a0.data(), a1.data(), a2.data(), a3.data(), a4.data(), a5.data()};
+  auto merged = srtb::program_options::parse_arguments(6, av, "does_not_exist.cfg");
+  srtb::configs c2;
+  srtb::program_options::apply_changed_configs(merged, c2);
+  CHECK(c2.dm == 56.778f && c2.spectrum_channel_count == 32768 && c2.baseband_input_bits == -8);
+  bool threw = false;
+  try {
+    srtb::program_options::parse_config_text("no_such_option = 1\n");
+  } catch (const std::invalid_argument&) {
+    threw = true;
+  }
+  CHECK(threw);
+  // NPY writer: header layout numpy accepts (checked again from Python in tests/test_host_abi.py)
+  std::vector<std::complex<float>> spec(6);
+  for (int i = 0; i < 6; i++) spec[i] = {float(i), float(-i)};
+  srtb::io::npy_save(dir + "/srtb_test.npy", spec.data(), {2, 3});
+  std::vector<float> tim = {1.f, 2.f, 3.f};
+  srtb::io::npy_save(dir + "/srtb_test_1d.npy", tim.data(), {3});
+  std::ifstream f(dir + "/srtb_test.npy", std::ios::binary);
+  std::string bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  CHECK(bytes.size() % 8 == 0 && bytes.substr(1, 5) == "NUMPY" && (bytes.size() - 48) % 64 == 0);
+  std::printf("host next ok\n");
+  return 0;
+}

@@ -562,3 +562,34 @@ def test_chain_full_size_properties(ctx):
     res = ctx.process_block(cfg, bb.view(torch.uint8).pin_memory(), n, None)
     assert res[0].zero_count <= C_ // 100
     assert res[0].signal_count[4] > 0                                    # boxcar 16 sees it
+
+
+def test_pipelined_submit_collect_matches_process_block(ctx):
+    """the pinned-ring ingest path (H2D on a copy stream overlapping the previous block's compute)
+    returns exactly what the synchronous call returns, block by block, in order"""
+    n, C_ = 1 << 18, 64
+    cfg = make_block_config(n, -8, srtb_b200.FORMAT_SIMPLE, C_, 0.0, avg_thr=5.0, sk_thr=1.3, snr=6.0)
+    blocks = [torch.from_numpy(synth_baseband(n, seed=s).view(np.uint8).copy()).pin_memory() for s in range(7)]
+    expect = [ctx.process_block(cfg, b, n, None)[0] for b in blocks]
+    got, tickets = [], []
+    for b in blocks:
+        tickets.append(ctx.submit_block(cfg, b, n))
+        if len(tickets) == srtb_b200_ring_slots():
+            got.append(ctx.collect_block(tickets.pop(0))[0])
+    while tickets:
+        got.append(ctx.collect_block(tickets.pop(0))[0])
+    assert len(got) == len(expect)
+    for g, e in zip(got, expect):
+        assert g.zero_count == e.zero_count and g.n_boxcars == e.n_boxcars
+        assert list(g.signal_count[:g.n_boxcars]) == list(e.signal_count[:e.n_boxcars])
+        assert list(g.threshold[:g.n_boxcars]) == list(e.threshold[:e.n_boxcars])
+    # a fourth un-collected submit is refused, not silently overwritten
+    tickets = [ctx.submit_block(cfg, blocks[0], n) for _ in range(srtb_b200_ring_slots())]
+    with pytest.raises(srtb_b200.SrtbError):
+        ctx.submit_block(cfg, blocks[0], n)
+    for t in tickets:
+        ctx.collect_block(t)
+
+
+def srtb_b200_ring_slots():
+    return 3

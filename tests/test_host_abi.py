@@ -86,3 +86,17 @@ def test_cpp_pipe_framework():
     subprocess.run(["make", "-C", str(d), "test_framework"], check=True, capture_output=True)
     r = subprocess.run([str(d / "test_framework")], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "framework ok" in r.stdout, r.stderr
+
+
+def test_cpp_host_next(tmp_path):
+    """SURVEY section 8(f) host pieces: cfg loader + expression grammar, NPY writer (tests/cpp/test_host_next.cpp);
+    the files it writes are read back with numpy"""
+    import numpy as np
+    d = ROOT / "tests" / "cpp"
+    subprocess.run(["make", "-C", str(d), "test_host_next"], check=True, capture_output=True)
+    r = subprocess.run([str(d / "test_host_next"), str(tmp_path)], capture_output=True, text=True, timeout=120,
+                       env={"SRTB_LOG_LEVEL": "1", "PATH": "/usr/bin:/bin"})
+    assert r.returncode == 0 and "host next ok" in r.stdout, r.stderr[-2000:]
+    a = np.load(tmp_path / "srtb_test.npy")
+    assert a.shape == (2, 3) and a.dtype == np.complex64 and a[1, 2] == 5 - 5j
+    assert np.load(tmp_path / "srtb_test_1d.npy").tolist() == [1.0, 2.0, 3.0]

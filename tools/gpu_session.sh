@@ -13,6 +13,6 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${T
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --stage-iters 1 > gpurun_out/ncu_bench_${TAG}.log 2>&1
 # full capture of the FFT pass kernels + the heaviest elementwise kernels of one step
-ncu --set full --clock-control none --import-source on -k regex:'fft_pass_kernel|dedisperse_kernel|r2c_post_kernel|unpack_simple_kernel|sk_kernel|colsum_partial' \
-    -s 40 -c 12 -o gpurun_out/prof_${TAG} -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --stage-iters 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'fft_.*kernel|dedisperse_kernel|r2c_post_kernel|sk_colsum_kernel' \
+    -s 36 -c 16 -o gpurun_out/prof_${TAG} -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --stage-iters 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out | tail -12
