@@ -174,6 +174,8 @@ int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_con
 #define SRTB_B200_RING_SLOTS 3
 int srtb_b200_submit_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
                            const void* h_baseband, size_t baseband_bytes);
+int srtb_b200_submit_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                                  const void* d_baseband, size_t baseband_bytes); /* input already in HBM */
 int srtb_b200_collect_block(srtb_b200_ctx* ctx, int ticket, srtb_b200_detect_result* h_results);
 /* device pointer of stream s's dynamic spectrum after process_block (valid until next call) */
 const void* srtb_b200_block_spectrum(const srtb_b200_ctx* ctx, int stream);

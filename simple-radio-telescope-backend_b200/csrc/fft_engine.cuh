@@ -408,10 +408,21 @@ struct row_tma_smem {
   static constexpr size_t bytes = 2 * (size_t)BUF * sizeof(float2) + 128 + (size_t)(TW + 8) * sizeof(float2);
 };
 
-template <int LOGL, int T, bool FWD>
-__global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOGL, T>::min_blocks)
+// SK = true (process_block only) fuses the next two pipes into the epilogue while a whole row is in
+// the CTA's registers: spectral kurtosis of the transformed row (K14/K15: zero it if flagged) and
+// the detector's partial column sums of the surviving rows (K17 stage 1), one partial row per CTA.
+struct row_sk_params {
+  float thr_lo, thr_hi;   // scaled SK window (spectrum/rfi_mitigation.hpp:300-306)
+  float* partial;         // [gridDim.x][ts_count]
+  unsigned ts_count;      // time samples kept by the detector
+};
+
+template <int LOGL, int T, bool FWD, bool SK = false>
+__global__ void __launch_bounds__(pass_threads<LOGL, T>::value,
+                                  SK ? (pass_threads<LOGL, T>::min_blocks > 2 ? 2 : pass_threads<LOGL, T>::min_blocks)
+                                     : pass_threads<LOGL, T>::min_blocks)
     fft_row_tma_kernel(const float2* __restrict__ in, float2* __restrict__ out, size_t nrows,
-                       const float2* __restrict__ tw) {
+                       const float2* __restrict__ tw, row_sk_params skp) {
   using SC = sched<LOGL>;
   using LAY = tile_layout<LOGL, T, MODE_ROW>;
   constexpr int L = 1 << LOGL, U = L / 8, S = SC::S, BUF = row_tma_smem<LOGL, T>::BUF;
@@ -443,6 +454,11 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
     mbar_expect_tx(&mbar[b], bytes);
     bulk_g2s(b ? buf1 : buf0, in + (row0 << LOGL), bytes, &mbar[b]);
   };
+  float colacc[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) colacc[e] = 0.f;
+  __shared__ float sk_s2[T][(U + 31) / 32], sk_s4[T][(U + 31) / 32];
+  __shared__ int sk_zap[T];
   unsigned tile = blockIdx.x;
   if (tile < ntiles && tid == 0) issue(tile, 0);
   for (unsigned it = 0; tile < ntiles; tile += gridDim.x, it++) {
@@ -491,12 +507,65 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
 #pragma unroll
       for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u + e * U, t)];
       stage_compute<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD, false, 0, false>(v, u, ctw + ((1 << (3 * (S - 1))) - 8) / 7, oidx);
-      if (valid) {
-        float2* o = out + (row << LOGL) + u;
+      if constexpr (SK) {
+        static_assert(!SK || U >= 32, "SK fusion needs at least one warp per row");
+        float pw[8], s2 = 0.f, s4 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; e++) o[e * U] = v[e];
+        for (int e = 0; e < 8; e++) {
+          pw[e] = valid ? (v[e].x * v[e].x + v[e].y * v[e].y) : 0.f;
+          s2 += pw[e];
+          s4 += pw[e] * pw[e];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+        }
+        if ((tid & 31) == 0) {
+          sk_s2[t][u >> 5] = s2;
+          sk_s4[t][u >> 5] = s4;
+        }
+        __syncthreads();
+        if (u == 0) {
+          float a = 0.f, bsum = 0.f;
+          for (int w = 0; w < (U + 31) / 32; w++) {  // fixed order
+            a += sk_s2[t][w];
+            bsum += sk_s4[t][w];
+          }
+          const float sk = (float)L * (bsum / (a * a));
+          sk_zap[t] = (sk > skp.thr_hi || sk < skp.thr_lo) ? 1 : 0;  // NaN (all-zero row): untouched
+        }
+        __syncthreads();
+        const bool zap = sk_zap[t] != 0;
+        if (valid) {
+          float2* o = out + (row << LOGL) + u;
+#pragma unroll
+          for (int e = 0; e < 8; e++) o[e * U] = zap ? make_float2(0.f, 0.f) : v[e];
+          if (!zap) {
+#pragma unroll
+            for (int e = 0; e < 8; e++) colacc[e] += pw[e];
+          }
+        }
+      } else {
+        if (valid) {
+          float2* o = out + (row << LOGL) + u;
+#pragma unroll
+          for (int e = 0; e < 8; e++) o[e * U] = v[e];
+        }
       }
       __syncthreads();  // all reads of buffer b done: it may be refilled from the next iteration on
+    }
+  }
+  if constexpr (SK) {
+    float* const red = reinterpret_cast<float*>(buf0);  // tile buffers are free now
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) red[t * L + u + e * U] = colacc[e];
+    __syncthreads();
+    for (int c = tid; c < L; c += blockDim.x) {
+      float a = 0.f;
+      for (int tt = 0; tt < T; tt++) a += red[tt * L + c];
+      if ((unsigned)c < skp.ts_count) skp.partial[(size_t)blockIdx.x * skp.ts_count + c] = a;
     }
   }
 }
@@ -539,10 +608,20 @@ struct tile_tma_smem {
 // L x T box at (row a*L, column b0) of the 2-D tensor [A*L][B]; ONE TMA box load (per 256 rows) brings
 // it into shared memory in exactly the column-mode layout [idx][t], double buffered across tiles.
 // Stores go straight from registers with the inter-pass twiddle W_{L*B}^{k b} applied.
-template <int LOGL, int T, bool FWD>
+// RAW != 0 (process_block only) fuses the unpack pipe into this first pass of the packed real
+// transform: the tensor map then describes the 8-bit baseband bytes, a tile is L x (T*G) bytes
+// (G = bytes per complex point: 2 for one stream, 4 when two streams share the block) and stage 0
+// converts the two samples at byte offsets o0/o1 of each group to float (K1's integer -> f32 cast,
+// exact) instead of reading complex64 that a separate kernel would have written and this one re-read.
+struct raw_params {
+  int G, o0, o1;
+};
+
+template <int LOGL, int T, bool FWD, int RAW = 0 /* 0 = complex64, 1 = int8 pairs, 2 = uint8 pairs */>
 __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOGL, T>::min_blocks)
     fft_col_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, size_t B,
-                       uint32_t btiles, uint32_t ntiles, big_twiddle btw, const float2* __restrict__ tw) {
+                       uint32_t btiles, uint32_t ntiles, big_twiddle btw, const float2* __restrict__ tw,
+                       raw_params rp) {
   using SC = sched<LOGL>;
   constexpr int L = 1 << LOGL, U = L / 8, S = SC::S, BUF = tile_tma_smem<LOGL, T>::BUF;
   constexpr int ROWS_PER_BOX = (L < 256) ? L : 256;
@@ -550,6 +629,9 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
   float2* const buf0 = reinterpret_cast<float2*>(smraw);
   float2* const buf1 = buf0 + BUF;
   uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  // RAW: buf0 is the exchange buffer, buf1 is carved into two raw-byte tiles of T*L*4 bytes each
+  unsigned char* const raw0 = reinterpret_cast<unsigned char*>(buf1);
+  unsigned char* const raw1 = raw0 + (size_t)BUF * 4;
   float2* const ltw = reinterpret_cast<float2*>(smraw + tile_tma_smem<LOGL, T>::data_bytes + 128);
   float2* const stw = ltw + L;
   const int tid = threadIdx.x;
@@ -564,25 +646,43 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
   __syncthreads();
   auto issue = [&](uint32_t tl, int b) {
     const uint32_t a = tl / btiles, b0 = (tl % btiles) * T;
-    float2* dst = b ? buf1 : buf0;
     fence_proxy_async();
-    mbar_expect_tx(&mbar[b], (uint32_t)(BUF * sizeof(float2)));
+    if constexpr (RAW == 0) {
+      float2* dst = b ? buf1 : buf0;
+      mbar_expect_tx(&mbar[b], (uint32_t)(BUF * sizeof(float2)));
 #pragma unroll
-    for (int r = 0; r < L; r += ROWS_PER_BOX)
-      tma_load_2d(dst + r * T, &tmap, (int)b0, (int)(a * L + r), &mbar[b]);
+      for (int r = 0; r < L; r += ROWS_PER_BOX)
+        tma_load_2d(dst + r * T, &tmap, (int)b0, (int)(a * L + r), &mbar[b]);
+    } else {
+      unsigned char* dst = b ? raw1 : raw0;
+      mbar_expect_tx(&mbar[b], (uint32_t)(BUF * rp.G));
+#pragma unroll
+      for (int r = 0; r < L; r += ROWS_PER_BOX)
+        tma_load_2d(dst + (size_t)r * T * rp.G, &tmap, (int)(b0 * rp.G), (int)(a * L + r), &mbar[b]);
+    }
   };
   uint32_t tile = blockIdx.x;
   if (tile < ntiles && tid == 0) issue(tile, 0);
   for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, it++) {
     const int b = it & 1;
-    float2* const sm = b ? buf1 : buf0;
+    float2* const sm = (RAW == 0) ? (b ? buf1 : buf0) : buf0;
     const uint32_t nxt = tile + gridDim.x;
     if (nxt < ntiles && tid == 0) issue(nxt, b ^ 1);
     mbar_wait(&mbar[b], (it >> 1) & 1);
     float2 v[8];
     int oidx[8];
+    if constexpr (RAW == 0) {
 #pragma unroll
-    for (int e = 0; e < 8; e++) v[e] = sm[(u + e * U) * T + t];
+      for (int e = 0; e < 8; e++) v[e] = sm[(u + e * U) * T + t];
+    } else {
+      const unsigned char* rawb = (b ? raw1 : raw0) + (size_t)t * rp.G;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const unsigned char* g = rawb + (size_t)(u + e * U) * T * rp.G;
+        if (RAW == 1) v[e] = make_float2((float)(int)(signed char)g[rp.o0], (float)(int)(signed char)g[rp.o1]);
+        else v[e] = make_float2((float)g[rp.o0], (float)g[rp.o1]);
+      }
+    }
     stage_compute<LOGL, SC::logr(0), 0, FWD>(v, u, tw, oidx);
     if constexpr (S > 1) {
       __syncthreads();
@@ -729,6 +829,218 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
       for (int e = 0; e < 8; e++) o[(size_t)A * e * U] = v[e];
     }
     __syncthreads();
+  }
+}
+
+
+// ---------------------------------------------------------------------------------
+// Last pass of the packed real transform with the R2C split fused in (process_block only).
+// H = FFT_M(x_even + i x_odd) is produced by this pass in natural order; the split
+//   X_k = F + G w,  X_{M-k} = conj(F - G w),  F = (H_k + conj H_{M-k})/2,  G = -i (H_k - conj H_{M-k})/2
+// needs H_k and H_{M-k} together. With k = k1 + L1*rest + A*kk (A = L1*S) the mirror of
+// (k1, rest, kk) is (L1 - k1, S-1-rest, L-1-kk) for k1 >= 1, so a CTA transforms a primary tile of T
+// consecutive k1 AND its mirror tile (two TMA boxes), exchanges the 2T*L results through shared
+// memory once and writes final X for both. Column k1 = 0 mirrors onto itself with a carry; it is
+// stored raw here and finished by r2c_col0_fixup_kernel, which also completes the mean of |X|^2.
+// ---------------------------------------------------------------------------------
+template <int LOGL, int T>
+struct trans_r2c_smem {
+  static constexpr int L = 1 << LOGL;
+  static constexpr int BUF = 2 * T * (L + 1);  // [2T][L] raw / exchange, reused as [2T][L+1] results
+  static constexpr size_t bytes = 2 * (size_t)BUF * sizeof(float2) + 128 + 2 * (size_t)L * sizeof(float2);
+};
+
+__device__ __forceinline__ float2 r2c_split_twiddle(size_t k, size_t M) {
+  float s, c;
+  if (M <= ((size_t)1 << 25)) {
+    sincospif(-(float)k / (float)M, &s, &c);
+    return make_float2(c, s);
+  }
+  const size_t kh = k >> 12, kl = k & 4095;
+  float s1, c1, s2, c2;
+  sincospif(-(float)kh / (float)(M >> 12), &s1, &c1);
+  sincospif(-(float)kl / (float)M, &s2, &c2);
+  return make_float2(c1 * c2 - s1 * s2, c1 * s2 + s1 * c2);
+}
+
+template <int LOGL, int T>
+__global__ void __launch_bounds__(2 * pass_threads<LOGL, T>::value)
+    fft_trans_r2c_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, uint32_t A,
+                             uint32_t S_, uint32_t L1, uint32_t tiles_per_rest, uint32_t ntiles,
+                             const float2* __restrict__ tw, double* __restrict__ partial) {
+  constexpr bool FWD = true;
+  constexpr int T2 = 2 * T;
+  using SC = sched<LOGL>;
+  using LAY = tile_layout<LOGL, T2, MODE_TRANS>;
+  constexpr int L = 1 << LOGL, U = L / 8, S = SC::S, BUF = trans_r2c_smem<LOGL, T>::BUF, LP = L + 1;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  float2* const buf0 = reinterpret_cast<float2*>(smraw);
+  float2* const buf1 = buf0 + BUF;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  float2* const ltw = reinterpret_cast<float2*>(smraw + 2 * (size_t)BUF * sizeof(float2) + 128);
+  float2* const htw = ltw + L;  // e^{-i pi kk / L}
+  __shared__ double red[32];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < L; i += blockDim.x) {
+    ltw[i] = __ldg(&tw[i]);
+    float sn, cs;
+    sincospif(-(float)i / (float)L, &sn, &cs);
+    htw[i] = make_float2(cs, sn);
+  }
+  const int t0 = tid / U, u0 = tid % U;    // stage 0: lanes along the FFT index
+  const int t1 = tid % T2, u1 = tid / T2;  // later stages: lanes along the 2T sequences
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const size_t M = (size_t)A << LOGL;
+  auto issue = [&](uint32_t tl, int b) {
+    const uint32_t tau = tl % tiles_per_rest, rest = tl / tiles_per_rest;
+    const uint32_t k10 = tau * T;
+    float2* dst = b ? buf1 : buf0;
+    fence_proxy_async();
+    mbar_expect_tx(&mbar[b], (uint32_t)(T2 * L * sizeof(float2)));
+    tma_load_3d(dst, &tmap, 0, (int)rest, (int)k10, &mbar[b]);                                          // primary
+    tma_load_3d(dst + T * L, &tmap, 0, (int)(S_ - 1 - rest), (int)(L1 - k10 - (T - 1)), &mbar[b]);      // mirror
+  };
+  float acc = 0.f;
+  uint32_t tile = blockIdx.x;
+  if (tile < ntiles && tid == 0) issue(tile, 0);
+  for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int b = it & 1;
+    float2* const sm = b ? buf1 : buf0;
+    const uint32_t nxt = tile + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue(nxt, b ^ 1);
+    mbar_wait(&mbar[b], (it >> 1) & 1);
+    float2 v[8];
+    int oidx[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = sm[t0 * L + u0 + e * U];
+    stage_compute<LOGL, SC::logr(0), 0, FWD>(v, u0, tw, oidx);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t0)] = v[e];
+    __syncthreads();
+    if constexpr (S >= 3) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u1 + e * U, t1)];
+      __syncthreads();
+      stage_compute<LOGL, SC::logr(1), SC::logns(1), FWD, true, LOGL - SC::logns(1) - SC::logr(1), false>(v, u1, ltw, oidx);
+#pragma unroll
+      for (int e = 0; e < 8; e++) sm[LAY::at(oidx[e], t1)] = v[e];
+      __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = sm[LAY::at(u1 + e * U, t1)];
+    stage_compute<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD, true, LOGL - SC::logns(S - 1) - SC::logr(S - 1), false>(v, u1, ltw, oidx);
+    __syncthreads();  // exchange buffer fully read: reuse it as the [2T][L+1] result array
+#pragma unroll
+    for (int e = 0; e < 8; e++) sm[t1 * LP + u1 + e * U] = v[e];
+    __syncthreads();
+    {
+      const uint32_t tau = tile % tiles_per_rest, rest = tile / tiles_per_rest;
+      const uint32_t k10 = tau * T;
+      const bool last_tile = (tau == tiles_per_rest - 1);  // k10 == L1/2: only its slot 0 is new work
+      // thread (u1, t1): primary slot t = t1 % T, output indices kk = u1 + e*U for e in [4*(t1/T), 4*(t1/T)+4)
+      const int t = t1 % T, e0 = 4 * (t1 / T);
+      const uint32_t k1 = k10 + t;
+      // w(gk) = e^{-i pi gk / M} with gk = (k1 + L1 rest) + A kk and A/M = 1/L:
+      // one sincospi per thread for the tile-constant factor, e^{-i pi kk / L} from a 2L-point table
+      const float2 wbase = r2c_split_twiddle((size_t)k1 + (size_t)L1 * rest, M);
+#pragma unroll
+      for (int e = e0; e < e0 + 4; e++) {
+        const int kk = u1 + e * U;
+        const float2 hk = sm[t * LP + kk];
+        const float2 hm = sm[(T2 - 1 - t) * LP + (L - 1 - kk)];
+        const size_t gk = (size_t)k1 + (size_t)L1 * rest + (size_t)A * kk;
+        // the self-mirrored column k1 = L1/2 is reached from both (rest, kk) and (S-1-rest, L-1-kk):
+        // take each pair once so the result does not depend on which CTA writes last
+        const bool self_dup = last_tile && (rest > S_ - 1 - rest || (rest == S_ - 1 - rest && 2 * kk >= L));
+        if (k1 == 0) {
+          out[gk] = hk;  // column 0: raw H, finished by the fix-up kernel
+        } else if (!(last_tile && t > 0) && !self_dup) {
+          const float2 F = make_float2(0.5f * (hk.x + hm.x), 0.5f * (hk.y - hm.y));
+          const float2 G = make_float2(0.5f * (hk.y + hm.y), -0.5f * (hk.x - hm.x));
+          const float2 w = c_mul(wbase, htw[kk]);
+          const float2 gw = make_float2(G.x * w.x - G.y * w.y, G.x * w.y + G.y * w.x);
+          const float2 xk = make_float2(F.x + gw.x, F.y + gw.y);
+          const float2 xm = make_float2(F.x - gw.x, -(F.y - gw.y));
+          out[gk] = xk;
+          out[M - gk] = xm;
+          acc += (xk.x * xk.x + xk.y * xk.y) + (xm.x * xm.x + xm.y * xm.y);
+        }
+      }
+    }
+    __syncthreads();  // result array consumed: the buffer may be refilled from the next iteration on
+  }
+  // per-CTA partial of sum |X|^2 (completed by the fix-up kernel)
+  double s = (double)acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0;
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; w++) a += red[w];
+    partial[blockIdx.x] = a;
+  }
+}
+
+// column k1 = 0 of the fused split (indices that are multiples of L1, mirror = M - index), the Nyquist
+// bin, and the final mean of |X_k|^2 over k < M. One pair per thread; the last CTA to finish adds the
+// partials of the fused pass and of this kernel in index order.
+__global__ void __launch_bounds__(256) r2c_col0_fixup_kernel(float2* __restrict__ H, size_t M, size_t L1,
+                                                              double* __restrict__ partial, unsigned nparts,
+                                                              unsigned* __restrict__ ticket,
+                                                              float* __restrict__ mean_out) {
+  __shared__ double red[8];
+  __shared__ bool last;
+  const size_t n = M / L1;  // column length; pairs j <-> n - j
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (j <= n / 2) {
+    const size_t k = j * L1;
+    const float2 hk = H[k];
+    const float2 hm = (k == 0) ? hk : H[M - k];
+    const float2 F = make_float2(0.5f * (hk.x + hm.x), 0.5f * (hk.y - hm.y));
+    const float2 G = make_float2(0.5f * (hk.y + hm.y), -0.5f * (hk.x - hm.x));
+    const float2 w = r2c_split_twiddle(k, M);
+    const float2 gw = make_float2(G.x * w.x - G.y * w.y, G.x * w.y + G.y * w.x);
+    const float2 xk = make_float2(F.x + gw.x, F.y + gw.y);
+    const float2 xm = make_float2(F.x - gw.x, -(F.y - gw.y));
+    H[k] = xk;
+    H[M - k] = xm;
+    const float wm = (k == 0 || 2 * k == M) ? 0.f : 1.f;
+    acc = (double)((xk.x * xk.x + xk.y * xk.y) + wm * (xm.x * xm.x + xm.y * xm.y));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0;
+    for (int w = 0; w < 8; w++) a += red[w];
+    partial[nparts + blockIdx.x] = a;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    double a = 0.0;
+    for (unsigned i = threadIdx.x; i < nparts + gridDim.x; i += blockDim.x) a += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; w++) t += red[w];
+      *mean_out = (float)t / (float)M;
+      *ticket = 0;
+    }
   }
 }
 

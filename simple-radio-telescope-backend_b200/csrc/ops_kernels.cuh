@@ -767,19 +767,19 @@ __global__ void __launch_bounds__(256) sk_colsum_kernel(float2* __restrict__ x, 
 }
 
 // K17 stage 2 + K16: ts[j] = sum over chunks (fixed order), zero_count.
-// CTA = 32 columns x 8 chunk groups: coalesced along time, tree over the groups in shared memory.
-__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial,
-                                                           size_t ts_count, size_t chunks,
-                                                           float* __restrict__ ts,
-                                                           const float2* __restrict__ x,
-                                                           size_t time_count, size_t chan_count,
-                                                           detect_dev_result* __restrict__ res) {
-  __shared__ float sm[8][33];
+// CTA = 32 columns x 32 chunk groups: coalesced along time, fixed-order tree over the groups.
+__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ partial,
+                                                            size_t ts_count, size_t chunks,
+                                                            float* __restrict__ ts,
+                                                            const float2* __restrict__ x,
+                                                            size_t time_count, size_t chan_count,
+                                                            detect_dev_result* __restrict__ res) {
+  __shared__ float sm[32][33];
   const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const size_t j = (size_t)blockIdx.x * 32 + lx;
   float a = 0.f;
   if (j < ts_count) {
-    const size_t per = (chunks + 7) / 8;
+    const size_t per = (chunks + 31) / 32;
     const size_t c0 = (size_t)ly * per, c1 = min(c0 + per, chunks);
     for (size_t c = c0; c < c1; c++) a += partial[c * ts_count + j];
   }
@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
   if (ly == 0 && j < ts_count) {
     float t = sm[0][lx];
 #pragma unroll
-    for (int g = 1; g < 8; g++) t += sm[g][lx];
+    for (int g = 1; g < 32; g++) t += sm[g][lx];
     ts[j] = t;
   }
   // K16: channels whose first sample is zero; every CTA takes a slice, integer atomics (exact)

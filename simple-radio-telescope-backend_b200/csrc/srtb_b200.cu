@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -348,9 +349,12 @@ template <int LOGL>
 struct row_t {
   static constexpr int value = (LOGL >= 11) ? 1 : (1 << (11 - LOGL));
 };
+#ifndef SRTB_COL_T
+#define SRTB_COL_T 16
+#endif
 template <int LOGL>
 struct col_t {
-  static constexpr int value = (LOGL <= 8) ? 16 : 8;
+  static constexpr int value = (LOGL <= 8) ? SRTB_COL_T : ((SRTB_COL_T < 8) ? SRTB_COL_T : 8);
 };
 
 template <int LOGL, bool FWD>
@@ -372,7 +376,7 @@ static int launch_row(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t 
     if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
     const size_t ntiles = (nrows + T - 1) / T;
     const unsigned grid = (unsigned)std::min<size_t>(ntiles, (size_t)ctx->sm_count * ctx->occupancy[key]);
-    kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(in, out, nrows, tw);
+    kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(in, out, nrows, tw, row_sk_params{});
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -406,13 +410,14 @@ static encode_tiled_fn get_encode_tiled() {
 
 // complex64 elements are described to TMA as 8-byte integers; dims/box are innermost first
 static bool make_tensor_map(tensor_map_blob* out, const void* base, int rank, const cuuint64_t* dims,
-                            const cuuint64_t* strides_bytes /* rank-1 */, const cuuint32_t* box) {
+                            const cuuint64_t* strides_bytes /* rank-1 */, const cuuint32_t* box,
+                            CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_INT64) {
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return false;
   static_assert(sizeof(CUtensorMap) <= sizeof(tensor_map_blob), "tensor map size");
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
-  const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_INT64, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+  const CUresult r = enc(&m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return false;
@@ -428,7 +433,7 @@ static int persistent_grid(srtb_b200_ctx* ctx, K kern, int threads, size_t smem,
     // the attribute is set once per kernel: use the largest size any later launch can ask for
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     int per_sm = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem_max));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     ctx->occupancy[key] = std::max(1, per_sm);
     ctx->configured.insert(key);
   }
@@ -455,11 +460,56 @@ static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, siz
   const size_t ntiles = A * (B / T);
   unsigned grid = 1;
   if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
-  kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw);
+  kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, raw_params{});
   ctx->launches++;
   CK(cudaGetLastError());
   *done = true;
   return 0;
+}
+
+// first pass of the packed real transform straight from the 8-bit baseband (unpack fused in)
+struct raw_source {
+  const void* base = nullptr;  // device pointer to the block's bytes
+  int G = 0, o0 = 0, o1 = 0;   // bytes per complex point, byte offsets of its two samples
+  bool is_signed = true;
+};
+
+template <int LOGL, int RAW>
+static int launch_col_tma_raw(srtb_b200_ctx* ctx, const raw_source& src, float2* out, size_t B, bool* done) {
+  constexpr int T = col_t<LOGL>::value, L = 1 << LOGL;
+  *done = false;
+  if ((reinterpret_cast<uintptr_t>(src.base) & 15u) || B >= ((size_t)1 << 29)) return 0;
+  tensor_map_blob tm;
+  const cuuint64_t dims[2] = {(cuuint64_t)B * src.G, (cuuint64_t)L};
+  const cuuint64_t strides[1] = {(cuuint64_t)B * src.G};
+  const cuuint32_t box[2] = {(cuuint32_t)(T * src.G), (cuuint32_t)std::min(L, 256)};
+  if (!make_tensor_map(&tm, src.base, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_UINT8)) return 0;
+  big_twiddle btw;
+  if (int rc = get_big_twiddles(ctx, LOGL + ilog2(B), &btw)) return rc;
+  const float2* tw = nullptr;
+  if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+  auto kern = fft_col_tma_kernel<LOGL, T, true, RAW>;
+  const size_t smem = tile_tma_smem<LOGL, T>::bytes(btw.q);
+  const size_t ntiles = B / T;
+  unsigned grid = 1;
+  if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
+  kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
+                                                                raw_params{src.G, src.o0, src.o1});
+  ctx->launches++;
+  CK(cudaGetLastError());
+  *done = true;
+  return 0;
+}
+
+static int dispatch_col_raw(srtb_b200_ctx* ctx, int logl, const raw_source& src, float2* out, size_t B, bool* done) {
+  *done = false;
+  switch (logl) {
+    case 7: return src.is_signed ? launch_col_tma_raw<7, 1>(ctx, src, out, B, done) : launch_col_tma_raw<7, 2>(ctx, src, out, B, done);
+    case 8: return src.is_signed ? launch_col_tma_raw<8, 1>(ctx, src, out, B, done) : launch_col_tma_raw<8, 2>(ctx, src, out, B, done);
+    case 9: return src.is_signed ? launch_col_tma_raw<9, 1>(ctx, src, out, B, done) : launch_col_tma_raw<9, 2>(ctx, src, out, B, done);
+    case 10: return src.is_signed ? launch_col_tma_raw<10, 1>(ctx, src, out, B, done) : launch_col_tma_raw<10, 2>(ctx, src, out, B, done);
+    default: return 0;
+  }
 }
 
 template <int LOGL, bool FWD>
@@ -643,11 +693,99 @@ extern "C" int srtb_b200_fft_r2c_inplace(srtb_b200_ctx* ctx, float* d_inout, siz
   return 0;
 }
 
+// launch of the fused last pass + split (LOGL <= 8 keeps two [2T][L] tiles double-buffered in smem)
+template <int LOGL>
+static int launch_trans_r2c(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t L1, bool* done) {
+  constexpr int T = 8, L = 1 << LOGL;
+  *done = false;
+  const size_t S = A / L1;
+  if ((reinterpret_cast<uintptr_t>(in) & 15u) || L1 < 4 * T || L1 >= ((size_t)1 << 31)) return 0;
+  tensor_map_blob tm;
+  const cuuint64_t dims[3] = {(cuuint64_t)L, (cuuint64_t)S, (cuuint64_t)L1};
+  const cuuint64_t strides[2] = {(cuuint64_t)L * sizeof(float2), (cuuint64_t)S * L * sizeof(float2)};
+  const cuuint32_t box[3] = {(cuuint32_t)L, 1u, (cuuint32_t)T};
+  if (!make_tensor_map(&tm, in, 3, dims, strides, box)) return 0;
+  const float2* tw = nullptr;
+  if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+  auto kern = fft_trans_r2c_tma_kernel<LOGL, T>;
+  constexpr size_t smem = trans_r2c_smem<LOGL, T>::bytes;
+  const size_t tiles_per_rest = L1 / (2 * T) + 1, ntiles = S * tiles_per_rest;
+  unsigned grid = 1;
+  if (int rc = persistent_grid(ctx, kern, 2 * pass_threads<LOGL, T>::value, smem, smem, ntiles, &grid)) return rc;
+  grid = std::min<unsigned>(grid, 2048);
+  kern<<<grid, 2 * pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
+                                                                      (uint32_t)tiles_per_rest, (uint32_t)ntiles, tw,
+                                                                      ctx->partial);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  {
+    const size_t pairs = ((A << LOGL) / L1) / 2 + 1;
+    const unsigned fgrid = (unsigned)((pairs + 255) / 256);
+    if (grid + fgrid > 4096) return fail(ctx, SRTB_B200_E_SIZE, "r2c: partial buffer too small");
+    r2c_col0_fixup_kernel<<<fgrid, 256, 0, ctx->stream>>>(out, A << LOGL, L1, ctx->partial, grid, ctx->ticket, ctx->mean);
+  }
+  ctx->launches++;
+  CK(cudaGetLastError());
+  *done = true;
+  return 0;
+}
+
 // R2C whose split pass also leaves mean(|X_k|^2, k < N/2) in ctx->mean (used by process_block:
-// the s1 statistic costs no extra sweep)
-static int fft_r2c_with_power_mean(srtb_b200_ctx* ctx, float* d_inout, size_t n_real) {
+// the s1 statistic costs no extra sweep). For multi-pass sizes the split is fused into the last FFT
+// pass (fft_trans_r2c_tma_kernel), so the packed transform costs P sweeps instead of P + 1.
+static int fft_r2c_with_power_mean(srtb_b200_ctx* ctx, float* d_inout, size_t n_real, const raw_source* raw = nullptr,
+                                   bool* raw_used = nullptr) {
+  if (raw_used) *raw_used = false;
   const size_t M = n_real / 2;
   float2* H = reinterpret_cast<float2*>(d_inout);
+  const int q = ilog2(M);
+  if (q >= 13 && q <= 30 && M >= 2) {
+    // same factorisation as fft_c2c_impl
+    int l1, l2, l3 = 0;
+    if (q <= 20) {
+      l1 = (q + 1) / 2;
+      l2 = q - l1;
+    } else {
+      l1 = (q + 2) / 3;
+      l2 = (q - l1 + 1) / 2;
+      l3 = q - l1 - l2;
+    }
+    const int llast = l3 ? l3 : l2;
+    if (llast >= 6 && llast <= 8 && get_encode_tiled()) {
+      if (int rc = ensure(ctx, &ctx->fft_scratch, &ctx->fft_scratch_bytes, M * sizeof(float2))) return rc;
+      float2* s = static_cast<float2*>(ctx->fft_scratch);
+      const size_t L1 = (size_t)1 << l1, L2 = (size_t)1 << l2, L3 = (size_t)1 << l3;
+      bool first_done = false;
+      if (raw && raw->base) {
+        // unpack fused into the first pass: the float buffer is not even written by an unpack kernel
+        if (int rc = dispatch_col_raw(ctx, l1, *raw, s, l3 ? L2 * L3 : L2, &first_done)) return rc;
+        if (raw_used) *raw_used = first_done;
+        if (!first_done) return SRTB_B200_E_UNSUPPORTED;  // caller unpacks and retries without `raw`
+      }
+      if (!first_done)
+        if (int rc = dispatch_col<true>(ctx, l1, H, s, 1, l3 ? L2 * L3 : L2)) return rc;
+      if (l3)
+        if (int rc = dispatch_col<true>(ctx, l2, s, s, L1, L3)) return rc;
+      const size_t A = l3 ? L1 * L2 : L1;
+      bool done = false;
+      int rc = 0;
+      switch (llast) {
+        case 6: rc = launch_trans_r2c<6>(ctx, s, H, A, L1, &done); break;
+        case 7: rc = launch_trans_r2c<7>(ctx, s, H, A, L1, &done); break;
+        default: rc = launch_trans_r2c<8>(ctx, s, H, A, L1, &done); break;
+      }
+      if (rc) return rc;
+      if (done) return 0;
+      // tensor map refused: finish with the plain last pass + split kernel
+      if (int rc2 = dispatch_trans<true>(ctx, llast, s, H, 1, A, L1)) return rc2;
+      const unsigned grid = std::min<unsigned>(grid_for(ctx, M / 2 + 1, 256), 4096);
+      r2c_post_kernel<true><<<grid, 256, 0, ctx->stream>>>(H, M, ctx->partial, ctx->ticket, ctx->mean);
+      ctx->launches++;
+      CK(cudaGetLastError());
+      return 0;
+    }
+  }
+  if (raw && raw->base) return SRTB_B200_E_UNSUPPORTED;  // fused unpack needs the multi-pass TMA route
   if (int rc = fft_c2c_impl<true>(ctx, H, M, 1)) return rc;
   const unsigned grid = std::min<unsigned>(grid_for(ctx, M / 2 + 1, 256), 4096);
   r2c_post_kernel<true><<<grid, 256, 0, ctx->stream>>>(H, M, ctx->partial, ctx->ticket, ctx->mean);
@@ -874,7 +1012,7 @@ static int detect_prepare(srtb_b200_ctx* ctx, int slot, size_t time_count, size_
 // column-sum reduction over `chunks` partial rows, zero count, scan, boxcar ladder
 static int detect_tail(srtb_b200_ctx* ctx, int slot, const float2* x, size_t time_count, size_t chan_count,
                        size_t ts_count, size_t chunks, float snr, float chan_thr, size_t max_boxcar) {
-  colsum_final_kernel<<<(unsigned)((ts_count + 31) / 32), 256, 0, ctx->stream>>>(
+  colsum_final_kernel<<<(unsigned)((ts_count + 31) / 32), 1024, 0, ctx->stream>>>(
       ctx->colsum_partial, ts_count, chunks, ctx->series[slot], x, time_count, chan_count, ctx->d_res + slot);
   ctx->launches++;
   CK(cudaGetLastError());
@@ -908,6 +1046,56 @@ static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t 
   colsum_partial_kernel<<<g, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, ctx->colsum_partial);
   ctx->launches++;
   CK(cudaGetLastError());
+  return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
+}
+
+// watfft (backward C2C of every channel row) with spectral kurtosis + the detector's partial column
+// sums fused into its epilogue: the dynamic spectrum is written once and not read again until the
+// candidate sink. Used by process_block when one CTA holds a whole row (L = 512 .. 4096).
+template <int LOGL>
+static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, float lo_, float hi_, size_t ts_count,
+                            size_t* chunks_out) {
+  constexpr int T = row_t<LOGL>::value;
+  auto kern = fft_row_tma_kernel<LOGL, T, false, true>;
+  constexpr size_t smem = row_tma_smem<LOGL, T>::bytes;
+  const size_t ntiles = (chan_count + T - 1) / T;
+  unsigned grid = 1;
+  if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, smem, ntiles, &grid)) return rc;
+  {
+    size_t have = ctx->colsum_partial_elems * sizeof(float);
+    if (int rc = ensure(ctx, reinterpret_cast<void**>(&ctx->colsum_partial), &have, (size_t)grid * ts_count * sizeof(float)))
+      return rc;
+    ctx->colsum_partial_elems = have / sizeof(float);
+  }
+  const float2* tw = nullptr;
+  if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+  row_sk_params p{lo_, hi_, ctx->colsum_partial, (unsigned)ts_count};
+  kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(x, x, chan_count, tw, p);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  *chunks_out = grid;
+  return 0;
+}
+
+static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_t time_count, size_t chan_count,
+                                  size_t time_reserved_count, float sk_threshold, float snr, float chan_thr,
+                                  size_t max_boxcar) {
+  const size_t ts_count = (time_count <= time_reserved_count) ? time_count : time_count - time_reserved_count;
+  if (int rc = detect_prepare(ctx, slot, time_count, 1)) return rc;
+  CK(cudaMemsetAsync(ctx->d_res + slot, 0, sizeof(detect_dev_result), ctx->stream));
+  const float M_ = static_cast<float>(time_count);
+  float hi = sk_threshold, lo = 2 - sk_threshold;
+  if (lo > hi) std::swap(lo, hi);
+  const float lo_ = lo * ((M_ - 1) / (M_ + 1)) + 1, hi_ = hi * ((M_ - 1) / (M_ + 1)) + 1;
+  size_t chunks = 0;
+  int rc = 0;
+  switch (ilog2(time_count)) {
+    case 9: rc = watfft_sk_launch<9>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks); break;
+    case 10: rc = watfft_sk_launch<10>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks); break;
+    case 11: rc = watfft_sk_launch<11>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks); break;
+    default: rc = watfft_sk_launch<12>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks); break;
+  }
+  if (rc) return rc;
   return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
 }
 
@@ -1014,9 +1202,37 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
       if (e != cudaSuccess) return fail(ctx, SRTB_B200_E_NOMEM, "process_block: stream buffer alloc failed");
     }
   ctx->stream_buf_elems = N + 2;
-  if (int rc = srtb_b200_unpack(ctx, d_baseband, baseband_bytes, cfg->baseband_input_bits, cfg->baseband_format,
-                                cfg->window, ctx->stream_buf, N))
-    return rc;
+  // unpack: fused into the first FFT pass when the samples are 8-bit and every complex point of a
+  // stream is one fixed-size byte group (simple, "1 1 2 2", "1 2 1 2"); otherwise the unpack kernel
+  raw_source raw[4];
+  bool fuse_unpack = false;
+  {
+    const int bits = cfg->baseband_input_bits;
+    const int fmt = cfg->baseband_format;
+    if ((bits == 8 || bits == -8) && cfg->window == SRTB_B200_WINDOW_RECTANGLE && N >= ((size_t)1 << 14) &&
+        (fmt == SRTB_B200_FORMAT_SIMPLE || fmt == SRTB_B200_FORMAT_NAOCPSR_SNAP1 ||
+         fmt == SRTB_B200_FORMAT_INTERLEAVED_2) &&
+        baseband_bytes >= N * (size_t)streams && get_encode_tiled() && !std::getenv("SRTB_B200_NO_FUSED_UNPACK")) {
+      fuse_unpack = true;
+      for (int s = 0; s < streams; s++) {
+        raw[s].base = d_baseband;
+        raw[s].is_signed = (bits < 0);
+        raw[s].G = 2 * streams;
+        if (fmt == SRTB_B200_FORMAT_SIMPLE) { raw[s].o0 = 0; raw[s].o1 = 1; }
+        else if (fmt == SRTB_B200_FORMAT_NAOCPSR_SNAP1 && bits == -8) { raw[s].o0 = 2 * s; raw[s].o1 = 2 * s + 1; }
+        else { raw[s].o0 = s; raw[s].o1 = s + 2; }
+      }
+    }
+  }
+  bool unpacked = false;
+  auto ensure_unpacked = [&]() -> int {
+    if (unpacked) return 0;
+    unpacked = true;
+    return srtb_b200_unpack(ctx, d_baseband, baseband_bytes, cfg->baseband_input_bits, cfg->baseband_format,
+                            cfg->window, ctx->stream_buf, N);
+  };
+  if (!fuse_unpack)
+    if (int rc = ensure_unpacked()) return rc;
   const size_t Nc = N / 2;
   const size_t batch = std::min<size_t>(cfg->spectrum_channel_count, Nc);  // fft_pipe.hpp:318-320
   if (batch == 0 || !is_pow2(batch)) return fail(ctx, SRTB_B200_E_SIZE, "spectrum_channel_count must be a power of 2");
@@ -1040,11 +1256,29 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
                           batch;
   for (int s = 0; s < streams; s++) {
     float* buf = ctx->stream_buf[s];
-    if (int rc = fft_r2c_with_power_mean(ctx, buf, N)) return rc;
+    {
+      int rc = SRTB_B200_E_UNSUPPORTED;
+      if (fuse_unpack && !unpacked) rc = fft_r2c_with_power_mean(ctx, buf, N, &raw[s], nullptr);
+      if (rc == SRTB_B200_E_UNSUPPORTED) {
+        // this size/alignment cannot take the fused route: unpack all streams once, then the plain R2C
+        if (int rc2 = ensure_unpacked()) return rc2;
+        rc = fft_r2c_with_power_mean(ctx, buf, N);
+      }
+      if (rc) return rc;
+    }
     if (int rc = rfi_s1_dedisperse_fused(ctx, reinterpret_cast<float2*>(buf), Nc,
                                          cfg->mitigate_rfi_average_method_threshold, coef, bins, f_min, f_c, df, cfg->dm,
                                          /*mean_ready=*/true))
       return rc;
+    if (sk_detect_fusable(L) && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0) {
+      // waterfall FFT + SK + partial column sums in one kernel, then the small detector tail
+      if (int rc = watfft_sk_detect_fused(ctx, s, reinterpret_cast<float2*>(buf), L, batch, reserved,
+                                          cfg->mitigate_rfi_spectral_kurtosis_threshold,
+                                          cfg->signal_detect_signal_noise_threshold,
+                                          cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length))
+        return rc;
+      continue;
+    }
     if (int rc = srtb_b200_watfft_c2c_backward(ctx, buf, L, batch)) return rc;
     if (sk_detect_fusable(L)) {
       if (int rc = sk_detect_fused(ctx, s, reinterpret_cast<float2*>(buf), L, batch, reserved,
@@ -1106,7 +1340,7 @@ extern "C" int srtb_b200_submit_block(srtb_b200_ctx* ctx, const srtb_b200_block_
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) {
       CK(cudaEventCreateWithFlags(&ctx->slot_h2d[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
+      if (!ctx->slot_done[i]) CK(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
     }
   }
   if (int rc = ensure(ctx, &ctx->slot_baseband[slot], &ctx->slot_baseband_bytes[slot], baseband_bytes)) return rc;
@@ -1114,6 +1348,27 @@ extern "C" int srtb_b200_submit_block(srtb_b200_ctx* ctx, const srtb_b200_block_
   CK(cudaEventRecord(ctx->slot_h2d[slot], ctx->copy_stream));
   CK(cudaStreamWaitEvent(ctx->stream, ctx->slot_h2d[slot], 0));
   if (int rc = block_enqueue(ctx, cfg, ctx->slot_baseband[slot], baseband_bytes, 4 * (1 + slot), &ctx->slot_streams[slot],
+                             &ctx->slot_L[slot]))
+    return rc;
+  CK(cudaEventRecord(ctx->slot_done[slot], ctx->stream));
+  ctx->slot_busy[slot] = true;
+  const int ticket = (int)(ctx->submit_count & 0x3fffffff);
+  ctx->submit_count++;
+  return ticket;
+}
+
+// same ring, input already on the device (no copy): lets a device-resident producer keep the GPU fed
+extern "C" int srtb_b200_submit_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                                             const void* d_baseband, size_t baseband_bytes) {
+  if (!ctx || !cfg || !d_baseband) return fail(ctx, SRTB_B200_E_INVALID, "submit_block_device: null argument");
+  CK(cudaSetDevice(ctx->device));
+  const int slot = (int)(ctx->submit_count % SRTB_B200_RING_SLOTS);
+  if (ctx->slot_busy[slot]) return fail(ctx, SRTB_B200_E_INVALID, "submit_block: ring full, collect a block first");
+  if (!ctx->slot_done[slot]) {
+    for (int i = 0; i < SRTB_B200_RING_SLOTS; i++)
+      if (!ctx->slot_done[i]) CK(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
+  }
+  if (int rc = block_enqueue(ctx, cfg, d_baseband, baseband_bytes, 4 * (1 + slot), &ctx->slot_streams[slot],
                              &ctx->slot_L[slot]))
     return rc;
   CK(cudaEventRecord(ctx->slot_done[slot], ctx->stream));

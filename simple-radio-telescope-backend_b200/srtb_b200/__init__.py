@@ -11,7 +11,7 @@ import os
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE.parent / "csrc" / "libsrtb_b200.so"
+LIB_PATH = _HERE.parent / "csrc" / os.environ.get("SRTB_B200_LIB", "libsrtb_b200.so")  # experiments may build variants
 
 FORMAT_SIMPLE, FORMAT_INTERLEAVED_2, FORMAT_NAOCPSR_SNAP1, FORMAT_GZNUPSR_A1_2, FORMAT_GZNUPSR_A1_4 = range(5)
 WINDOW_RECTANGLE, WINDOW_HANN, WINDOW_HAMMING = range(3)
@@ -98,6 +98,7 @@ SYMBOLS = {
     "srtb_b200_process_block": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, C.POINTER(DetectResult), _P, _I]),
     "srtb_b200_process_block_device": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, C.POINTER(DetectResult), _P, _I]),
     "srtb_b200_submit_block": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ]),
+    "srtb_b200_submit_block_device": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ]),
     "srtb_b200_collect_block": (_I, [_P, _I, C.POINTER(DetectResult)]),
     "srtb_b200_block_spectrum": (_P, [_P, _I]),
 }
@@ -222,6 +223,9 @@ class Context:
     def submit_block(self, cfg: BlockConfig, h_baseband, nbytes: int) -> int:
         """pipelined ingest: H2D on the copy stream overlaps the previous block's compute"""
         return self._ck(self.lib.srtb_b200_submit_block(self.h, C.byref(cfg), _ptr(h_baseband), nbytes))
+
+    def submit_block_device(self, cfg: BlockConfig, d_baseband, nbytes: int) -> int:
+        return self._ck(self.lib.srtb_b200_submit_block_device(self.h, C.byref(cfg), _ptr(d_baseband), nbytes))
 
     def collect_block(self, ticket: int):
         res = (DetectResult * 4)()

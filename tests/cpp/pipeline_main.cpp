@@ -22,9 +22,12 @@
 #include "srtb/pipeline/framework/composite_pipe.hpp"
 #include "srtb/pipeline/framework/pipe.hpp"
 #include "srtb/pipeline/framework/pipe_io.hpp"
+#include "srtb/pipeline/read_file_pipe.hpp"
 #include "srtb/pipeline/rfi_mitigation_pipe.hpp"
 #include "srtb/pipeline/signal_detect_pipe.hpp"
 #include "srtb/pipeline/unpack_pipe.hpp"
+#include "srtb/pipeline/write_signal_pipe.hpp"
+#include "srtb/program_options.hpp"
 #include "srtb/work.hpp"
 
 namespace {
@@ -32,7 +35,9 @@ namespace {
 struct sink_out_functor {
   std::shared_ptr<std::atomic<int>> done;
   std::string dump_prefix;
-  void operator()(std::stop_token, srtb::work::write_signal_work w) {
+  std::shared_ptr<srtb::pipeline::write_signal_pipe> writer;  // candidate sink (.bin/.npy/.tim), optional
+  void operator()(std::stop_token st, srtb::work::write_signal_work w) {
+    if (writer) (*writer)(st, w);
     std::string line = "{\"stream\": " + std::to_string(w.data_stream_id) + ", \"block\": " +
                        std::to_string(w.udp_packet_counter) + ", \"count\": " + std::to_string(w.count) +
                        ", \"batch_size\": " + std::to_string(w.batch_size) + ", \"zero_count\": " +
@@ -83,8 +88,17 @@ int main(int argc, char** argv) {
   cfg.mitigate_rfi_freq_list = arg(argc, argv, "--freq-list", "");
   cfg.signal_detect_signal_noise_threshold = std::atof(arg(argc, argv, "--snr", "6"));
   cfg.signal_detect_max_boxcar_length = std::strtoull(arg(argc, argv, "--max-boxcar", "64"), nullptr, 10);
-  const std::string input = arg(argc, argv, "--input", "");
+  // a reference-style config file (expressions and all) overrides the flags above
+  const std::string cfg_file = arg(argc, argv, "--config_file_name", "");
+  if (!cfg_file.empty()) {
+    std::string a0 = argv[0], a1 = "--config_file_name", a2 = cfg_file;
+    char* av[] = {a0.data(), a1.data(), a2.data()};
+    srtb::program_options::apply_changed_configs(srtb::program_options::parse_arguments(3, av, cfg_file), cfg);
+  }
+  const std::string input = cfg.input_file_path.empty() ? arg(argc, argv, "--input", "") : cfg.input_file_path;
+  cfg.input_file_path = input;
   const std::string dump = arg(argc, argv, "--dump-prefix", "");
+  const bool write_candidates = std::atoi(arg(argc, argv, "--write-candidates", "0")) != 0;
   const bool composite = std::atoi(arg(argc, argv, "--composite", "0")) != 0;
   if (input.empty()) {
     std::fprintf(stderr, "usage: pipeline_main --input <file> [--log2n 20 --bits -8 --format simple ...]\n");
@@ -109,7 +123,8 @@ int main(int argc, char** argv) {
   auto s2_q = std::make_shared<srtb::work_queue<rfi_mitigation_s2_work>>();
   auto det_q = std::make_shared<srtb::work_queue<signal_detect_work>>();
   auto done = std::make_shared<std::atomic<int>>(0);
-  sink_out_functor sink{done, dump};
+  sink_out_functor sink{done, dump, nullptr};
+  if (write_candidates) sink.writer = std::make_shared<write_signal_pipe>(q);
 
   std::vector<std::jthread> threads;
   threads.push_back(start_pipe<copy_to_device_pipe>(queue_in_functor{copy_q}, queue_out_functor{unpack_q}, q));
@@ -130,26 +145,14 @@ int main(int argc, char** argv) {
     threads.push_back(start_pipe<chain>(queue_in_functor{r2c_q}, sink, q));
   }
 
-  // source: the reference's read_file_pipe in miniature (pinned host block, zero padded tail)
-  std::ifstream f(input, std::ios::binary);
-  if (!f) {
-    std::fprintf(stderr, "cannot open %s\n", input.c_str());
-    return 2;
-  }
+  // source: read_file_pipe (pinned host block, zero padded tail, overlap-save rewind by nsamps_reserved)
+  read_file_pipe reader;
   int blocks = 0;
-  while (true) {
-    auto h = srtb::host_allocator.allocate_shared<std::byte>(block_bytes);
-    std::memset(h.get(), 0, block_bytes);
-    f.read(reinterpret_cast<char*>(h.get()), (std::streamsize)block_bytes);
-    if (f.gcount() <= 0) break;
-    copy_to_device_work w;
-    w.count = block_bytes;
-    w.udp_packet_counter = (uint64_t)blocks;
-    w.data_stream_id = 0;
-    w.baseband_data = {h, block_bytes};
-    copy_q->push(w);
+  while (auto w = reader(std::stop_token{}, srtb::work::dummy_work{})) {
+    w->udp_packet_counter = (uint64_t)blocks;  // deterministic file names / JSON keys for the test
+    while (copy_q->read_available() >= 2) std::this_thread::sleep_for(std::chrono::microseconds(50));
+    copy_q->push(*w);
     blocks++;
-    if ((size_t)f.gcount() < block_bytes) break;
   }
   while (done->load() < blocks * (int)streams) std::this_thread::sleep_for(std::chrono::milliseconds(1));
   for (auto& t : threads) t.request_stop();

@@ -111,3 +111,70 @@ def test_pipeline_dual_pol_fanout(tmp_path, oracle):
     assert sorted((w["block"], w["stream"]) for w in works) == [(0, 0), (0, 1)]
     for w in works:
         _check_work(w, prefix, (a, b)[w["stream"]], oracle, n, C_, dm)
+
+
+def test_pipeline_cfg_file_reader_overlap_and_candidate_sink(tmp_path, oracle):
+    """the pipeline driven by a reference-style .cfg (expression values), fed by
+    read_file_pipe (overlap-save rewind) and drained by write_signal_pipe (.bin/.npy/.tim)."""
+    _build()
+    logn, C_ = 16, 16
+    n = 1 << logn
+    rng = np.random.default_rng(5)
+    total = 3 * n
+    v = rng.standard_normal(total) * 20
+    v[n // 2:n // 2 + 128] += rng.standard_normal(128) * 110          # burst in block 0
+    raw = np.clip(np.round(v), -127, 127).astype(np.int8)
+    inp = tmp_path / "bb.bin"
+    raw.tofile(inp)
+    prefix = tmp_path / "cand_"
+    cfg = tmp_path / "srtb_test.cfg"
+    cfg.write_text(f"""# reference-style config: every numeric value is an expression
+baseband_input_count = 2 ** {logn}
+baseband_input_bits = -8
+baseband_format_type = simple
+baseband_freq_low = 1000 + (0 / 2)
+baseband_bandwidth = 500
+baseband_sample_rate = 1000 * 1e6
+baseband_reserve_sample = 1
+dm = 0.0005
+spectrum_channel_count = 2 ** 4
+mitigate_rfi_average_method_threshold = 10
+mitigate_rfi_spectral_kurtosis_threshold = 1.5
+signal_detect_signal_noise_threshold = 6
+signal_detect_max_boxcar_length = 2 ** 5
+input_file_path = {inp}
+baseband_output_file_prefix = {prefix}
+""")
+    r = subprocess.run([str(BIN), "--config_file_name", str(cfg), "--write-candidates", "1", "--dump-prefix",
+                        str(tmp_path / "dump_")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    works = sorted((json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")), key=lambda w: w["block"])
+    # overlap: with reserve on, consecutive blocks start (n - reserved) samples apart -> more than 3 blocks
+    reserved = oracle.nsamps_reserved(n, C_, 1000.0, 500.0, 1e9, 0.0005, True)
+    assert 0 < reserved < n
+    stride = n - reserved
+    expect_blocks = 1
+    pos = stride
+    while pos < total:
+        expect_blocks += 1
+        pos += stride
+    assert len(works) == expect_blocks > 3
+    L = n // 2 // C_
+    assert all(w["count"] == L and w["batch_size"] == C_ for w in works)
+    det = [w for w in works if w["series"]]
+    assert det and det[0]["block"] == 0
+    # candidate files of the first detection
+    w = det[0]
+    stem = f"{prefix}{w['block']}"
+    bb = np.fromfile(stem + ".bin", dtype=np.int8)
+    assert np.array_equal(bb, raw[:n])                                   # raw baseband of that block
+    spec = np.load(stem + ".0.npy")
+    assert spec.shape == (C_, L) and spec.dtype == np.complex64          # plot_spectrum.py's [freq][time]
+    dumped = np.fromfile(f"{tmp_path / 'dump_'}{w['block']}.0.bin", dtype=np.complex64).reshape(C_, L)
+    assert np.array_equal(spec, dumped)
+    for sinfo in w["series"]:
+        tim = np.fromfile(f"{stem}.{sinfo['boxcar']}.tim", dtype=np.float32)
+        assert tim.size == sinfo["length"] and abs(float(tim.max()) - sinfo["peak"]) < 1e-3 * abs(sinfo["peak"]) + 1e-3
+    # blocks without a detection leave no files (file mode keeps only positives)
+    quiet = [w for w in works if not w["series"]]
+    assert quiet and not Path(f"{prefix}{quiet[0]['block']}.bin").exists()

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 nvidia-smi -L
 python -m pytest tests -m gpu -q --timeout 300 ${KEXPR:+-k "$KEXPR"} 2>&1 | tee gpurun_out/pytest_gpu_${TAG}.log | tail -15
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee gpurun_out/smoke_${TAG}.log
-python bench.py --steps 20 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -c 3000 gpurun_out/bench_${TAG}.json; tail -5 gpurun_out/bench_${TAG}.err
+python bench.py --steps 200 --warmup 5 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; tail -c 3000 gpurun_out/bench_${TAG}.json; tail -5 gpurun_out/bench_${TAG}.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2>> gpurun_out/bench_${TAG}.err; tail -c 600 gpurun_out/bench_ref_${TAG}.json
 # launch list (cold-cache, serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
