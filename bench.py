@@ -10,7 +10,9 @@ Contract (driver): python bench.py --gpus N --steps K --warmup W [--impl referen
     C = 2^11 channels (srtb_config.cfg thresholds); N > 1 shards independent blocks across ranks
     (weak scaling, no collective on the data path);
   * `value`  = samples / time with the blocks already resident in HBM (ring of 16 distinct blocks,
-    256 MiB > L2, so successive steps never re-read a cached input);
+    256 MiB > L2, so successive steps never re-read a cached input); blocks alternate over 3 contexts
+    (CUDA streams) per GPU, two blocks in flight per context, so one block's small detector-tail kernels
+    overlap the next block's FFT sweeps — every block still runs the whole chain and its result is read back;
   * `e2e`    = the same from pinned HOST buffers through srtb_b200_submit_block()/collect_block() (the
     pinned-host ring: H2D of block i overlaps the compute of block i-1); every block's H2D and the D2H
     of its detector result are inside the timed region;
@@ -259,6 +261,8 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SRTB_BENCH_WORKLOAD", "config2"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-iters", type=int, default=5)
+    ap.add_argument("--contexts", type=int, default=int(os.environ.get("SRTB_BENCH_CONTEXTS", "3")),
+                    help="contexts (CUDA streams) per GPU that blocks alternate over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     wname = args.workload
@@ -288,6 +292,10 @@ def main():
     ring = max(2, min(16, (288 << 20) // block_bytes))      # > L2 (126 MB) of distinct input
     stream = torch.cuda.current_stream()
     ctx = srtb_b200.Context(local_rank, stream.cuda_stream)
+    # optional extra contexts on their own streams: consecutive blocks alternate over them so the small
+    # detector-tail kernels of one block overlap the FFT sweeps of the next
+    extra_streams = [torch.cuda.Stream() for _ in range(max(0, args.contexts - 1))]
+    ctxs = [ctx] + [srtb_b200.Context(local_rank, st.cuda_stream) for st in extra_streams]
 
     pairs = srtb_b200.eval_rfi_ranges(w["freq_list"]) if w["freq_list"] else []
     cfg = srtb_b200.BlockConfig()
@@ -327,10 +335,14 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        for st in extra_streams:
+            st.wait_stream(stream)
         for i in range(steps):
             fn(i)
         if finish:
             finish()
+        for st in extra_streams:
+            stream.wait_stream(st)
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
@@ -348,12 +360,14 @@ def main():
     dtickets = []
 
     def _dcollect():
-        res = ctx.collect_block(dtickets.pop(0))
+        c, t = dtickets.pop(0)
+        res = c.collect_block(t)
         detections[0] += sum(int(r.signal_count[b]) for r in res for b in range(r.n_boxcars))
 
     def step_device(i):
-        dtickets.append(ctx.submit_block_device(cfg, dev_blocks[i % ring], block_bytes))
-        if len(dtickets) >= 2:
+        c = ctxs[i % len(ctxs)]
+        dtickets.append((c, c.submit_block_device(cfg, dev_blocks[i % ring], block_bytes)))
+        if len(dtickets) >= 2 * len(ctxs):
             _dcollect()
 
     def drain_device():
@@ -365,12 +379,14 @@ def main():
     tickets = []
 
     def _collect():
-        res = ctx.collect_block(tickets.pop(0))
+        c, t = tickets.pop(0)
+        res = c.collect_block(t)
         detections[0] += sum(int(r.signal_count[b]) for r in res for b in range(r.n_boxcars))
 
     def step_e2e(i):
-        tickets.append(ctx.submit_block(cfg, host_blocks[i % ring], block_bytes))
-        if len(tickets) >= 2:
+        c = ctxs[i % len(ctxs)]
+        tickets.append((c, c.submit_block(cfg, host_blocks[i % ring], block_bytes)))
+        if len(tickets) >= 2 * len(ctxs):
             _collect()
 
     def drain_e2e():
@@ -384,9 +400,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launch_count
+    l0 = sum(c.launch_count for c in ctxs)
     ms_total = timed(step_device, args.steps, drain_device)
-    launches = ctx.launch_count - l0
+    launches = sum(c.launch_count for c in ctxs) - l0
     if rank == 0 and not sampler.rows:
         sampler.snapshot()          # short run: take one sample while the GPU is still under load
     ms_per_step = ms_total / args.steps
@@ -477,7 +493,7 @@ def main():
                                    f"{abs(w['bits'])}-bit {w['fmt']}, C=2^11, DM={w['dm']}, full RFI + detect",
                        "parallelism": f"block-sharded x{world} (no collective)",
                        "l2": f"inputs larger than L2: ring of {ring} distinct blocks ({ring * block_bytes >> 20} MiB)",
-                       "detections": detections[0]},
+                       "contexts_per_gpu": len(ctxs), "detections": detections[0]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": block_bytes * world, "d2h_bytes_per_step": d2h * world},
@@ -490,7 +506,8 @@ def main():
     if dist:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
+    for c in ctxs:
+        c.close()
     return 0
 
 
