@@ -73,6 +73,42 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# kernels of each per-pipe stage, for summing the ncu DRAM traffic of profiles/traffic.json
+STAGE_KERNELS = {
+    "unpack": r"^unpack_",
+    "fft_r2c": r"^(fft_col_tma_kernel<.*, 0>|fft_trans_tma_kernel|fft_pass_kernel|r2c_post_kernel<0>)",
+    "rfi_s1": r"^(power_sum_kernel|rfi_s1_apply_kernel|rfi_zero_ranges_kernel)",
+    "dedisperse": r"^dedisperse_kernel<0>",
+    "watfft": r"^fft_row_tma_kernel<.*, 0>$",
+    "rfi_s2": r"^sk_kernel",
+    "signal_detect": r"^(colsum_|detect_)",
+}
+
+
+def stage_traffic():
+    """per-stage DRAM bytes (read + write) per launch from the committed ncu capture, or {}"""
+    import re
+    p = ROOT / "profiles" / "traffic.json"
+    if not p.exists():
+        return {}, None
+    try:
+        d = json.loads(p.read_text())
+        out = {}
+        seen_fused = False
+        for k in d["kernels"]:
+            # the capture ends with one fused process_block: stop at its first kernel (RAW first sweep)
+            if re.search(r"fft_col_tma_kernel<.*, 1>$", k["kernel"]):
+                seen_fused = True
+            if seen_fused:
+                continue
+            for stage, pat in STAGE_KERNELS.items():
+                if re.search(pat, k["kernel"]):
+                    out[stage] = out.get(stage, 0.0) + k["dram_read"] + k["dram_write"]
+        return out, d.get("tag")
+    except Exception:
+        return {}, None
+
+
 def synth_block(n_samples: int, streams: int, seed: int) -> np.ndarray:
     """V1/V2-style synthetic voltage: Gaussian sigma 20 + CW tone + a short burst,
     int8, clipped; multi-stream blocks are laid out by the caller."""
@@ -462,8 +498,15 @@ def main():
             stages[name] = {"ms": ms, "bytes": bytes_per[name] * per_call_streams, "gbs": gbs, "frac": gbs / peak}
         chain_bytes = sum(bytes_per.values()) * streams
         dom = max((s for s in STAGES), key=lambda s: stages[s]["ms"])
+        traffic, traffic_tag = stage_traffic() if wname == "config2" else ({}, None)
+        for k_, v_ in traffic.items():
+            if k_ in stages:
+                stages[k_]["dram_traffic"] = v_
         roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic.get(dom),
+                    "traffic_source": (f"ncu --set full capture profiles/{traffic_tag}_summary.md (dram read+write of the "
+                                       "stage's kernels, one launch each, L2 flushed)") if traffic_tag else None,
+                    "peak_source": peak_src,
                     "chain": {"bytes_per_sample": chain_bytes / (n * streams),
                               "achieved": chain_bytes / (ms_per_step * 1e-3) / 1e9,
                               "frac": chain_bytes / (ms_per_step * 1e-3) / 1e9 / peak}}

@@ -166,6 +166,13 @@ int srtb_b200_process_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cf
 int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
                                    const void* d_baseband, size_t baseband_bytes,
                                    srtb_b200_detect_result* h_results, float* h_series, int copy_all);
+/* DM sweep on one block (BASELINE config #4): unpack + R2C once, then per trial DM the s1-apply + chirp
+ * (coherent_dedispersion.hpp:223-237, out of place), waterfall FFT, SK and detector; h_results is
+ * [n_dm][streams], each entry equal to process_block with cfg->dm = h_dms[j]. The reference handles one
+ * DM per run (config.hpp:132); this loops its own dedisperse..detect stages over a list. */
+int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                                     const void* baseband, size_t baseband_bytes, int on_device,
+                                     const float* h_dms, size_t n_dm, srtb_b200_detect_result* h_results);
 /* pipelined ingest (the pinned-host ring of SURVEY section 8e): submit copies the block on a
  * dedicated copy stream while the previous block computes and returns a ticket (>= 0);
  * collect waits for that block and fills h_results[stream] (returns the stream count).

@@ -555,8 +555,9 @@ __device__ __forceinline__ float2 chirp_factor(double f_min, double df, double i
 
 // S1 = true fuses K10 (zap + normalise, rfi_mitigation_pipe.hpp:66-79) in front of the chirp: used by
 // srtb_b200_process_block, where the s1 and dedisperse pipes run back to back on one stream.
+// `in` may equal `out` (in place, the pipe's contract) or differ (DM sweep: the spectrum is kept).
 template <bool S1>
-__global__ void __launch_bounds__(256) dedisperse_kernel(float2* __restrict__ x, size_t count,
+__global__ void __launch_bounds__(256) dedisperse_kernel(const float2* in, float2* x, size_t count,
                                                          double f_min, double df, double f_c,
                                                          double ddm, const float* __restrict__ mean,
                                                          float threshold, float coef) {
@@ -565,8 +566,9 @@ __global__ void __launch_bounds__(256) dedisperse_kernel(float2* __restrict__ x,
   const double inv_fc = 1.0 / f_c;
   const float limit = S1 ? threshold * (*mean) : 0.f;
   float4* x4 = reinterpret_cast<float4*>(x);
+  const float4* in4 = reinterpret_cast<const float4*>(in);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
-    float4 v = x4[i];
+    float4 v = in4[i];
     if (S1) {
       const float p0 = v.x * v.x + v.y * v.y, p1 = v.z * v.z + v.w * v.w;
       if (p0 > limit) { v.x = 0.f; v.y = 0.f; } else { v.x *= coef; v.y *= coef; }
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(256) dedisperse_kernel(float2* __restrict__ x,
     x4[i] = o;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && (count & 1)) {
-    float2 v = x[count - 1];
+    float2 v = in[count - 1];
     if (S1) {
       if (v.x * v.x + v.y * v.y > limit) v = make_float2(0.f, 0.f);
       else { v.x *= coef; v.y *= coef; }

@@ -59,6 +59,9 @@ struct srtb_b200_ctx {
   size_t slot_L[SRTB_B200_RING_SLOTS] = {0};
   bool slot_busy[SRTB_B200_RING_SLOTS] = {false};
   uint64_t submit_count = 0;
+  // DM sweep working copy of the spectrum
+  void* sweep_buf = nullptr;
+  size_t sweep_buf_bytes = 0;
   // process_block
   void* d_baseband = nullptr;
   size_t d_baseband_bytes = 0;
@@ -161,6 +164,7 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   cudaFree(ctx->d_res);
   cudaFreeHost(ctx->h_res);
   cudaFree(ctx->d_baseband);
+  cudaFree(ctx->sweep_buf);
   for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) {
     cudaFree(ctx->slot_baseband[i]);
     if (ctx->slot_h2d[i]) cudaEventDestroy(ctx->slot_h2d[i]);
@@ -904,7 +908,7 @@ extern "C" int srtb_b200_dedisperse(srtb_b200_ctx* ctx, void* d_x, size_t count,
   constexpr double D = 4.148808e3;  // coherent_dedispersion.hpp:67
   const double ddm = (D * 1e6) * (double)dm;
   dedisperse_kernel<false><<<grid_for(ctx, count / 2 + 1, 256, 16), 256, 0, ctx->stream>>>(
-      static_cast<float2*>(d_x), count, (double)f_min, (double)df, (double)f_c, ddm, nullptr, 0.f, 1.f);
+      static_cast<const float2*>(d_x), static_cast<float2*>(d_x), count, (double)f_min, (double)df, (double)f_c, ddm, nullptr, 0.f, 1.f);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -914,7 +918,8 @@ extern "C" int srtb_b200_dedisperse(srtb_b200_ctx* ctx, void* d_x, size_t count,
 // fused apply + chirp sweep, then the manual zap (zero * chirp = zero, so the order is equivalent)
 static int rfi_s1_dedisperse_fused(srtb_b200_ctx* ctx, float2* x, size_t count, float avg_threshold, float coef,
                                    const std::vector<size_t>& bins, float f_min, float f_c, float df, float dm,
-                                   bool mean_ready) {
+                                   bool mean_ready, const float2* src = nullptr) {
+  if (!src) src = x;  // in place unless a separate (kept) spectrum is given
   if (!mean_ready) {
     const unsigned grid = std::min<unsigned>(grid_for(ctx, count / 2 + 1, 256), 4096);
     power_sum_kernel<<<grid, 256, 0, ctx->stream>>>(x, count, ctx->partial, ctx->ticket, ctx->mean);
@@ -924,7 +929,7 @@ static int rfi_s1_dedisperse_fused(srtb_b200_ctx* ctx, float2* x, size_t count, 
   constexpr double D = 4.148808e3;
   const double ddm = (D * 1e6) * (double)dm;
   dedisperse_kernel<true><<<grid_for(ctx, count / 2 + 1, 256, 16), 256, 0, ctx->stream>>>(
-      x, count, (double)f_min, (double)df, (double)f_c, ddm, ctx->mean, avg_threshold, coef);
+      src, x, count, (double)f_min, (double)df, (double)f_c, ddm, ctx->mean, avg_threshold, coef);
   ctx->launches++;
   CK(cudaGetLastError());
   for (size_t r0 = 0; r0 < bins.size() / 2; r0 += 16) {
@@ -1325,6 +1330,91 @@ extern "C" int srtb_b200_process_block(srtb_b200_ctx* ctx, const srtb_b200_block
   if (int rc = ensure(ctx, &ctx->d_baseband, &ctx->d_baseband_bytes, baseband_bytes)) return rc;
   CK(cudaMemcpyAsync(ctx->d_baseband, h_baseband, baseband_bytes, cudaMemcpyHostToDevice, ctx->stream));
   return srtb_b200_process_block_device(ctx, cfg, ctx->d_baseband, baseband_bytes, h_results, h_series, copy_all);
+}
+
+// ---- DM sweep on one block (BASELINE config #4): unpack + R2C + mean once per stream, then for every
+// trial DM the s1-apply + chirp (out of place, the spectrum is kept), waterfall FFT, SK and detector.
+// Each trial's result equals process_block with cfg->dm = that DM on the same block.
+extern "C" int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                                                const void* baseband, size_t baseband_bytes, int on_device,
+                                                const float* h_dms, size_t n_dm,
+                                                srtb_b200_detect_result* h_results /* [n_dm][streams] */) {
+  if (!ctx || !cfg || !baseband || !h_dms || !h_results || n_dm == 0)
+    return fail(ctx, SRTB_B200_E_INVALID, "dm_sweep: bad argument");
+  CK(cudaSetDevice(ctx->device));
+  const int streams = format_streams(cfg->baseband_format);
+  if (!streams) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "dm_sweep: unknown format");
+  const size_t N = cfg->baseband_input_count;
+  if (N < 2 || !is_pow2(N)) return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(N));
+  const void* d_baseband = baseband;
+  if (!on_device) {
+    if (int rc = ensure(ctx, &ctx->d_baseband, &ctx->d_baseband_bytes, baseband_bytes)) return rc;
+    CK(cudaMemcpyAsync(ctx->d_baseband, baseband, baseband_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_baseband = ctx->d_baseband;
+  }
+  if (ctx->stream_buf_elems < N + 2) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& p : ctx->stream_buf) {
+      if (p) CK(cudaFree(p));
+      p = nullptr;
+    }
+    ctx->stream_buf_elems = 0;
+  }
+  for (int s = 0; s < streams; s++)
+    if (!ctx->stream_buf[s]) {
+      cudaError_t e = cudaMalloc(&ctx->stream_buf[s], (N + 2) * sizeof(float));
+      if (e != cudaSuccess) return fail(ctx, SRTB_B200_E_NOMEM, "dm_sweep: stream buffer alloc failed");
+    }
+  ctx->stream_buf_elems = N + 2;
+  const size_t Nc = N / 2;
+  const size_t batch = std::min<size_t>(cfg->spectrum_channel_count, Nc);
+  if (batch == 0 || !is_pow2(batch)) return fail(ctx, SRTB_B200_E_SIZE, "spectrum_channel_count must be a power of 2");
+  const size_t L = Nc / batch;
+  if (int rc = ensure(ctx, &ctx->sweep_buf, &ctx->sweep_buf_bytes, (Nc + 1) * sizeof(float2))) return rc;
+  float2* W = static_cast<float2*>(ctx->sweep_buf);
+  if (int rc = srtb_b200_unpack(ctx, d_baseband, baseband_bytes, cfg->baseband_input_bits, cfg->baseband_format,
+                                cfg->window, ctx->stream_buf, N))
+    return rc;
+  std::vector<size_t> bins;
+  for (uint64_t r = 0; r < cfg->n_rfi_freq_pairs; r++) {
+    size_t lo, hi;
+    if (srtb_b200_rfi_range_to_bins(cfg->rfi_freq_pairs[2 * r], cfg->rfi_freq_pairs[2 * r + 1],
+                                    cfg->baseband_freq_low, cfg->baseband_bandwidth, Nc, &lo, &hi)) {
+      bins.push_back(lo);
+      bins.push_back(hi);
+    }
+  }
+  const float coef = srtb_b200_norm_coefficient(Nc, cfg->spectrum_channel_count);
+  const float df = cfg->baseband_bandwidth / static_cast<float>(Nc);
+  const float f_min = cfg->baseband_freq_low, f_c = f_min + cfg->baseband_bandwidth;
+  for (int s = 0; s < streams; s++) {
+    float* buf = ctx->stream_buf[s];
+    if (int rc = fft_r2c_with_power_mean(ctx, buf, N)) return rc;  // leaves mean(|X|^2) in ctx->mean
+    for (size_t j = 0; j < n_dm; j++) {
+      const size_t reserved = srtb_b200_nsamps_reserved(N, cfg->spectrum_channel_count, cfg->baseband_freq_low,
+                                                        cfg->baseband_bandwidth, cfg->baseband_sample_rate, h_dms[j],
+                                                        cfg->baseband_reserve_sample) / batch;
+      if (int rc = rfi_s1_dedisperse_fused(ctx, W, Nc, cfg->mitigate_rfi_average_method_threshold, coef, bins, f_min,
+                                           f_c, df, h_dms[j], /*mean_ready=*/true, reinterpret_cast<const float2*>(buf)))
+        return rc;
+      if (sk_detect_fusable(L)) {
+        if (int rc = watfft_sk_detect_fused(ctx, 0, W, L, batch, reserved, cfg->mitigate_rfi_spectral_kurtosis_threshold,
+                                            cfg->signal_detect_signal_noise_threshold,
+                                            cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length))
+          return rc;
+      } else {
+        if (int rc = srtb_b200_watfft_c2c_backward(ctx, W, L, batch)) return rc;
+        if (int rc = srtb_b200_rfi_s2_sk(ctx, W, L, batch, cfg->mitigate_rfi_spectral_kurtosis_threshold, nullptr)) return rc;
+        if (int rc = detect_enqueue(ctx, 0, W, L, batch, reserved, cfg->signal_detect_signal_noise_threshold,
+                                    cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length))
+          return rc;
+      }
+      CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(detect_dev_result), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      std::memcpy(h_results + j * streams + s, ctx->h_res, sizeof(srtb_b200_detect_result));
+    }
+  }
+  return streams;
 }
 
 // ---- pipelined ingest: the pinned-host ring of SURVEY section 8e -------------------------------

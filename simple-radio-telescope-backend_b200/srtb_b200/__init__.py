@@ -97,6 +97,8 @@ SYMBOLS = {
     "srtb_b200_signal_detect": (_I, [_P, _P, _SZ, _SZ, _SZ, _F, _F, _SZ, C.POINTER(DetectResult), _P, _I]),
     "srtb_b200_process_block": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, C.POINTER(DetectResult), _P, _I]),
     "srtb_b200_process_block_device": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, C.POINTER(DetectResult), _P, _I]),
+    "srtb_b200_process_block_dm_sweep": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, _I, C.POINTER(_F), _SZ,
+                                              C.POINTER(DetectResult)]),
     "srtb_b200_submit_block": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ]),
     "srtb_b200_submit_block_device": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ]),
     "srtb_b200_collect_block": (_I, [_P, _I, C.POINTER(DetectResult)]),
@@ -219,6 +221,15 @@ class Context:
         fn = self.lib.srtb_b200_process_block_device if on_device else self.lib.srtb_b200_process_block
         n = self._ck(fn(self.h, C.byref(cfg), _ptr(baseband), nbytes, res, _ptr(h_series), int(copy_all)))
         return [res[i] for i in range(n)]
+
+    def process_block_dm_sweep(self, cfg: BlockConfig, baseband, nbytes: int, dms, on_device: bool = False):
+        """one block, many trial DMs: returns results[dm_index][stream]"""
+        n_dm = len(dms)
+        arr = (C.c_float * n_dm)(*[float(d) for d in dms])
+        res = (DetectResult * (4 * n_dm))()
+        streams = self._ck(self.lib.srtb_b200_process_block_dm_sweep(self.h, C.byref(cfg), _ptr(baseband), nbytes,
+                                                                      int(on_device), arr, n_dm, res))
+        return [[res[j * streams + s] for s in range(streams)] for j in range(n_dm)]
 
     def submit_block(self, cfg: BlockConfig, h_baseband, nbytes: int) -> int:
         """pipelined ingest: H2D on the copy stream overlaps the previous block's compute"""

@@ -25,6 +25,7 @@
 #include "srtb/pipeline/read_file_pipe.hpp"
 #include "srtb/pipeline/rfi_mitigation_pipe.hpp"
 #include "srtb/pipeline/signal_detect_pipe.hpp"
+#include "srtb/pipeline/udp_receiver_pipe.hpp"
 #include "srtb/pipeline/unpack_pipe.hpp"
 #include "srtb/pipeline/write_signal_pipe.hpp"
 #include "srtb/program_options.hpp"
@@ -145,14 +146,40 @@ int main(int argc, char** argv) {
     threads.push_back(start_pipe<chain>(queue_in_functor{r2c_q}, sink, q));
   }
 
-  // source: read_file_pipe (pinned host block, zero padded tail, overlap-save rewind by nsamps_reserved)
-  read_file_pipe reader;
   int blocks = 0;
-  while (auto w = reader(std::stop_token{}, srtb::work::dummy_work{})) {
-    w->udp_packet_counter = (uint64_t)blocks;  // deterministic file names / JSON keys for the test
-    while (copy_q->read_available() >= 2) std::this_thread::sleep_for(std::chrono::microseconds(50));
-    copy_q->push(*w);
-    blocks++;
+  auto feed = [&](auto& source, bool renumber) {
+    while (auto w = source(std::stop_token{}, srtb::work::dummy_work{})) {
+      if (renumber) w->udp_packet_counter = (uint64_t)blocks;  // deterministic file names / JSON keys for the test
+      while (copy_q->read_available() >= 2) std::this_thread::sleep_for(std::chrono::microseconds(50));
+      copy_q->push(*w);
+      blocks++;
+    }
+  };
+  const int drop_every = std::atoi(arg(argc, argv, "--udp-drop-every", "0"));
+  if (std::atoi(arg(argc, argv, "--udp-shaped", "0")) != 0) {
+    // UDP-shaped source (BASELINE config #5): the file is framed into backend packets (8-byte counter +
+    // 4096 payload bytes), every `drop_every`-th packet is lost on the way, and udp_receiver_pipe
+    // assembles blocks by counter with zero fill. The block key is the counter of its first packet.
+    namespace io = srtb::io;
+    std::ifstream f(input, std::ios::binary);
+    std::vector<char> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    auto run = [&]<typename B>(B) {
+      auto packets = io::udp::frame_stream<B>(
+          std::span<const std::byte>(reinterpret_cast<const std::byte*>(bytes.data()), bytes.size()), 0);
+      io::udp::memory_packet_provider prov;
+      for (size_t i = 0; i < packets.size(); i++)
+        if (!(drop_every > 0 && i % (size_t)drop_every == (size_t)drop_every - 1)) prov.push(std::move(packets[i]));
+      udp_receiver_pipe<io::udp::memory_packet_provider, B> receiver{std::move(prov)};
+      feed(receiver, false);
+      std::fprintf(stderr, "[udp-shaped] received %zu packets, lost %zu\n", receiver.received_packets(),
+                   receiver.lost_packets());
+    };
+    if (streams == 2) run(io::backend_registry::naocpsr_snap1{});
+    else run(io::backend_registry::fastmb_roach2{});
+  } else {
+    // source: read_file_pipe (pinned host block, zero padded tail, overlap-save rewind by nsamps_reserved)
+    read_file_pipe reader;
+    feed(reader, true);
   }
   while (done->load() < blocks * (int)streams) std::this_thread::sleep_for(std::chrono::milliseconds(1));
   for (auto& t : threads) t.request_stop();

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "srtb/io/npy.hpp"
+#include "srtb/io/udp_block_assembler.hpp"
 #include "srtb/program_options.hpp"
 
 #define CHECK(...)                                                                     \
@@ -117,6 +118,54 @@ int main(int argc, char** argv) {
   std::ifstream f(dir + "/srtb_test.npy", std::ios::binary);
   std::string bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
   CHECK(bytes.size() % 8 == 0 && bytes.substr(1, 5) == "NUMPY" && (bytes.size() - 48) % 64 == 0);
+  // ---- UDP-shaped stream: packet framing + counter-keyed block assembly with loss and reordering
+  {
+    using namespace srtb::io;
+    using B = backend_registry::fastmb_roach2;
+    constexpr size_t d = B::packet_payload_size - B::packet_header_size;
+    CHECK(d == 4096);
+    std::vector<std::byte> stream(d * 24);
+    for (size_t i = 0; i < stream.size(); i++) stream[i] = static_cast<std::byte>((i * 2654435761u >> 13) & 0xff);
+    auto packets = udp::frame_stream<B>(stream, /*first_counter=*/1000);
+    CHECK(packets.size() == 24 && B::parse_counter(packets[5]) == 1005);
+    udp::memory_packet_provider prov;
+    for (size_t i = 0; i < packets.size(); i++) {
+      if (i == 3 || i == 12 || i == 13) continue;             // lost packets
+      if (i == 4) { prov.push(packets[5]); prov.push(packets[4]); continue; }  // 4 and 5 swapped (mid-block)
+      if (i == 5) continue;
+      prov.push(packets[i]);
+    }
+    udp::block_assembler<udp::memory_packet_provider, B> asmblr{std::move(prov)};
+    std::vector<std::byte> block(d * 8);
+    for (int blk = 0; blk < 3; blk++) {
+      auto first = asmblr.receive(block);
+      CHECK(first.has_value() && *first == 1000u + 8u * blk);
+      for (size_t pkt = 0; pkt < 8; pkt++) {
+        const size_t g = blk * 8 + pkt;
+        const bool lost = (g == 3 || g == 12 || g == 13);
+        for (size_t j = 0; j < d; j += 511) {
+          const std::byte expect = lost ? std::byte{0} : stream[g * d + j];
+          CHECK(block[pkt * d + j] == expect);
+        }
+      }
+    }
+    CHECK(asmblr.total_lost_packet_count == 3 && asmblr.total_received_packet_count == 21);
+    CHECK(!asmblr.receive(block).has_value());                 // stream exhausted
+    bool threw2 = false;
+    std::vector<std::byte> odd(d * 2 + 1);
+    try {
+      asmblr.receive(odd);
+    } catch (const std::invalid_argument&) {
+      threw2 = true;
+    }
+    CHECK(threw2);
+    // gznupsr_a1: 64-byte header, counter in VDIF words 6|7, 8192 data bytes
+    using G = backend_registry::gznupsr_a1;
+    std::vector<std::byte> gp(G::packet_payload_size);
+    G::write_header(gp, 0x0123456789abcdefull);
+    CHECK(G::parse_counter(gp) == 0x0123456789abcdefull && G::packet_payload_size - G::packet_header_size == 8192);
+    CHECK(backend_registry::naocpsr_snap1::data_stream_count == 2);
+  }
   std::printf("host next ok\n");
   return 0;
 }

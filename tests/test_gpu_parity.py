@@ -593,3 +593,41 @@ def test_pipelined_submit_collect_matches_process_block(ctx):
 
 def srtb_b200_ring_slots():
     return 3
+
+
+def test_dm_sweep_equals_single_dm_runs(ctx):
+    """BASELINE config #4 shape at reduced size: one block, a ladder of trial DMs; every trial must equal
+    process_block at that DM (same detector numbers), and the dispersed pulse is recovered best at its DM."""
+    n, C_ = 1 << 20, 256
+    f_low, bw = 1000.0, 500.0
+    true_dm = 30.0
+    # Crab-style injection (SURVEY section 8d V3): a narrow pulse dispersed with the conjugate chirp in float64
+    rng = np.random.default_rng(4)
+    nc = n // 2
+    pulse = np.zeros(n)
+    pulse[n // 2:n // 2 + 48] = rng.standard_normal(48) * 400
+    X = np.fft.rfft(pulse)[:nc]
+    f = f_low + (bw / nc) * np.arange(nc)
+    f_c = f_low + bw
+    k = 4.148808e3 * 1e6 * true_dm / f * ((f - f_c) / f_c) ** 2
+    X *= np.exp(+2j * np.pi * (k - np.trunc(k)))                  # inverse of the dedispersion chirp
+    v = np.fft.irfft(np.concatenate([X, [0]]), n) + rng.standard_normal(n) * 20
+    bb = np.clip(np.round(v), -127, 127).astype(np.int8)
+    dms = [0.0, 10.0, 20.0, 30.0, 40.0, 60.0]
+    cfg = make_block_config(n, -8, srtb_b200.FORMAT_SIMPLE, C_, 0.0, f_low=f_low, bw=bw, avg_thr=10.0, sk_thr=2.0,
+                            snr=6.0, maxbox=64)
+    pinned = torch.from_numpy(bb.view(np.uint8).copy()).pin_memory()
+    sweep = ctx.process_block_dm_sweep(cfg, pinned, n, dms)
+    assert len(sweep) == len(dms) and all(len(r) == 1 for r in sweep)
+    peaks = []
+    for dm, r in zip(dms, sweep):
+        cfg.dm = dm
+        single = ctx.process_block(cfg, pinned, n, None)[0]
+        g = r[0]
+        assert g.zero_count == single.zero_count and g.n_boxcars == single.n_boxcars
+        for b in range(g.n_boxcars):
+            assert g.threshold[b] == pytest.approx(single.threshold[b], rel=1e-5)
+            assert abs(int(g.signal_count[b]) - int(single.signal_count[b])) <= 1
+        peaks.append(sum(int(g.signal_count[b]) for b in range(g.n_boxcars)))
+    assert peaks[dms.index(true_dm)] > 0
+    assert peaks[dms.index(true_dm)] >= max(peaks[0], peaks[-1])

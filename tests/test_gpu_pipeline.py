@@ -44,13 +44,13 @@ def _oracle_cfg(n, C_, dm, freq_pairs):
     return oc
 
 
-def _run(tmp_path, fmt, raw, logn, C_, dm, composite, freq_list="1200-1201"):
+def _run(tmp_path, fmt, raw, logn, C_, dm, composite, freq_list="1200-1201", extra=()):
     inp = tmp_path / f"bb_{fmt}_{composite}.bin"
     raw.tofile(inp)
     prefix = tmp_path / f"dump_{fmt}_{composite}_"
     cmd = [str(BIN), "--input", str(inp), "--log2n", str(logn), "--bits", "-8", "--format", fmt, "--channels",
            str(C_), "--dm", str(dm), "--avg-thr", "5", "--sk-thr", "1.3", "--snr", "6", "--max-boxcar", "64",
-           "--freq-list", freq_list, "--dump-prefix", str(prefix), "--composite", str(composite)]
+           "--freq-list", freq_list, "--dump-prefix", str(prefix), "--composite", str(composite), *extra]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     works = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
@@ -95,6 +95,27 @@ def test_pipeline_simple_three_blocks(tmp_path, oracle, composite):
         assert w["stream"] == 0
         detected += _check_work(w, prefix, blocks[w["block"]], oracle, n, C_, dm)
     assert detected > 0                                             # the injected bursts were found
+
+
+def test_pipeline_udp_shaped_with_packet_loss(tmp_path, oracle):
+    """BASELINE config #5 / SURVEY 8(f-2): the stream arrives as fastmb_roach2 packets (8-byte counter + 4096
+    bytes), every 7th packet is lost; udp_receiver_pipe assembles blocks by counter and zero-fills the holes
+    (io/udp/udp_receiver.hpp:180-272). Each block's results equal the oracle's on the zero-filled block."""
+    _build()
+    logn, C_, dm = 18, 64, 0.0
+    n = 1 << logn
+    blocks = [_block(n, s) for s in (21, 22, 23)]
+    works, prefix = _run(tmp_path, "simple", np.concatenate(blocks), logn, C_, dm, 1,
+                         extra=("--udp-shaped", "1", "--udp-drop-every", "7"))
+    ppb = n // 4096                                                  # packets per block
+    assert sorted(w["block"] for w in works) == [0, ppb, 2 * ppb]    # keyed by first packet counter
+    for w in works:
+        k = w["block"] // ppb
+        holed = blocks[k].copy().reshape(ppb, 4096)
+        for pkt in range(ppb):
+            if (k * ppb + pkt) % 7 == 6:
+                holed[pkt] = 0
+        _check_work(w, prefix, holed.reshape(-1), oracle, n, C_, dm)
 
 
 def test_pipeline_dual_pol_fanout(tmp_path, oracle):
