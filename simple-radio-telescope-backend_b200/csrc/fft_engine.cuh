@@ -151,6 +151,88 @@ __device__ __forceinline__ void stage_compute(float2 (&v)[8], int u, const float
   }
 }
 
+
+// ---- sixteen points per thread (radix-16 stages): half the shared-memory round trips and barriers of
+// the eight-point schedule for L = 256 (16 x 16) and L = 128 (16 x 8) ------------------------------
+template <bool FWD>
+__device__ __forceinline__ float2 c_mulc(float2 a, float wr, float wi_fwd) {  // a * (wr, wi), table holds forward
+  const float wi = FWD ? wi_fwd : -wi_fwd;
+  return make_float2(fmaf(a.x, wr, -a.y * wi), fmaf(a.x, wi, a.y * wr));
+}
+// multiply by W8^1 = (c, -c) and W8^3 = (-c, -c) (forward; conjugates backward)
+template <bool FWD>
+__device__ __forceinline__ float2 c_w8_1(float2 a) {
+  constexpr float c = 0.70710678118654752440f;
+  return FWD ? make_float2(c * (a.x + a.y), c * (a.y - a.x)) : make_float2(c * (a.x - a.y), c * (a.x + a.y));
+}
+template <bool FWD>
+__device__ __forceinline__ float2 c_w8_3(float2 a) {
+  constexpr float c = 0.70710678118654752440f;
+  return FWD ? make_float2(c * (a.y - a.x), -c * (a.x + a.y)) : make_float2(-c * (a.x + a.y), c * (a.x - a.y));
+}
+template <bool FWD>
+__device__ __forceinline__ void dft16(float2 (&a)[16]) {
+  constexpr float C1 = 0.92387953251128675613f, S1 = 0.38268343236508977173f;
+#pragma unroll
+  for (int j = 0; j < 4; j++) dft4<FWD>(a[j], a[j + 4], a[j + 8], a[j + 12]);  // a[j + 4q] = A_j[q]
+  // A_j[q] *= W16^{j q}
+  a[5] = c_mulc<FWD>(a[5], C1, -S1);    // j=1,q=1: W^1
+  a[9] = c_w8_1<FWD>(a[9]);             // j=1,q=2: W^2
+  a[13] = c_mulc<FWD>(a[13], S1, -C1);  // j=1,q=3: W^3
+  a[6] = c_w8_1<FWD>(a[6]);             // j=2,q=1: W^2
+  a[10] = c_rot<FWD>(a[10]);            // j=2,q=2: W^4
+  a[14] = c_w8_3<FWD>(a[14]);           // j=2,q=3: W^6
+  a[7] = c_mulc<FWD>(a[7], S1, -C1);    // j=3,q=1: W^3
+  a[11] = c_w8_3<FWD>(a[11]);           // j=3,q=2: W^6
+  a[15] = c_mulc<FWD>(a[15], -C1, S1);  // j=3,q=3: W^9
+#pragma unroll
+  for (int q = 0; q < 4; q++) dft4<FWD>(a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);  // a[4q+p] = X[q+4p]
+#pragma unroll
+  for (int q = 0; q < 4; q++)
+#pragma unroll
+    for (int p = q + 1; p < 4; p++) {
+      const float2 tmp = a[4 * q + p];
+      a[4 * q + p] = a[4 * p + q];
+      a[4 * p + q] = tmp;
+    }
+}
+
+template <int LOGL>
+struct sched16 {
+  static constexpr int S = (LOGL + 3) / 4;
+  __host__ __device__ static constexpr int logr(int s) { return (s < S - 1) ? 4 : (LOGL - 4 * (S - 1)); }
+  __host__ __device__ static constexpr int logns(int s) { return 4 * s; }
+};
+
+// stage_compute for sixteen slots: slot e is the point read at u + e*U (U = L/16); radix 16 (one
+// butterfly), 8 (two), 4 (four). Twiddles always come from the table (column-mode mapping).
+template <int LOGL, int LOGR, int LOGNS, bool FWD, int TWSHIFT = LOGL - LOGNS - LOGR>
+__device__ __forceinline__ void stage_compute16(float2 (&v)[16], int u, const float2* __restrict__ tw,
+                                                int (&oidx)[16]) {
+  constexpr int L = 1 << LOGL, U = L / 16, R = 1 << LOGR, NB = 16 / R, NS = 1 << LOGNS;
+  static_assert(LOGR >= 2 && LOGR <= 4, "radix 4, 8 or 16");
+#pragma unroll
+  for (int m = 0; m < NB; m++) {
+    const int b = u + m * U;
+    const int k = b & (NS - 1);
+    if constexpr (LOGNS > 0) {
+      constexpr int SH = (TWSHIFT < 0) ? 0 : TWSHIFT;
+#pragma unroll
+      for (int i = 1; i < R; i++) v[m + i * NB] = c_mul(v[m + i * NB], c_dir<FWD>(tw[(k * i) << SH]));
+    }
+    if constexpr (R == 16) {
+      dft16<FWD>(v);
+    } else if constexpr (R == 8) {
+      dft8<FWD>(v[m], v[m + 2], v[m + 4], v[m + 6], v[m + 8], v[m + 10], v[m + 12], v[m + 14]);
+    } else {
+      dft4<FWD>(v[m], v[m + 4], v[m + 8], v[m + 12]);
+    }
+    const int obase = ((b >> LOGNS) << (LOGNS + LOGR)) + k;
+#pragma unroll
+    for (int i = 0; i < R; i++) oidx[m + i * NB] = obase + i * NS;
+  }
+}
+
 // shared-memory layout of the tile
 template <int LOGL, int T, int MODE>
 struct tile_layout {
@@ -572,6 +654,215 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value,
 
 
 // ---------------------------------------------------------------------------------
+// Row pass with sixteen points per thread (radix-16 stages: L = 4096 as 16^3, 2048 as 16*16*8,
+// 1024 as 16*16*4, 256 as 16*16): three stages and five CTA barriers per 4096-point row instead of
+// four and eight. Lanes run along the FFT index, so a thread reads W^k, W^2k, W^4k of its butterfly from
+// compact per-stage tables and forms the other powers by at most two further multiplications.
+// The exchange layout is an XOR swizzle (idx ^ ((idx >> 4) & 15)): conflict-free for every stage's
+// reads and writes without padding, so the tile buffers stay at exactly T*L elements.
+// ---------------------------------------------------------------------------------
+template <int LOGL>
+struct row16_t {
+  static constexpr int value = (LOGL >= 12) ? 1 : (1 << (12 - LOGL));  // 4096 points, 256 threads per tile
+};
+template <int LOGL, int T>
+struct row16_smem {
+  static constexpr int L = 1 << LOGL;
+  static constexpr int BUF = T * L;
+  static constexpr int S = sched16<LOGL>::S;
+  // stage s >= 1: three tables (W^k, W^2k, W^4k) of 16^s entries
+  static constexpr int TW = 3 * ((S > 1 ? 16 : 0) + (S > 2 ? 256 : 0));
+  static constexpr size_t bytes = 2 * (size_t)BUF * sizeof(float2) + 128 + (size_t)(TW + 8) * sizeof(float2);
+};
+
+__device__ __forceinline__ int row16_sw(int idx) { return idx ^ ((idx >> 4) & 15); }
+
+template <int LOGL, int LOGR, int LOGNS, bool FWD>
+__device__ __forceinline__ void stage_compute16_row(float2 (&v)[16], int u, const float2* __restrict__ ctw,
+                                                    int (&oidx)[16]) {
+  constexpr int L = 1 << LOGL, U = L / 16, R = 1 << LOGR, NB = 16 / R, NS = 1 << LOGNS;
+  static_assert(LOGR >= 2 && LOGR <= 4, "radix 4, 8 or 16");
+#pragma unroll
+  for (int m = 0; m < NB; m++) {
+    const int b = u + m * U;
+    const int k = b & (NS - 1);
+    if constexpr (LOGNS > 0) {
+      const float2 w1 = c_dir<FWD>(ctw[k]), w2 = c_dir<FWD>(ctw[NS + k]);
+      const float2 w3 = c_mul(w1, w2);
+      v[m + NB] = c_mul(v[m + NB], w1);
+      v[m + 2 * NB] = c_mul(v[m + 2 * NB], w2);
+      v[m + 3 * NB] = c_mul(v[m + 3 * NB], w3);
+      if constexpr (R >= 8) {
+        const float2 w4 = c_dir<FWD>(ctw[2 * NS + k]);
+        const float2 w5 = c_mul(w4, w1), w6 = c_mul(w4, w2), w7 = c_mul(w4, w3);
+        v[m + 4 * NB] = c_mul(v[m + 4 * NB], w4);
+        v[m + 5 * NB] = c_mul(v[m + 5 * NB], w5);
+        v[m + 6 * NB] = c_mul(v[m + 6 * NB], w6);
+        v[m + 7 * NB] = c_mul(v[m + 7 * NB], w7);
+        if constexpr (R == 16) {
+          const float2 w8 = c_sqr(w4);
+          v[8] = c_mul(v[8], w8);
+          v[9] = c_mul(v[9], c_mul(w8, w1));
+          v[10] = c_mul(v[10], c_mul(w8, w2));
+          v[11] = c_mul(v[11], c_mul(w8, w3));
+          v[12] = c_mul(v[12], c_mul(w8, w4));
+          v[13] = c_mul(v[13], c_mul(w8, w5));
+          v[14] = c_mul(v[14], c_mul(w8, w6));
+          v[15] = c_mul(v[15], c_mul(w8, w7));
+        }
+      }
+    }
+    if constexpr (R == 16) {
+      dft16<FWD>(v);
+    } else if constexpr (R == 8) {
+      dft8<FWD>(v[m], v[m + 2], v[m + 4], v[m + 6], v[m + 8], v[m + 10], v[m + 12], v[m + 14]);
+    } else {
+      dft4<FWD>(v[m], v[m + 4], v[m + 8], v[m + 12]);
+    }
+    const int obase = ((b >> LOGNS) << (LOGNS + LOGR)) + k;
+#pragma unroll
+    for (int i = 0; i < R; i++) oidx[m + i * NB] = obase + i * NS;
+  }
+}
+
+template <int LOGL, int T, bool FWD, bool SK = false>
+__global__ void __launch_bounds__(((1 << LOGL) / 16) * T, 3)
+    fft_row16_tma_kernel(const float2* __restrict__ in, float2* __restrict__ out, size_t nrows,
+                         const float2* __restrict__ tw, row_sk_params skp) {
+  using SC = sched16<LOGL>;
+  constexpr int L = 1 << LOGL, U = L / 16, S = SC::S, BUF = row16_smem<LOGL, T>::BUF;
+  static_assert(S == 2 || S == 3, "256 <= L <= 4096");
+  extern __shared__ __align__(128) unsigned char smraw[];
+  float2* const buf0 = reinterpret_cast<float2*>(smraw);
+  float2* const buf1 = buf0 + BUF;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  float2* const ctw = reinterpret_cast<float2*>(smraw + 2 * (size_t)BUF * sizeof(float2) + 128);
+  const int tid = threadIdx.x;
+  const int t = tid / U, u = tid % U;
+  const unsigned ntiles = (unsigned)((nrows + T - 1) / T);
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  // stage s >= 1 (Ns = 16^s, radix R): tables p = 1, 2, 4 of W_{Ns*R}^{k p} = W_L^{(k p) << (LOGL - 4s - logr)}
+#pragma unroll
+  for (int s = 1; s < S; s++) {
+    const int ns = 1 << (4 * s), off = (s == 1) ? 0 : 48, sh = LOGL - 4 * s - SC::logr(s);
+    for (int i = tid; i < 3 * ns; i += blockDim.x) {
+      const int p = i / ns, k = i - p * ns;
+      ctw[off + i] = __ldg(&tw[(k << p) << sh]);
+    }
+  }
+  __syncthreads();
+  auto issue = [&](unsigned tl, int b) {
+    const size_t row0 = (size_t)tl * T;
+    const size_t rows = (nrows - row0 < (size_t)T) ? nrows - row0 : (size_t)T;
+    const uint32_t bytes = (uint32_t)(rows << LOGL) * (uint32_t)sizeof(float2);
+    fence_proxy_async();
+    mbar_expect_tx(&mbar[b], bytes);
+    bulk_g2s(b ? buf1 : buf0, in + (row0 << LOGL), bytes, &mbar[b]);
+  };
+  float colacc[SK ? 16 : 1];
+#pragma unroll
+  for (int e = 0; e < (SK ? 16 : 1); e++) colacc[e] = 0.f;
+  __shared__ float sk_s2[T][(U + 31) / 32], sk_s4[T][(U + 31) / 32];
+  __shared__ int sk_zap[T];
+  unsigned tile = blockIdx.x;
+  if (tile < ntiles && tid == 0) issue(tile, 0);
+  for (unsigned it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int b = it & 1;
+    float2* const sm = (b ? buf1 : buf0) + t * L;
+    const unsigned nxt = tile + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue(nxt, b ^ 1);
+    mbar_wait(&mbar[b], (it >> 1) & 1);
+    const size_t row = (size_t)tile * T + t;
+    const bool valid = row < nrows;
+    float2 v[16];
+    int oidx[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = valid ? sm[u + e * U] : make_float2(0.f, 0.f);
+    stage_compute16_row<LOGL, SC::logr(0), 0, FWD>(v, u, ctw, oidx);
+    __syncthreads();  // every linear read done before the swizzled layout overwrites the buffer
+#pragma unroll
+    for (int e = 0; e < 16; e++) sm[row16_sw(oidx[e])] = v[e];
+    __syncthreads();
+    if constexpr (S == 3) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) v[e] = sm[row16_sw(u + e * U)];
+      __syncthreads();
+      stage_compute16_row<LOGL, SC::logr(1), SC::logns(1), FWD>(v, u, ctw, oidx);
+#pragma unroll
+      for (int e = 0; e < 16; e++) sm[row16_sw(oidx[e])] = v[e];
+      __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = sm[row16_sw(u + e * U)];
+    stage_compute16_row<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD>(v, u, ctw + ((S == 3) ? 48 : 0), oidx);
+    if constexpr (SK) {
+      static_assert(!SK || U >= 32, "SK fusion needs at least one warp per row");
+      float s2 = 0.f, s4 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const float pw = valid ? (v[e].x * v[e].x + v[e].y * v[e].y) : 0.f;
+        s2 += pw;
+        s4 += pw * pw;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+      }
+      if ((tid & 31) == 0) {
+        sk_s2[t][u >> 5] = s2;
+        sk_s4[t][u >> 5] = s4;
+      }
+      __syncthreads();
+      if (u == 0) {
+        float a = 0.f, bsum = 0.f;
+        for (int w = 0; w < (U + 31) / 32; w++) {  // fixed order
+          a += sk_s2[t][w];
+          bsum += sk_s4[t][w];
+        }
+        const float sk = (float)L * (bsum / (a * a));
+        sk_zap[t] = (sk > skp.thr_hi || sk < skp.thr_lo) ? 1 : 0;  // NaN (all-zero row): untouched
+      }
+      __syncthreads();
+      const bool zap = sk_zap[t] != 0;
+      if (valid) {
+        float2* o = out + (row << LOGL) + u;
+#pragma unroll
+        for (int e = 0; e < 16; e++) o[e * U] = zap ? make_float2(0.f, 0.f) : v[e];
+        if (!zap) {
+#pragma unroll
+          for (int e = 0; e < 16; e++) colacc[e] += v[e].x * v[e].x + v[e].y * v[e].y;
+        }
+      }
+    } else {
+      if (valid) {
+        float2* o = out + (row << LOGL) + u;
+#pragma unroll
+        for (int e = 0; e < 16; e++) o[e * U] = v[e];
+      }
+    }
+    __syncthreads();  // all reads of buffer b done: it may be refilled from the next iteration on
+  }
+  if constexpr (SK) {
+    float* const red = reinterpret_cast<float*>(buf0);  // tile buffers are free now
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; e++) red[t * L + u + e * U] = colacc[e];
+    __syncthreads();
+    for (int c = tid; c < L; c += blockDim.x) {
+      float a = 0.f;
+      for (int tt = 0; tt < T; tt++) a += red[tt * L + c];
+      if ((unsigned)c < skp.ts_count) skp.partial[(size_t)blockIdx.x * skp.ts_count + c] = a;
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------
 // COL and TRANS passes fed by tensor-map TMA (cp.async.bulk.tensor, SASS: UTMALDG)
 // ---------------------------------------------------------------------------------
 struct alignas(64) tensor_map_blob {
@@ -736,6 +1027,113 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
       for (int e = 0; e < 8; e++) o[(size_t)e * U * B] = c_mul(v[e], w[e]);
     }
     __syncthreads();  // buffer b may be refilled from the next iteration on
+  }
+}
+
+// Column pass with sixteen points per thread and radix-16 stages (two stages: L = 256 as 16 x 16, L = 128 as
+// 16 x 8): one shared-memory exchange and three CTA barriers per tile instead of two and five. Same tiles,
+// tensor maps, twiddle tables and results (up to fp32 rounding) as fft_col_tma_kernel.
+template <int LOGL, int T>
+struct col16_threads {
+  static constexpr int value = ((1 << LOGL) / 16) * T;
+};
+
+template <int LOGL, int T, bool FWD, int RAW = 0>
+__global__ void __launch_bounds__(col16_threads<LOGL, T>::value, 3)
+    fft_col16_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, size_t B,
+                         uint32_t btiles, uint32_t ntiles, big_twiddle btw, const float2* __restrict__ tw,
+                         raw_params rp) {
+  using SC = sched16<LOGL>;
+  static_assert(SC::S == 2, "two-stage lengths only (32 <= L <= 256)");
+  constexpr int L = 1 << LOGL, U = L / 16, BUF = tile_tma_smem<LOGL, T>::BUF;
+  constexpr int ROWS_PER_BOX = (L < 256) ? L : 256;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  float2* const buf0 = reinterpret_cast<float2*>(smraw);
+  float2* const buf1 = buf0 + BUF;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  unsigned char* const raw0 = reinterpret_cast<unsigned char*>(buf1);
+  unsigned char* const raw1 = raw0 + (size_t)BUF * 4;
+  float2* const ltw = reinterpret_cast<float2*>(smraw + tile_tma_smem<LOGL, T>::data_bytes + 128);
+  float2* const stw = ltw + L;
+  const int tid = threadIdx.x;
+  const int t = tid % T, u = tid / T;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < (3 << btw.q); i += blockDim.x) stw[i] = __ldg(&btw.tab[i]);
+  for (int i = tid; i < L; i += blockDim.x) ltw[i] = __ldg(&tw[i]);
+  __syncthreads();
+  auto issue = [&](uint32_t tl, int b) {
+    const uint32_t a = tl / btiles, b0 = (tl % btiles) * T;
+    fence_proxy_async();
+    if constexpr (RAW == 0) {
+      float2* dst = b ? buf1 : buf0;
+      mbar_expect_tx(&mbar[b], (uint32_t)(BUF * sizeof(float2)));
+#pragma unroll
+      for (int r = 0; r < L; r += ROWS_PER_BOX)
+        tma_load_2d(dst + r * T, &tmap, (int)b0, (int)(a * L + r), &mbar[b]);
+    } else {
+      unsigned char* dst = b ? raw1 : raw0;
+      mbar_expect_tx(&mbar[b], (uint32_t)(BUF * rp.G));
+#pragma unroll
+      for (int r = 0; r < L; r += ROWS_PER_BOX)
+        tma_load_2d(dst + (size_t)r * T * rp.G, &tmap, (int)(b0 * rp.G), (int)(a * L + r), &mbar[b]);
+    }
+  };
+  uint32_t tile = blockIdx.x;
+  if (tile < ntiles && tid == 0) issue(tile, 0);
+  for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int b = it & 1;
+    float2* const sm = (RAW == 0) ? (b ? buf1 : buf0) : buf0;
+    const uint32_t nxt = tile + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue(nxt, b ^ 1);
+    mbar_wait(&mbar[b], (it >> 1) & 1);
+    float2 v[16];
+    int oidx[16];
+    if constexpr (RAW == 0) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) v[e] = sm[(u + e * U) * T + t];
+    } else {
+      const unsigned char* rawb = (b ? raw1 : raw0) + (size_t)t * rp.G;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const unsigned char* g = rawb + (size_t)(u + e * U) * T * rp.G;
+        if (RAW == 1) v[e] = make_float2((float)(int)(signed char)g[rp.o0], (float)(int)(signed char)g[rp.o1]);
+        else v[e] = make_float2((float)g[rp.o0], (float)g[rp.o1]);
+      }
+    }
+    stage_compute16<LOGL, SC::logr(0), 0, FWD>(v, u, ltw, oidx);
+    if constexpr (RAW == 0) __syncthreads();  // every thread has read the tile before it is overwritten
+#pragma unroll
+    for (int e = 0; e < 16; e++) sm[oidx[e] * T + t] = v[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = sm[(u + e * U) * T + t];
+    stage_compute16<LOGL, SC::logr(1), SC::logns(1), FWD>(v, u, ltw, oidx);
+    {
+      // store k = u + e*U of column b0 + t, times W_{L*B}^{k (b0 + t)} = wb * r1^e; the sixteen powers
+      // are formed as hi[e >> 2] * lo[e & 3] (products of at most three table values deep)
+      const uint32_t a = tile / btiles, b0 = (tile % btiles) * T;
+      const uint32_t bb = b0 + t;
+      float2 wb = big_tw_lookup(stw, btw.q, (uint32_t)u * bb);
+      float2 r1 = big_tw_lookup(stw, btw.q, (uint32_t)U * bb);
+      if (!FWD) {
+        wb.y = -wb.y;
+        r1.y = -r1.y;
+      }
+      const float2 r2 = c_sqr(r1), r3 = c_mul(r2, r1), r4 = c_sqr(r2), r8 = c_sqr(r4), r12 = c_mul(r8, r4);
+      const float2 hi1 = c_mul(wb, r4), hi2 = c_mul(wb, r8), hi3 = c_mul(wb, r12);
+      float2* o = out + ((size_t)a << LOGL) * B + b0 + (size_t)u * B + t;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const float2 h = (e >> 2) == 0 ? wb : ((e >> 2) == 1 ? hi1 : ((e >> 2) == 2 ? hi2 : hi3));
+        const float2 w = (e & 3) == 0 ? h : c_mul(h, (e & 3) == 1 ? r1 : ((e & 3) == 2 ? r2 : r3));
+        o[(size_t)e * U * B] = c_mul(v[e], w);
+      }
+    }
+    __syncthreads();  // buffer b (and the exchange buffer) may be refilled from the next iteration on
   }
 }
 

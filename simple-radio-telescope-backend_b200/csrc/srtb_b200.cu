@@ -361,9 +361,39 @@ struct col_t {
   static constexpr int value = (LOGL <= 8) ? SRTB_COL_T : ((SRTB_COL_T < 8) ? SRTB_COL_T : 8);
 };
 
+// sixteen-points-per-thread row kernels (L = 256, 1024, 2048, 4096); SRTB_B200_ROW16=0 selects the
+// eight-point kernels (A/B measurements)
+static bool use_row16() {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_ROW16");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <int LOGL>
+struct has_row16 {
+  static constexpr bool value = (LOGL == 8 || LOGL == 10 || LOGL == 11 || LOGL == 12);
+};
+
 template <int LOGL, bool FWD>
 static int launch_row(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t nrows) {
   constexpr int T = row_t<LOGL>::value;
+  if constexpr (has_row16<LOGL>::value) {
+    if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0 && use_row16()) {
+      constexpr int T16 = row16_t<LOGL>::value, threads = ((1 << LOGL) / 16) * T16;
+      auto kern = fft_row16_tma_kernel<LOGL, T16, FWD>;
+      constexpr size_t smem = row16_smem<LOGL, T16>::bytes;
+      const size_t ntiles = (nrows + T16 - 1) / T16;
+      unsigned grid = 1;
+      if (int rc = persistent_grid(ctx, kern, threads, smem, smem, ntiles, &grid)) return rc;
+      const float2* tw = nullptr;
+      if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+      kern<<<grid, threads, smem, ctx->stream>>>(in, out, nrows, tw, row_sk_params{});
+      ctx->launches++;
+      CK(cudaGetLastError());
+      return 0;
+    }
+  }
   if ((reinterpret_cast<uintptr_t>(in) & 15u) == 0) {
     // persistent TMA-fed kernel (cp.async.bulk needs 16-byte aligned rows)
     auto kern = fft_row_tma_kernel<LOGL, T, FWD>;
@@ -445,6 +475,16 @@ static int persistent_grid(srtb_b200_ctx* ctx, K kern, int threads, size_t smem,
   return 0;
 }
 
+// sixteen-points-per-thread column kernels (radix 16 x 16 / 16 x 8) for L = 256 / 128; SRTB_B200_COL16=0
+// selects the eight-point kernels instead (A/B measurements)
+static bool use_col16() {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_COL16");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <int LOGL, bool FWD>
 static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t B, bool* done) {
   constexpr int T = col_t<LOGL>::value, L = 1 << LOGL;
@@ -459,10 +499,22 @@ static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, siz
   if (int rc = get_big_twiddles(ctx, LOGL + ilog2(B), &btw)) return rc;
   const float2* tw = nullptr;
   if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
-  auto kern = fft_col_tma_kernel<LOGL, T, FWD>;
   const size_t smem = tile_tma_smem<LOGL, T>::bytes(btw.q);
   const size_t ntiles = A * (B / T);
   unsigned grid = 1;
+  if constexpr (LOGL == 7 || LOGL == 8) {
+    if (use_col16()) {
+      auto kern16 = fft_col16_tma_kernel<LOGL, T, FWD>;
+      constexpr int threads = col16_threads<LOGL, T>::value;
+      if (int rc = persistent_grid(ctx, kern16, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
+      kern16<<<grid, threads, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, raw_params{});
+      ctx->launches++;
+      CK(cudaGetLastError());
+      *done = true;
+      return 0;
+    }
+  }
+  auto kern = fft_col_tma_kernel<LOGL, T, FWD>;
   if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
   kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, raw_params{});
   ctx->launches++;
@@ -492,10 +544,23 @@ static int launch_col_tma_raw(srtb_b200_ctx* ctx, const raw_source& src, float2*
   if (int rc = get_big_twiddles(ctx, LOGL + ilog2(B), &btw)) return rc;
   const float2* tw = nullptr;
   if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
-  auto kern = fft_col_tma_kernel<LOGL, T, true, RAW>;
   const size_t smem = tile_tma_smem<LOGL, T>::bytes(btw.q);
   const size_t ntiles = B / T;
   unsigned grid = 1;
+  if constexpr (LOGL == 7 || LOGL == 8) {
+    if (use_col16()) {
+      auto kern16 = fft_col16_tma_kernel<LOGL, T, true, RAW>;
+      constexpr int threads = col16_threads<LOGL, T>::value;
+      if (int rc = persistent_grid(ctx, kern16, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
+      kern16<<<grid, threads, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
+                                                   raw_params{src.G, src.o0, src.o1});
+      ctx->launches++;
+      CK(cudaGetLastError());
+      *done = true;
+      return 0;
+    }
+  }
+  auto kern = fft_col_tma_kernel<LOGL, T, true, RAW>;
   if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
   kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
                                                                 raw_params{src.G, src.o0, src.o1});
@@ -1060,6 +1125,28 @@ static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t 
 template <int LOGL>
 static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, float lo_, float hi_, size_t ts_count,
                             size_t* chunks_out) {
+  if constexpr (has_row16<LOGL>::value && LOGL >= 9) {
+    if (use_row16()) {
+      constexpr int T16 = row16_t<LOGL>::value, threads = ((1 << LOGL) / 16) * T16;
+      auto kern = fft_row16_tma_kernel<LOGL, T16, false, true>;
+      constexpr size_t smem = row16_smem<LOGL, T16>::bytes;
+      const size_t ntiles = (chan_count + T16 - 1) / T16;
+      unsigned grid = 1;
+      if (int rc = persistent_grid(ctx, kern, threads, smem, smem, ntiles, &grid)) return rc;
+      size_t have = ctx->colsum_partial_elems * sizeof(float);
+      if (int rc = ensure(ctx, reinterpret_cast<void**>(&ctx->colsum_partial), &have, (size_t)grid * ts_count * sizeof(float)))
+        return rc;
+      ctx->colsum_partial_elems = have / sizeof(float);
+      const float2* tw = nullptr;
+      if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+      row_sk_params p{lo_, hi_, ctx->colsum_partial, (unsigned)ts_count};
+      kern<<<grid, threads, smem, ctx->stream>>>(x, x, chan_count, tw, p);
+      ctx->launches++;
+      CK(cudaGetLastError());
+      *chunks_out = grid;
+      return 0;
+    }
+  }
   constexpr int T = row_t<LOGL>::value;
   auto kern = fft_row_tma_kernel<LOGL, T, false, true>;
   constexpr size_t smem = row_tma_smem<LOGL, T>::bytes;
