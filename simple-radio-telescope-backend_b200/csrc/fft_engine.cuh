@@ -1386,6 +1386,122 @@ __global__ void __launch_bounds__(2 * pass_threads<LOGL, T>::value)
   }
 }
 
+// Sixteen-points-per-thread form of the fused last pass + split (L = 256 as 16 x 16, L = 128 as 16 x 8):
+// one exchange between the two stages, then the [2T][L+1] result array; same tiles, mirror rule and
+// results (up to fp32 rounding) as fft_trans_r2c_tma_kernel.
+template <int LOGL, int T>
+__global__ void __launch_bounds__(2 * T * ((1 << LOGL) / 16), 3)
+    fft_trans_r2c16_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, uint32_t A,
+                               uint32_t S_, uint32_t L1, uint32_t tiles_per_rest, uint32_t ntiles,
+                               const float2* __restrict__ tw, double* __restrict__ partial) {
+  constexpr bool FWD = true;
+  constexpr int T2 = 2 * T;
+  using SC = sched16<LOGL>;
+  static_assert(SC::S == 2 && T2 == 16, "two radix stages, sixteen sequences per tile");
+  constexpr int L = 1 << LOGL, U = L / 16, BUF = trans_r2c_smem<LOGL, T>::BUF, LP = L + 1;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  float2* const buf0 = reinterpret_cast<float2*>(smraw);
+  float2* const buf1 = buf0 + BUF;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  float2* const ltw = reinterpret_cast<float2*>(smraw + 2 * (size_t)BUF * sizeof(float2) + 128);
+  float2* const htw = ltw + L;  // e^{-i pi kk / L}
+  __shared__ double red[32];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < L; i += blockDim.x) {
+    ltw[i] = __ldg(&tw[i]);
+    float sn, cs;
+    sincospif(-(float)i / (float)L, &sn, &cs);
+    htw[i] = make_float2(cs, sn);
+  }
+  const int t0 = tid / U, u0 = tid % U;    // stage 0: lanes along the FFT index
+  const int t1 = tid % T2, u1 = tid / T2;  // stage 1: lanes along the 2T sequences
+  // exchange layout: column rotated by idx >> 4 so both mappings are conflict-free
+  auto at = [](int idx, int t) { return idx * T2 + ((t + (idx >> 4)) & (T2 - 1)); };
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const size_t M = (size_t)A << LOGL;
+  auto issue = [&](uint32_t tl, int b) {
+    const uint32_t tau = tl % tiles_per_rest, rest = tl / tiles_per_rest;
+    const uint32_t k10 = tau * T;
+    float2* dst = b ? buf1 : buf0;
+    fence_proxy_async();
+    mbar_expect_tx(&mbar[b], (uint32_t)(T2 * L * sizeof(float2)));
+    tma_load_3d(dst, &tmap, 0, (int)rest, (int)k10, &mbar[b]);                                          // primary
+    tma_load_3d(dst + T * L, &tmap, 0, (int)(S_ - 1 - rest), (int)(L1 - k10 - (T - 1)), &mbar[b]);      // mirror
+  };
+  float acc = 0.f;
+  uint32_t tile = blockIdx.x;
+  if (tile < ntiles && tid == 0) issue(tile, 0);
+  for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int b = it & 1;
+    float2* const sm = b ? buf1 : buf0;
+    const uint32_t nxt = tile + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue(nxt, b ^ 1);
+    mbar_wait(&mbar[b], (it >> 1) & 1);
+    float2 v[16];
+    int oidx[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = sm[t0 * L + u0 + e * U];
+    stage_compute16<LOGL, SC::logr(0), 0, FWD>(v, u0, ltw, oidx);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; e++) sm[at(oidx[e], t0)] = v[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = sm[at(u1 + e * U, t1)];
+    stage_compute16<LOGL, SC::logr(1), SC::logns(1), FWD>(v, u1, ltw, oidx);
+    __syncthreads();  // exchange buffer fully read: reuse it as the [2T][L+1] result array
+#pragma unroll
+    for (int e = 0; e < 16; e++) sm[t1 * LP + u1 + e * U] = v[e];
+    __syncthreads();
+    {
+      const uint32_t tau = tile % tiles_per_rest, rest = tile / tiles_per_rest;
+      const uint32_t k10 = tau * T;
+      const bool last_tile = (tau == tiles_per_rest - 1);  // k10 == L1/2: only its slot 0 is new work
+      // thread (u1, t1): primary slot t = t1 % T, output indices kk = u1 + e*U for e in [8*(t1/T), 8*(t1/T)+8)
+      const int t = t1 % T, e0 = 8 * (t1 / T);
+      const uint32_t k1 = k10 + t;
+      const float2 wbase = r2c_split_twiddle((size_t)k1 + (size_t)L1 * rest, M);
+#pragma unroll
+      for (int e = e0; e < e0 + 8; e++) {
+        const int kk = u1 + e * U;
+        const float2 hk = sm[t * LP + kk];
+        const float2 hm = sm[(T2 - 1 - t) * LP + (L - 1 - kk)];
+        const size_t gk = (size_t)k1 + (size_t)L1 * rest + (size_t)A * kk;
+        const bool self_dup = last_tile && (rest > S_ - 1 - rest || (rest == S_ - 1 - rest && 2 * kk >= L));
+        if (k1 == 0) {
+          out[gk] = hk;  // column 0: raw H, finished by the fix-up kernel
+        } else if (!(last_tile && t > 0) && !self_dup) {
+          const float2 F = make_float2(0.5f * (hk.x + hm.x), 0.5f * (hk.y - hm.y));
+          const float2 G = make_float2(0.5f * (hk.y + hm.y), -0.5f * (hk.x - hm.x));
+          const float2 w = c_mul(wbase, htw[kk]);
+          const float2 gw = make_float2(G.x * w.x - G.y * w.y, G.x * w.y + G.y * w.x);
+          const float2 xk = make_float2(F.x + gw.x, F.y + gw.y);
+          const float2 xm = make_float2(F.x - gw.x, -(F.y - gw.y));
+          out[gk] = xk;
+          out[M - gk] = xm;
+          acc += (xk.x * xk.x + xk.y * xk.y) + (xm.x * xm.x + xm.y * xm.y);
+        }
+      }
+    }
+    __syncthreads();  // result array consumed: the buffer may be refilled from the next iteration on
+  }
+  double s = (double)acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double a = 0.0;
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; w++) a += red[w];
+    partial[blockIdx.x] = a;
+  }
+}
+
 // column k1 = 0 of the fused split (indices that are multiples of L1, mirror = M - index), the Nyquist
 // bin, and the final mean of |X_k|^2 over k < M. One pair per thread; the last CTA to finish adds the
 // partials of the fused pass and of this kernel in index order.

@@ -475,6 +475,23 @@ static int persistent_grid(srtb_b200_ctx* ctx, K kern, int threads, size_t smem,
   return 0;
 }
 
+// three-sweep factorisation of 2^q: the first sweep takes ceil(q/3); of the rest the longer half goes to the
+// LAST sweep (2^23 = 2^8 * 2^7 * 2^8) so that the transposing pass runs as 16 x 16; SRTB_B200_PLAN_878=0
+// gives the longer half to the middle sweep instead (8, 8, 7)
+static bool plan_last_long() {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_PLAN_878");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+static void plan3(int q, int* l1, int* l2, int* l3) {
+  *l1 = (q + 2) / 3;
+  const int big = (q - *l1 + 1) / 2, small = q - *l1 - big;
+  *l2 = plan_last_long() ? small : big;
+  *l3 = plan_last_long() ? big : small;
+}
+
 // sixteen-points-per-thread column kernels (radix 16 x 16 / 16 x 8) for L = 256 / 128; SRTB_B200_COL16=0
 // selects the eight-point kernels instead (A/B measurements)
 static bool use_col16() {
@@ -726,7 +743,8 @@ static int fft_c2c_impl(srtb_b200_ctx* ctx, float2* x, size_t n, size_t batch) {
     if (int rc = dispatch_col<FWD>(ctx, l1, x, s, batch, L2)) return rc;
     return dispatch_trans<FWD>(ctx, l2, s, x, batch, L1, L1);
   }
-  const int l1 = (q + 2) / 3, l2 = (q - l1 + 1) / 2, l3 = q - l1 - l2;
+  int l1, l2, l3;
+  plan3(q, &l1, &l2, &l3);
   const size_t L1 = (size_t)1 << l1, L2 = (size_t)1 << l2, L3 = (size_t)1 << l3;
   if (int rc = dispatch_col<FWD>(ctx, l1, x, s, batch, L2 * L3)) return rc;
   if (int rc = dispatch_col<FWD>(ctx, l2, s, s, batch * L1, L3)) return rc;
@@ -748,18 +766,32 @@ extern "C" int srtb_b200_watfft_c2c_backward(srtb_b200_ctx* ctx, void* d_x, size
   return srtb_b200_fft_c2c(ctx, d_x, length, batch, -1);
 }
 
+static int fft_r2c_with_power_mean(srtb_b200_ctx* ctx, float* d_inout, size_t n_real, const raw_source* raw = nullptr,
+                                   bool* raw_used = nullptr);
+
 extern "C" int srtb_b200_fft_r2c_inplace(srtb_b200_ctx* ctx, float* d_inout, size_t n_real) {
   if (!ctx || !d_inout) return fail(ctx, SRTB_B200_E_INVALID, "fft_r2c: null argument");
   if (n_real < 2 || !is_pow2(n_real))
     return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(n_real));
   CK(cudaSetDevice(ctx->device));
   const size_t M = n_real / 2;
+  if (M >= ((size_t)1 << 13) && (reinterpret_cast<uintptr_t>(d_inout) & 15u) == 0)
+    return fft_r2c_with_power_mean(ctx, d_inout, n_real);  // multi-sweep sizes: split fused into the last sweep
   float2* H = reinterpret_cast<float2*>(d_inout);
   if (int rc = fft_c2c_impl<true>(ctx, H, M, 1)) return rc;
   r2c_post_kernel<false><<<grid_for(ctx, M / 2 + 1, 256), 256, 0, ctx->stream>>>(H, M, nullptr, nullptr, nullptr);
   ctx->launches++;
   CK(cudaGetLastError());
   return 0;
+}
+
+// SRTB_B200_TRANS16=0: eight-point fused last pass; SRTB_B200_PLAN_878=0: factor 2^23 as 8,8,7 instead of 8,7,8
+static bool use_trans16() {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_TRANS16");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 // launch of the fused last pass + split (LOGL <= 8 keeps two [2T][L] tiles double-buffered in smem)
@@ -776,15 +808,29 @@ static int launch_trans_r2c(srtb_b200_ctx* ctx, const float2* in, float2* out, s
   if (!make_tensor_map(&tm, in, 3, dims, strides, box)) return 0;
   const float2* tw = nullptr;
   if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
-  auto kern = fft_trans_r2c_tma_kernel<LOGL, T>;
   constexpr size_t smem = trans_r2c_smem<LOGL, T>::bytes;
   const size_t tiles_per_rest = L1 / (2 * T) + 1, ntiles = S * tiles_per_rest;
   unsigned grid = 1;
-  if (int rc = persistent_grid(ctx, kern, 2 * pass_threads<LOGL, T>::value, smem, smem, ntiles, &grid)) return rc;
-  grid = std::min<unsigned>(grid, 2048);
-  kern<<<grid, 2 * pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
-                                                                      (uint32_t)tiles_per_rest, (uint32_t)ntiles, tw,
-                                                                      ctx->partial);
+  bool launched = false;
+  if constexpr (LOGL == 7 || LOGL == 8) {
+    if (use_trans16()) {
+      auto kern16 = fft_trans_r2c16_tma_kernel<LOGL, T>;
+      constexpr int threads = 2 * T * (L / 16);
+      if (int rc = persistent_grid(ctx, kern16, threads, smem, smem, ntiles, &grid)) return rc;
+      grid = std::min<unsigned>(grid, 2048);
+      kern16<<<grid, threads, smem, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
+                                                  (uint32_t)tiles_per_rest, (uint32_t)ntiles, tw, ctx->partial);
+      launched = true;
+    }
+  }
+  if (!launched) {
+    auto kern = fft_trans_r2c_tma_kernel<LOGL, T>;
+    if (int rc = persistent_grid(ctx, kern, 2 * pass_threads<LOGL, T>::value, smem, smem, ntiles, &grid)) return rc;
+    grid = std::min<unsigned>(grid, 2048);
+    kern<<<grid, 2 * pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
+                                                                        (uint32_t)tiles_per_rest, (uint32_t)ntiles, tw,
+                                                                        ctx->partial);
+  }
   ctx->launches++;
   CK(cudaGetLastError());
   {
@@ -802,8 +848,8 @@ static int launch_trans_r2c(srtb_b200_ctx* ctx, const float2* in, float2* out, s
 // R2C whose split pass also leaves mean(|X_k|^2, k < N/2) in ctx->mean (used by process_block:
 // the s1 statistic costs no extra sweep). For multi-pass sizes the split is fused into the last FFT
 // pass (fft_trans_r2c_tma_kernel), so the packed transform costs P sweeps instead of P + 1.
-static int fft_r2c_with_power_mean(srtb_b200_ctx* ctx, float* d_inout, size_t n_real, const raw_source* raw = nullptr,
-                                   bool* raw_used = nullptr) {
+static int fft_r2c_with_power_mean(srtb_b200_ctx* ctx, float* d_inout, size_t n_real, const raw_source* raw,
+                                   bool* raw_used) {
   if (raw_used) *raw_used = false;
   const size_t M = n_real / 2;
   float2* H = reinterpret_cast<float2*>(d_inout);
@@ -815,9 +861,7 @@ static int fft_r2c_with_power_mean(srtb_b200_ctx* ctx, float* d_inout, size_t n_
       l1 = (q + 1) / 2;
       l2 = q - l1;
     } else {
-      l1 = (q + 2) / 3;
-      l2 = (q - l1 + 1) / 2;
-      l3 = q - l1 - l2;
+      plan3(q, &l1, &l2, &l3);
     }
     const int llast = l3 ? l3 : l2;
     if (llast >= 6 && llast <= 8 && get_encode_tiled()) {
