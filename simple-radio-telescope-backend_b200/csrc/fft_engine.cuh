@@ -199,9 +199,19 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
 
 template <int LOGL>
 struct sched16 {
-  static constexpr int S = (LOGL + 3) / 4;
-  __host__ __device__ static constexpr int logr(int s) { return (s < S - 1) ? 4 : (LOGL - 4 * (S - 1)); }
-  __host__ __device__ static constexpr int logns(int s) { return 4 * s; }
+  // two stages up to L = 256 (16 x 2^(LOGL-4)); three above: 512 = 16*8*4, 1024 = 16*16*4, 2048 = 16*16*8,
+  // 4096 = 16^3 (every radix is 4, 8 or 16)
+  static constexpr int S = (LOGL <= 8) ? 2 : 3;
+  __host__ __device__ static constexpr int logr(int s) {
+    if (LOGL <= 8) return s == 0 ? 4 : LOGL - 4;
+    if (LOGL == 9) return s == 0 ? 4 : (s == 1 ? 3 : 2);
+    return s < 2 ? 4 : LOGL - 8;
+  }
+  __host__ __device__ static constexpr int logns(int s) {
+    int a = 0;
+    for (int i = 0; i < s; i++) a += logr(i);
+    return a;
+  }
 };
 
 // stage_compute for sixteen slots: slot e is the point read at u + e*U (U = L/16); radix 16 (one
@@ -670,8 +680,8 @@ struct row16_smem {
   static constexpr int L = 1 << LOGL;
   static constexpr int BUF = T * L;
   static constexpr int S = sched16<LOGL>::S;
-  // stage s >= 1: three tables (W^k, W^2k, W^4k) of 16^s entries
-  static constexpr int TW = 3 * ((S > 1 ? 16 : 0) + (S > 2 ? 256 : 0));
+  // stage s >= 1: three tables (W^k, W^2k, W^4k) of Ns = 2^logns(s) entries
+  static constexpr int TW = 3 * ((1 << sched16<LOGL>::logns(1)) + (S > 2 ? (1 << sched16<LOGL>::logns(2)) : 0));
   static constexpr size_t bytes = 2 * (size_t)BUF * sizeof(float2) + 128 + (size_t)(TW + 8) * sizeof(float2);
 };
 
@@ -731,7 +741,7 @@ __global__ void __launch_bounds__(((1 << LOGL) / 16) * T, 3)
                          const float2* __restrict__ tw, row_sk_params skp) {
   using SC = sched16<LOGL>;
   constexpr int L = 1 << LOGL, U = L / 16, S = SC::S, BUF = row16_smem<LOGL, T>::BUF;
-  static_assert(S == 2 || S == 3, "256 <= L <= 4096");
+  static_assert(S == 2 || S == 3, "64 <= L <= 4096");
   extern __shared__ __align__(128) unsigned char smraw[];
   float2* const buf0 = reinterpret_cast<float2*>(smraw);
   float2* const buf1 = buf0 + BUF;
@@ -746,9 +756,10 @@ __global__ void __launch_bounds__(((1 << LOGL) / 16) * T, 3)
     fence_mbar_init();
   }
   // stage s >= 1 (Ns = 16^s, radix R): tables p = 1, 2, 4 of W_{Ns*R}^{k p} = W_L^{(k p) << (LOGL - 4s - logr)}
+  constexpr int OFF2 = 3 << SC::logns(1);  // table offset of the third stage
 #pragma unroll
   for (int s = 1; s < S; s++) {
-    const int ns = 1 << (4 * s), off = (s == 1) ? 0 : 48, sh = LOGL - 4 * s - SC::logr(s);
+    const int ns = 1 << SC::logns(s), off = (s == 1) ? 0 : OFF2, sh = LOGL - SC::logns(s) - SC::logr(s);
     for (int i = tid; i < 3 * ns; i += blockDim.x) {
       const int p = i / ns, k = i - p * ns;
       ctw[off + i] = __ldg(&tw[(k << p) << sh]);
@@ -766,8 +777,7 @@ __global__ void __launch_bounds__(((1 << LOGL) / 16) * T, 3)
   float colacc[SK ? 16 : 1];
 #pragma unroll
   for (int e = 0; e < (SK ? 16 : 1); e++) colacc[e] = 0.f;
-  __shared__ float sk_s2[T][(U + 31) / 32], sk_s4[T][(U + 31) / 32];
-  __shared__ int sk_zap[T];
+  __shared__ float sk_s2[2][T][(U + 31) / 32], sk_s4[2][T][(U + 31) / 32];
   unsigned tile = blockIdx.x;
   if (tile < ntiles && tid == 0) issue(tile, 0);
   for (unsigned it = 0; tile < ntiles; tile += gridDim.x, it++) {
@@ -798,7 +808,7 @@ __global__ void __launch_bounds__(((1 << LOGL) / 16) * T, 3)
     }
 #pragma unroll
     for (int e = 0; e < 16; e++) v[e] = sm[row16_sw(u + e * U)];
-    stage_compute16_row<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD>(v, u, ctw + ((S == 3) ? 48 : 0), oidx);
+    stage_compute16_row<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD>(v, u, ctw + ((S == 3) ? OFF2 : 0), oidx);
     if constexpr (SK) {
       static_assert(!SK || U >= 32, "SK fusion needs at least one warp per row");
       float s2 = 0.f, s4 = 0.f;
@@ -813,22 +823,30 @@ __global__ void __launch_bounds__(((1 << LOGL) / 16) * T, 3)
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         s4 += __shfl_xor_sync(0xffffffffu, s4, o);
       }
+      // per-warp partials alternate between two slots so that one barrier per tile is enough
+      float(*const ps2)[(U + 31) / 32] = sk_s2[it & 1];
+      float(*const ps4)[(U + 31) / 32] = sk_s4[it & 1];
       if ((tid & 31) == 0) {
-        sk_s2[t][u >> 5] = s2;
-        sk_s4[t][u >> 5] = s4;
+        ps2[t][u >> 5] = s2;
+        ps4[t][u >> 5] = s4;
       }
       __syncthreads();
-      if (u == 0) {
-        float a = 0.f, bsum = 0.f;
-        for (int w = 0; w < (U + 31) / 32; w++) {  // fixed order
-          a += sk_s2[t][w];
-          bsum += sk_s4[t][w];
+      bool zap;
+      {
+        // every warp folds the row's NW per-warp partials with the same fixed shuffle tree
+        constexpr int NW = (U + 31) / 32;
+        const int lane = tid & 31;
+        float a = (lane < NW) ? ps2[t][lane] : 0.f, bsum = (lane < NW) ? ps4[t][lane] : 0.f;
+#pragma unroll
+        for (int o = NW / 2; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
         }
+        a = __shfl_sync(0xffffffffu, a, 0);
+        bsum = __shfl_sync(0xffffffffu, bsum, 0);
         const float sk = (float)L * (bsum / (a * a));
-        sk_zap[t] = (sk > skp.thr_hi || sk < skp.thr_lo) ? 1 : 0;  // NaN (all-zero row): untouched
+        zap = (sk > skp.thr_hi || sk < skp.thr_lo);  // NaN (all-zero row): untouched
       }
-      __syncthreads();
-      const bool zap = sk_zap[t] != 0;
       if (valid) {
         float2* o = out + (row << LOGL) + u;
 #pragma unroll
@@ -1036,16 +1054,16 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
 template <int LOGL, int T>
 struct col16_threads {
   static constexpr int value = ((1 << LOGL) / 16) * T;
+  static constexpr int min_blocks = (768 / value) < 1 ? 1 : (768 / value);  // aim at 24 resident warps per SM
 };
 
 template <int LOGL, int T, bool FWD, int RAW = 0>
-__global__ void __launch_bounds__(col16_threads<LOGL, T>::value, 3)
+__global__ void __launch_bounds__(col16_threads<LOGL, T>::value, col16_threads<LOGL, T>::min_blocks)
     fft_col16_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, size_t B,
                          uint32_t btiles, uint32_t ntiles, big_twiddle btw, const float2* __restrict__ tw,
                          raw_params rp) {
   using SC = sched16<LOGL>;
-  static_assert(SC::S == 2, "two-stage lengths only (32 <= L <= 256)");
-  constexpr int L = 1 << LOGL, U = L / 16, BUF = tile_tma_smem<LOGL, T>::BUF;
+  constexpr int L = 1 << LOGL, U = L / 16, S = SC::S, BUF = tile_tma_smem<LOGL, T>::BUF;
   constexpr int ROWS_PER_BOX = (L < 256) ? L : 256;
   extern __shared__ __align__(128) unsigned char smraw[];
   float2* const buf0 = reinterpret_cast<float2*>(smraw);
@@ -1109,9 +1127,18 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, 3)
 #pragma unroll
     for (int e = 0; e < 16; e++) sm[oidx[e] * T + t] = v[e];
     __syncthreads();
+    if constexpr (S == 3) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) v[e] = sm[(u + e * U) * T + t];
+      __syncthreads();
+      stage_compute16<LOGL, SC::logr(1), SC::logns(1), FWD>(v, u, ltw, oidx);
+#pragma unroll
+      for (int e = 0; e < 16; e++) sm[oidx[e] * T + t] = v[e];
+      __syncthreads();
+    }
 #pragma unroll
     for (int e = 0; e < 16; e++) v[e] = sm[(u + e * U) * T + t];
-    stage_compute16<LOGL, SC::logr(1), SC::logns(1), FWD>(v, u, ltw, oidx);
+    stage_compute16<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD>(v, u, ltw, oidx);
     {
       // store k = u + e*U of column b0 + t, times W_{L*B}^{k (b0 + t)} = wb * r1^e; the sixteen powers
       // are formed as hi[e >> 2] * lo[e & 3] (products of at most three table values deep)

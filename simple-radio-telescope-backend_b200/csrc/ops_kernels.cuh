@@ -567,8 +567,7 @@ __global__ void __launch_bounds__(256) dedisperse_kernel(const float2* in, float
   const float limit = S1 ? threshold * (*mean) : 0.f;
   float4* x4 = reinterpret_cast<float4*>(x);
   const float4* in4 = reinterpret_cast<const float4*>(in);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += stride) {
-    float4 v = in4[i];
+  auto one = [&](float4 v, size_t i) {
     if (S1) {
       const float p0 = v.x * v.x + v.y * v.y, p1 = v.z * v.z + v.w * v.w;
       if (p0 > limit) { v.x = 0.f; v.y = 0.f; } else { v.x *= coef; v.y *= coef; }
@@ -576,10 +575,16 @@ __global__ void __launch_bounds__(256) dedisperse_kernel(const float2* in, float
     }
     const float2 w0 = chirp_factor(f_min, df, inv_fc, f_c, ddm, (unsigned)(2 * i));
     const float2 w1 = chirp_factor(f_min, df, inv_fc, f_c, ddm, (unsigned)(2 * i + 1));
-    const float4 o = make_float4(v.x * w0.x - v.y * w0.y, v.x * w0.y + v.y * w0.x,
-                                 v.z * w1.x - v.w * w1.y, v.z * w1.y + v.w * w1.x);
-    x4[i] = o;
+    x4[i] = make_float4(v.x * w0.x - v.y * w0.y, v.x * w0.y + v.y * w0.x,
+                        v.z * w1.x - v.w * w1.y, v.z * w1.y + v.w * w1.x);
+  };
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < pairs; i += 2 * stride) {  // two independent 16-byte loads in flight per thread
+    const float4 a = in4[i], b = in4[i + stride];
+    one(a, i);
+    one(b, i + stride);
   }
+  if (i < pairs) one(in4[i], i);
   if (blockIdx.x == 0 && threadIdx.x == 0 && (count & 1)) {
     float2 v = in[count - 1];
     if (S1) {

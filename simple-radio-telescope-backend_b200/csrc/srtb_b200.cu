@@ -372,7 +372,7 @@ static bool use_row16() {
 }
 template <int LOGL>
 struct has_row16 {
-  static constexpr bool value = (LOGL == 8 || LOGL == 10 || LOGL == 11 || LOGL == 12);
+  static constexpr bool value = (LOGL >= 8 && LOGL <= 12);
 };
 
 template <int LOGL, bool FWD>
@@ -488,8 +488,10 @@ static bool plan_last_long() {
 static void plan3(int q, int* l1, int* l2, int* l3) {
   *l1 = (q + 2) / 3;
   const int big = (q - *l1 + 1) / 2, small = q - *l1 - big;
-  *l2 = plan_last_long() ? small : big;
-  *l3 = plan_last_long() ? big : small;
+  // the fused R2C last sweep exists up to L = 256: keep the last factor <= 8 when one of the two is
+  const bool last_big = plan_last_long() && big <= 8;
+  *l2 = last_big ? small : big;
+  *l3 = last_big ? big : small;
 }
 
 // sixteen-points-per-thread column kernels (radix 16 x 16 / 16 x 8) for L = 256 / 128; SRTB_B200_COL16=0
@@ -519,7 +521,7 @@ static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, siz
   const size_t smem = tile_tma_smem<LOGL, T>::bytes(btw.q);
   const size_t ntiles = A * (B / T);
   unsigned grid = 1;
-  if constexpr (LOGL == 7 || LOGL == 8) {
+  if constexpr (LOGL >= 7 && LOGL <= 9) {
     if (use_col16()) {
       auto kern16 = fft_col16_tma_kernel<LOGL, T, FWD>;
       constexpr int threads = col16_threads<LOGL, T>::value;
@@ -564,7 +566,7 @@ static int launch_col_tma_raw(srtb_b200_ctx* ctx, const raw_source& src, float2*
   const size_t smem = tile_tma_smem<LOGL, T>::bytes(btw.q);
   const size_t ntiles = B / T;
   unsigned grid = 1;
-  if constexpr (LOGL == 7 || LOGL == 8) {
+  if constexpr (LOGL >= 7 && LOGL <= 9) {
     if (use_col16()) {
       auto kern16 = fft_col16_tma_kernel<LOGL, T, true, RAW>;
       constexpr int threads = col16_threads<LOGL, T>::value;
@@ -1169,7 +1171,7 @@ static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t 
 template <int LOGL>
 static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, float lo_, float hi_, size_t ts_count,
                             size_t* chunks_out) {
-  if constexpr (has_row16<LOGL>::value && LOGL >= 9) {
+  if constexpr (has_row16<LOGL>::value && LOGL >= 10) {
     if (use_row16()) {
       constexpr int T16 = row16_t<LOGL>::value, threads = ((1 << LOGL) / 16) * T16;
       auto kern = fft_row16_tma_kernel<LOGL, T16, false, true>;

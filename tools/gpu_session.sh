@@ -14,7 +14,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --stage-iters 1 > gpurun_out/ncu_bench_${TAG}.log 2>&1
 # full capture of the FFT pass kernels + the heaviest elementwise kernels of one step
 ncu --set full --clock-control none --import-source on -k regex:'fft_.*kernel|dedisperse_kernel|r2c_post_kernel|sk_colsum_kernel' \
-    -s 36 -c 16 -o gpurun_out/prof_${TAG} -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --stage-iters 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
+    -s 36 -c 10 -o gpurun_out/prof_${TAG} -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --stage-iters 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
 # per-stage capture: every per-pipe kernel once + one fused block (feeds profiles/traffic.json)
-ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/prof_stages_${TAG} -f python tools/stage_once.py > gpurun_out/ncu_stages_${TAG}.log 2>&1
-ls -la gpurun_out | tail -12
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -o gpurun_out/prof_stages_${TAG} -f python tools/stage_once.py > gpurun_out/ncu_stages_${TAG}.log 2>&1
+du -sh gpurun_out; ls -la gpurun_out | tail -12

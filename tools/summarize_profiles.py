@@ -113,17 +113,15 @@ def main():
             idx = {h: i for i, h in enumerate(hdr)}
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             traffic = []
-            lines += ["## per-stage capture (ncu --set full, L2 flushed between stages; one launch each)", "",
-                      "| # | kernel | time us | dram read MB | dram write MB | issue% | dram% |", "|---|---|---|---|---|---|---|"]
+            lines += ["## per-stage capture (ncu dram byte counters, L2 flushed between stages; one launch each)", "",
+                      "| # | kernel | time us | dram read MB | dram write MB |", "|---|---|---|---|---|"]
             for n_, r in enumerate(data):
                 rd = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * scale.get(units[idx["dram__bytes_read.sum"]], 1)
                 wr = float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * scale.get(units[idx["dram__bytes_write.sum"]], 1)
                 t = r[idx["gpu__time_duration.sum"]]
                 name = short(r[idx["Kernel Name"]])
                 traffic.append({"kernel": name, "dram_read": rd, "dram_write": wr, "time_us": float(t.replace(",", ""))})
-                lines.append(f"| {n_} | `{name}` | {t} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | "
-                             f"{r[idx['smsp__issue_active.avg.pct_of_peak_sustained_active']]} | "
-                             f"{r[idx['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']]} |")
+                lines.append(f"| {n_} | `{name}` | {t} | {rd / 1e6:.1f} | {wr / 1e6:.1f} |")
             lines.append("")
             (PROF / f"{tag}_traffic.json").write_text(json.dumps(traffic, indent=1))
             (PROF / "traffic.json").write_text(json.dumps({"tag": tag, "kernels": traffic}, indent=1))
