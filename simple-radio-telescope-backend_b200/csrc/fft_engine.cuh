@@ -1258,6 +1258,72 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
 }
 
 
+// Sixteen-points-per-thread transposing last sweep (L = 128 as 16 x 8, L = 256 as 16 x 16), T = 16 rows
+// per tile: stage 0 in the row mapping on the TMA buffer, one exchange through the rotated layout,
+// stage 1 in the column mapping, results straight from registers in natural order.
+template <int LOGL, int T, bool FWD>
+__global__ void __launch_bounds__(T * ((1 << LOGL) / 16), 768 / (T * ((1 << LOGL) / 16)))
+    fft_trans16_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, uint32_t A,
+                           uint32_t S_, uint32_t L1, uint32_t k1tiles, uint32_t ntiles,
+                           const float2* __restrict__ tw) {
+  using SC = sched16<LOGL>;
+  static_assert(SC::S == 2 && T == 16 && LOGL <= 8, "two radix stages, sixteen rows per tile");
+  constexpr int L = 1 << LOGL, U = L / 16, BUF = tile_tma_smem<LOGL, T>::BUF;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  float2* const buf0 = reinterpret_cast<float2*>(smraw);
+  float2* const buf1 = buf0 + BUF;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  float2* const ltw = reinterpret_cast<float2*>(smraw + tile_tma_smem<LOGL, T>::data_bytes + 128);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < L; i += blockDim.x) ltw[i] = __ldg(&tw[i]);
+  const int t0 = tid / U, u0 = tid % U;  // stage 0: lanes along the FFT index (rows are contiguous)
+  const int t1 = tid % T, u1 = tid / T;  // stage 1 and the store: lanes along t
+  auto at = [](int idx, int t) { return idx * T + ((t + (idx >> 4)) & (T - 1)); };
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](uint32_t tl, int b) {
+    const uint32_t k1t = tl % k1tiles, r = tl / k1tiles;
+    const uint32_t rest = r % S_, beta = r / S_;
+    fence_proxy_async();
+    mbar_expect_tx(&mbar[b], (uint32_t)(BUF * sizeof(float2)));
+    tma_load_3d(b ? buf1 : buf0, &tmap, 0, (int)rest, (int)(beta * L1 + k1t * T), &mbar[b]);
+  };
+  uint32_t tile = blockIdx.x;
+  if (tile < ntiles && tid == 0) issue(tile, 0);
+  for (uint32_t it = 0; tile < ntiles; tile += gridDim.x, it++) {
+    const int b = it & 1;
+    float2* const sm = b ? buf1 : buf0;
+    const uint32_t nxt = tile + gridDim.x;
+    if (nxt < ntiles && tid == 0) issue(nxt, b ^ 1);
+    mbar_wait(&mbar[b], (it >> 1) & 1);
+    float2 v[16];
+    int oidx[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = sm[t0 * L + u0 + e * U];
+    stage_compute16<LOGL, SC::logr(0), 0, FWD>(v, u0, ltw, oidx);
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; e++) sm[at(oidx[e], t0)] = v[e];
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = sm[at(u1 + e * U, t1)];
+    stage_compute16<LOGL, SC::logr(1), SC::logns(1), FWD>(v, u1, ltw, oidx);
+    {
+      const uint32_t k1t = tile % k1tiles, r = tile / k1tiles;
+      const uint32_t rest = r % S_, beta = r / S_;
+      float2* o = out + (((size_t)beta * A) << LOGL) + (size_t)k1t * T + (size_t)L1 * rest + t1 + (size_t)A * u1;
+#pragma unroll
+      for (int e = 0; e < 16; e++) o[(size_t)A * e * U] = v[e];
+    }
+    __syncthreads();
+  }
+}
+
+
 // ---------------------------------------------------------------------------------
 // Last pass of the packed real transform with the R2C split fused in (process_block only).
 // H = FFT_M(x_even + i x_odd) is produced by this pass in natural order; the split

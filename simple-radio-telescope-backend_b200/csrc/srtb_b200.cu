@@ -615,6 +615,22 @@ static int launch_trans_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, s
   if (!make_tensor_map(&tm, in, 3, dims, strides, box)) return 0;
   const float2* tw = nullptr;
   if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
+  if constexpr ((LOGL == 7 || LOGL == 8) && T == 16) {
+    if (use_col16()) {
+      auto kern16 = fft_trans16_tma_kernel<LOGL, T, FWD>;
+      constexpr int threads = T * (L / 16);
+      const size_t smem16 = tile_tma_smem<LOGL, T>::bytes(0);
+      const size_t k1tiles16 = L1 / T, ntiles16 = batch * S * k1tiles16;
+      unsigned grid16 = 1;
+      if (int rc = persistent_grid(ctx, kern16, threads, smem16, smem16, ntiles16, &grid16)) return rc;
+      kern16<<<grid16, threads, smem16, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
+                                                     (uint32_t)k1tiles16, (uint32_t)ntiles16, tw);
+      ctx->launches++;
+      CK(cudaGetLastError());
+      *done = true;
+      return 0;
+    }
+  }
   auto kern = fft_trans_tma_kernel<LOGL, T, FWD>;
   const size_t smem = tile_tma_smem<LOGL, T>::bytes(0);
   const size_t k1tiles = L1 / T, ntiles = batch * S * k1tiles;

@@ -145,8 +145,8 @@ def test_unpack_errors(ctx):
 
 # ----------------------------------------------------------------------------- FFT
 @pytest.mark.parametrize("k,batch", [(1, 5), (2, 7), (3, 300), (4, 33), (5, 9), (6, 64), (7, 3), (8, 16),
-                                     (9, 5), (10, 4), (11, 3), (12, 5), (13, 3), (14, 2), (16, 2), (20, 1),
-                                     (21, 1), (23, 1)])
+                                     (9, 5), (10, 4), (11, 3), (12, 5), (13, 3), (14, 2), (16, 2), (17, 2),
+                                     (18, 1), (20, 1), (21, 1), (22, 1), (23, 1), (25, 1)])
 @pytest.mark.parametrize("direction", [1, -1])
 def test_fft_c2c_vs_float64(ctx, k, batch, direction):
     rng = np.random.default_rng(k * 31 + batch)
@@ -174,7 +174,7 @@ def test_fft_c2c_matches_oracle_small(ctx, oracle):
         assert rel_l2(d.cpu().numpy(), oracle.fft_c2c(x, direction)) < REL_L2
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 12, 13, 14, 17, 21, 22, 24])
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 12, 13, 14, 16, 17, 18, 21, 22, 24, 26, 27])
 def test_fft_r2c_inplace_vs_float64(ctx, k):
     # input of test-fft_wrappers.cpp:127-131: uniform [-1, 1]
     rng = np.random.default_rng(233 + k)
@@ -473,7 +473,7 @@ def synth_baseband(n, seed, tone=True, pulse=True):
     return np.clip(np.round(v), -127, 127).astype(np.int8)
 
 
-@pytest.mark.parametrize("logn,C_,dm", [(16, 16, 0.0), (20, 256, 10.0)])
+@pytest.mark.parametrize("logn,C_,dm", [(16, 16, 0.0), (20, 256, 10.0), (18, 128, 0.5), (17, 128, 0.0)])
 def test_chain_vs_oracle(ctx, oracle, logn, C_, dm):
     n = 1 << logn
     bb = synth_baseband(n, seed=logn)
