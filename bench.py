@@ -44,6 +44,9 @@ METRIC = "Gsamples/s 8-bit baseband through full dedisperse chain"
 UNIT = "Gsamples/s"
 
 WORKLOADS = {
+    # BASELINE.json configs[0] shape (srtb_config_1644-4559.cfg): 2^30 two-bit samples, inverted 64 MHz band
+    "config1": dict(log2n=30, bits=2, fmt="simple", channels=1 << 11, dm=-478.80, f_low=1437.0, bw=-64.0,
+                    fs=128e6, avg_thr=1.5, sk_thr=1.05, snr=8.0, chan_thr=0.9, maxbox=256, freq_list="1418-1422"),
     # BASELINE.json configs[1]
     "config2": dict(log2n=24, bits=-8, fmt="simple", channels=1 << 11, dm=56.778, f_low=1000.0, bw=500.0,
                     fs=1e9, avg_thr=5.0, sk_thr=1.05, snr=8.0, chan_thr=0.9, maxbox=256, freq_list=""),
@@ -76,10 +79,11 @@ def hbm_peak():
 # kernels of each per-pipe stage, for summing the ncu DRAM traffic of profiles/traffic.json
 STAGE_KERNELS = {
     "unpack": r"^unpack_",
-    "fft_r2c": r"^(fft_col_tma_kernel<.*, 0>|fft_trans_tma_kernel|fft_pass_kernel|r2c_post_kernel<0>)",
+    "fft_r2c": r"^(fft_col(16)?_tma_kernel<.*, 0>|fft_trans(16)?_tma_kernel|fft_trans_r2c(16)?_tma_kernel|fft_pass_kernel|"
+               r"r2c_post_kernel|r2c_col0_fixup_kernel)",
     "rfi_s1": r"^(power_sum_kernel|rfi_s1_apply_kernel|rfi_zero_ranges_kernel)",
     "dedisperse": r"^dedisperse_kernel<0>",
-    "watfft": r"^fft_row_tma_kernel<.*, 0>$",
+    "watfft": r"^fft_row(16)?_tma_kernel<.*, 0>$",
     "rfi_s2": r"^sk_kernel",
     "signal_detect": r"^(colsum_|detect_)",
 }
@@ -97,7 +101,7 @@ def stage_traffic():
         seen_fused = False
         for k in d["kernels"]:
             # the capture ends with one fused process_block: stop at its first kernel (RAW first sweep)
-            if re.search(r"fft_col_tma_kernel<.*, 1>$", k["kernel"]):
+            if re.search(r"fft_col(16)?_tma_kernel<.*, [12]>$", k["kernel"]):
                 seen_fused = True
             if seen_fused:
                 continue
@@ -109,10 +113,13 @@ def stage_traffic():
         return {}, None
 
 
-def synth_block(n_samples: int, streams: int, seed: int) -> np.ndarray:
+def synth_block(n_samples: int, streams: int, seed: int, bits: int = -8) -> np.ndarray:
     """V1/V2-style synthetic voltage: Gaussian sigma 20 + CW tone + a short burst,
-    int8, clipped; multi-stream blocks are laid out by the caller."""
+    int8, clipped; multi-stream blocks are laid out by the caller. Sub-byte widths: uniform random
+    packed samples (white noise)."""
     rng = np.random.default_rng(0x53525442 + seed)
+    if abs(bits) < 8:
+        return rng.integers(0, 256, n_samples * streams * abs(bits) // 8, dtype=np.uint8).view(np.int8)
     v = rng.standard_normal(n_samples * streams, dtype=np.float32) * 20.0
     t = np.arange(n_samples * streams, dtype=np.float32)
     v += 30.0 * np.cos(np.float32(2 * np.pi * 0.1185) * (t % 4096))
@@ -221,7 +228,7 @@ def pick_cpu_threads(w: dict) -> int:
         avail = os.cpu_count() or 1
     cands = sorted({t for t in (avail, avail // 2, avail // 4, 32, 16, 8) if 1 <= t <= avail})
     cfg = oracle_chain_config(w, 1 << 20, [])
-    blk = synth_block(1 << 20, 1, 7).view(np.uint8)
+    blk = synth_block(1 << 20, 1, 7, w["bits"]).view(np.uint8)
     best, best_t = None, None
     for t in cands:
         o.set_threads(t)
@@ -245,7 +252,7 @@ def cpu_chain_seconds(w: dict, n: int, reps: int, streams: int):
     pick_cpu_threads(w)
     pairs = o.eval_rfi_ranges(w["freq_list"]) if w["freq_list"] else []
     cfg = oracle_chain_config(w, n, pairs)
-    blocks = [synth_block(n, 1, 1000 + i) for i in range(min(reps, 2))]
+    blocks = [synth_block(n, 1, 1000 + i, w["bits"]) for i in range(min(reps, 2))]
     t0 = time.perf_counter()
     stage = np.zeros(7)
     for i in range(reps):
@@ -356,7 +363,7 @@ def main():
     # synthetic blocks: distinct per rank and per ring slot
     host_blocks = []
     for i in range(ring):
-        b = synth_block(n, streams, seed=rank * 1000 + i)
+        b = synth_block(n, streams, seed=rank * 1000 + i, bits=w["bits"])
         host_blocks.append(torch.from_numpy(b.view(np.uint8)).pin_memory())
     dev_blocks = [hb.cuda(non_blocking=True) for hb in host_blocks]
     torch.cuda.synchronize()
@@ -449,7 +456,8 @@ def main():
     for i in range(args.warmup):
         step_e2e(i)
     drain_e2e()
-    ms_e2e = timed(step_e2e, args.steps, drain_e2e) / args.steps
+    e2e_runs = [timed(step_e2e, args.steps, drain_e2e) / args.steps for _ in range(3)]
+    ms_e2e = float(np.median(e2e_runs))           # host-side jitter (PCIe, the feeding thread): median of three
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = samples_per_step / (ms_e2e * 1e-3) / 1e9
     d2h = C.sizeof(srtb_b200.DetectResult) * streams
@@ -518,7 +526,28 @@ def main():
             sample_n = min(n, 1 << 24)
             cpu_chain_seconds(w, 1 << 18, 1, 1)        # warm the OpenMP pool
             dt, threads, stage = cpu_chain_seconds(w, sample_n, 2, streams)
+            fast = None
+            try:  # the same chain with a fast CPU FFT (pocketfft) in place of the naive radix-2 for the two FFT stages
+                import scipy.fft as sfft
+                xs = synth_block(sample_n, 1, 1, w["bits"]).astype(np.float32) if abs(w["bits"]) == 8 else \
+                    np.random.default_rng(1).standard_normal(sample_n).astype(np.float32)
+                nc_ = sample_n // 2
+                cols = min(w["channels"], nc_)
+                sfft.rfft(xs[:1 << 16], workers=threads)
+                t0 = time.perf_counter()
+                spec = sfft.rfft(xs, workers=threads)[:nc_].astype(np.complex64)
+                t_r2c = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                sfft.ifft(spec.reshape(cols, nc_ // cols), axis=1, workers=threads, norm="forward")
+                t_wat = time.perf_counter() - t0
+                per_block = dt / (2 * streams) - stage[1] / streams - stage[4] / streams + t_r2c + t_wat
+                fast = {"value": sample_n / per_block / 1e9, "unit": UNIT,
+                        "fft": f"scipy.fft (pocketfft, workers={threads}) for fft_r2c and watfft, other stages as above",
+                        "fft_r2c_s": t_r2c, "watfft_s": t_wat}
+            except Exception as e:
+                fast = {"value": None, "fft": f"failed: {e}"}
             cpu_baseline = {"value": sample_n * streams * 2 / dt / 1e9, "unit": UNIT, "cores": threads,
+                            "fast_fft": fast,
                             "kind": "port",
                             "sample": f"2 blocks of 2^{int(np.log2(sample_n))} samples x{streams} stream(s) of "
                                       "this workload; restated reference operators with the in-tree naive "
@@ -539,6 +568,7 @@ def main():
                        "contexts_per_gpu": len(ctxs), "detections": detections[0]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "runs_ms_per_step": e2e_runs, "note": "median of three runs of K steps each",
                     "h2d_bytes_per_step": block_bytes * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches,
             "roofline": roofline,

@@ -78,6 +78,26 @@ int srtb_b200_synchronize(srtb_b200_ctx* ctx);
 const char* srtb_b200_last_error(const srtb_b200_ctx* ctx); /* ctx may be NULL: last global error */
 /* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
 uint64_t srtb_b200_launch_count(const srtb_b200_ctx* ctx);
+
+/* ---- optional per-stage timing (srtb_b200_stage_stats) ------------------------
+ * When enabled, every stage entry point below records a CUDA-event pair around its launches on the
+ * ctx stream. srtb_b200_stage_stats waits for the LAST call of `stage` and returns its duration and
+ * the algorithmic bytes it moved (unpack N*b/8 + 4N, fft_r2c 8N, rfi_s1 12N, dedisperse 8N,
+ * watfft 8N, rfi_s2 4N, signal_detect 4N, N = real samples of the block), so achieved GB/s =
+ * bytes / ms / 1e6. The reference has no per-pipe device timing (its pipes only .wait()); this is the
+ * measurement hook SURVEY 8b proposes for the drop-in. */
+typedef enum {
+  SRTB_B200_STAGE_UNPACK = 0,
+  SRTB_B200_STAGE_FFT_R2C = 1,
+  SRTB_B200_STAGE_RFI_S1 = 2,
+  SRTB_B200_STAGE_DEDISPERSE = 3,
+  SRTB_B200_STAGE_WATFFT = 4,
+  SRTB_B200_STAGE_RFI_S2 = 5,
+  SRTB_B200_STAGE_SIGNAL_DETECT = 6,
+  SRTB_B200_STAGE_COUNT = 7
+} srtb_b200_stage;
+int srtb_b200_stage_stats_enable(srtb_b200_ctx* ctx, int on);
+int srtb_b200_stage_stats(srtb_b200_ctx* ctx, int stage, double* ms, double* bytes);
 const char* srtb_b200_version(void);
 
 /* ---- unpack: srtb::unpack::unpack<BITS> and the multi-stream unpackers --------------

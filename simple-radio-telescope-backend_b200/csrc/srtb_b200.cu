@@ -62,6 +62,11 @@ struct srtb_b200_ctx {
   // DM sweep working copy of the spectrum
   void* sweep_buf = nullptr;
   size_t sweep_buf_bytes = 0;
+  // optional per-stage timing (srtb_b200_stage_stats)
+  bool stats_on = false;
+  cudaEvent_t stat_ev[SRTB_B200_STAGE_COUNT][2] = {};
+  double stat_bytes[SRTB_B200_STAGE_COUNT] = {};
+  bool stat_have[SRTB_B200_STAGE_COUNT] = {};
   // process_block
   void* d_baseband = nullptr;
   size_t d_baseband_bytes = 0;
@@ -111,6 +116,28 @@ static inline unsigned grid_for(const srtb_b200_ctx* ctx, size_t work_items, int
   const size_t cap = (size_t)ctx->sm_count * per_sm;
   return (unsigned)std::max<size_t>(1, std::min(need, cap));
 }
+
+// records a CUDA-event pair around one stage call when per-stage statistics are enabled
+struct stage_scope {
+  srtb_b200_ctx* ctx;
+  int stage;
+  stage_scope(srtb_b200_ctx* c, int st, double bytes) : ctx(c), stage(st) {
+    if (!ctx->stats_on) {
+      ctx = nullptr;
+      return;
+    }
+    if (!ctx->stat_ev[stage][0]) {
+      cudaEventCreate(&ctx->stat_ev[stage][0]);
+      cudaEventCreate(&ctx->stat_ev[stage][1]);
+    }
+    ctx->stat_bytes[stage] = bytes;
+    ctx->stat_have[stage] = true;
+    cudaEventRecord(ctx->stat_ev[stage][0], ctx->stream);
+  }
+  ~stage_scope() {
+    if (ctx) cudaEventRecord(ctx->stat_ev[stage][1], ctx->stream);
+  }
+};
 
 extern "C" {
 
@@ -172,6 +199,9 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& p : ctx->stream_buf) cudaFree(p);
+  for (auto& ev : ctx->stat_ev)
+    for (auto& e2 : ev)
+      if (e2) cudaEventDestroy(e2);
   delete ctx;
   return 0;
 }
@@ -193,6 +223,25 @@ const char* srtb_b200_last_error(const srtb_b200_ctx* ctx) {
 }
 
 uint64_t srtb_b200_launch_count(const srtb_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int srtb_b200_stage_stats_enable(srtb_b200_ctx* ctx, int on) {
+  if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "stage_stats_enable: ctx is null");
+  ctx->stats_on = on != 0;
+  return 0;
+}
+
+int srtb_b200_stage_stats(srtb_b200_ctx* ctx, int stage, double* ms, double* bytes) {
+  if (!ctx || !ms || !bytes) return fail(ctx, SRTB_B200_E_INVALID, "stage_stats: null argument");
+  if (stage < 0 || stage >= SRTB_B200_STAGE_COUNT) return fail(ctx, SRTB_B200_E_INVALID, "stage_stats: unknown stage");
+  if (!ctx->stat_have[stage]) return fail(ctx, SRTB_B200_E_INVALID, "stage_stats: stage not timed yet (enable first)");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->stat_ev[stage][1]));
+  float t = 0.f;
+  CK(cudaEventElapsedTime(&t, ctx->stat_ev[stage][0], ctx->stat_ev[stage][1]));
+  *ms = t;
+  *bytes = ctx->stat_bytes[stage];
+  return 0;
+}
 
 }  // extern "C"
 
@@ -229,6 +278,7 @@ extern "C" int srtb_b200_unpack(srtb_b200_ctx* ctx, const void* d_in, size_t in_
   if (window < 0 || window > 2) return fail(ctx, SRTB_B200_E_INVALID, "unpack: unknown window");
   if (out_count == 0) return 0;
   const int abits = bits < 0 ? -bits : bits;
+  stage_scope stats_(ctx, SRTB_B200_STAGE_UNPACK, (double)in_bytes + 4.0 * (double)out_count * (format == SRTB_B200_FORMAT_SIMPLE ? 1 : (format == SRTB_B200_FORMAT_GZNUPSR_A1_4 ? 4 : 2)));
   int streams = 1;
   if (format == SRTB_B200_FORMAT_INTERLEAVED_2 || format == SRTB_B200_FORMAT_NAOCPSR_SNAP1 ||
       format == SRTB_B200_FORMAT_GZNUPSR_A1_2)
@@ -781,6 +831,8 @@ extern "C" int srtb_b200_fft_c2c(srtb_b200_ctx* ctx, void* d_x, size_t length, s
 }
 
 extern "C" int srtb_b200_watfft_c2c_backward(srtb_b200_ctx* ctx, void* d_x, size_t length, size_t batch) {
+  if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "watfft: ctx is null");
+  stage_scope stats_(ctx, SRTB_B200_STAGE_WATFFT, 16.0 * (double)length * (double)batch);
   return srtb_b200_fft_c2c(ctx, d_x, length, batch, -1);
 }
 
@@ -793,6 +845,7 @@ extern "C" int srtb_b200_fft_r2c_inplace(srtb_b200_ctx* ctx, float* d_inout, siz
     return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(n_real));
   CK(cudaSetDevice(ctx->device));
   const size_t M = n_real / 2;
+  stage_scope stats_(ctx, SRTB_B200_STAGE_FFT_R2C, 8.0 * (double)n_real);
   if (M >= ((size_t)1 << 13) && (reinterpret_cast<uintptr_t>(d_inout) & 15u) == 0)
     return fft_r2c_with_power_mean(ctx, d_inout, n_real);  // multi-sweep sizes: split fused into the last sweep
   float2* H = reinterpret_cast<float2*>(d_inout);
@@ -996,6 +1049,7 @@ extern "C" int srtb_b200_rfi_s1(srtb_b200_ctx* ctx, void* d_x, size_t count, flo
   if (count == 0) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s1: zero count");
   if (n_ranges && !h_bin_ranges) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s1: null ranges");
   CK(cudaSetDevice(ctx->device));
+  stage_scope stats_(ctx, SRTB_B200_STAGE_RFI_S1, 24.0 * (double)count);
   float2* x = static_cast<float2*>(d_x);
   const unsigned grid = std::min<unsigned>(grid_for(ctx, count / 2 + 1, 256), 4096);
   power_sum_kernel<<<grid, 256, 0, ctx->stream>>>(x, count, ctx->partial, ctx->ticket, ctx->mean);
@@ -1032,6 +1086,7 @@ extern "C" int srtb_b200_dedisperse(srtb_b200_ctx* ctx, void* d_x, size_t count,
   if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "dedisperse: null argument");
   if (count == 0) return 0;
   CK(cudaSetDevice(ctx->device));
+  stage_scope stats_(ctx, SRTB_B200_STAGE_DEDISPERSE, 16.0 * (double)count);
   constexpr double D = 4.148808e3;  // coherent_dedispersion.hpp:67
   const double ddm = (D * 1e6) * (double)dm;
   dedisperse_kernel<false><<<grid_for(ctx, count / 2 + 1, 256, 16), 256, 0, ctx->stream>>>(
@@ -1099,6 +1154,7 @@ extern "C" int srtb_b200_rfi_s2_sk(srtb_b200_ctx* ctx, void* d_x, size_t time_co
   if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s2: null argument");
   if (time_count == 0 || chan_count == 0) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s2: zero size");
   CK(cudaSetDevice(ctx->device));
+  stage_scope stats_(ctx, SRTB_B200_STAGE_RFI_S2, 8.0 * (double)time_count * (double)chan_count);
   const float M_ = static_cast<float>(time_count);
   float hi = sk_threshold, lo = 2 - sk_threshold;
   if (lo > hi) std::swap(lo, hi);
@@ -1312,6 +1368,7 @@ extern "C" int srtb_b200_signal_detect(srtb_b200_ctx* ctx, const void* d_x, size
   if (!ctx || !d_x || !h_result) return fail(ctx, SRTB_B200_E_INVALID, "signal_detect: null argument");
   if (time_count == 0 || chan_count == 0) return fail(ctx, SRTB_B200_E_INVALID, "signal_detect: zero size");
   CK(cudaSetDevice(ctx->device));
+  stage_scope stats_(ctx, SRTB_B200_STAGE_SIGNAL_DETECT, 8.0 * (double)time_count * (double)chan_count);
   if (int rc = detect_enqueue(ctx, 0, static_cast<const float2*>(d_x), time_count, chan_count,
                               time_reserved_count, snr_threshold, channel_threshold, max_boxcar_length))
     return rc;

@@ -83,6 +83,8 @@ SYMBOLS = {
     "srtb_b200_last_error": (C.c_char_p, [_P]),
     "srtb_b200_launch_count": (C.c_uint64, [_P]),
     "srtb_b200_version": (C.c_char_p, []),
+    "srtb_b200_stage_stats_enable": (C.c_int, [_P, C.c_int]),
+    "srtb_b200_stage_stats": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "srtb_b200_unpack": (_I, [_P, _P, _SZ, _I, _I, _I, C.POINTER(_P), _SZ]),
     "srtb_b200_fft_r2c_inplace": (_I, [_P, _P, _SZ]),
     "srtb_b200_fft_c2c": (_I, [_P, _P, _SZ, _SZ, _I]),
@@ -214,6 +216,15 @@ class Context:
                                                   time_reserved_count, snr, channel_threshold, max_boxcar,
                                                   C.byref(res), _ptr(h_series), int(copy_all)))
         return res
+
+    def stage_stats_enable(self, on: bool = True):
+        self._ck(self.lib.srtb_b200_stage_stats_enable(self.h, int(on)))
+
+    def stage_stats(self, stage: int):
+        """(ms, algorithmic bytes) of the last call of `stage` (0 unpack .. 6 signal_detect)"""
+        ms, nbytes = C.c_double(), C.c_double()
+        self._ck(self.lib.srtb_b200_stage_stats(self.h, int(stage), C.byref(ms), C.byref(nbytes)))
+        return ms.value, nbytes.value
 
     def process_block(self, cfg: BlockConfig, baseband, nbytes: int, h_series=None, copy_all: bool = False,
                       on_device: bool = False):

@@ -631,3 +631,103 @@ def test_dm_sweep_equals_single_dm_runs(ctx):
         peaks.append(sum(int(g.signal_count[b]) for b in range(g.n_boxcars)))
     assert peaks[dms.index(true_dm)] > 0
     assert peaks[dms.index(true_dm)] >= max(peaks[0], peaks[-1])
+
+
+def test_j1644_config_shape_full_size(ctx):
+    """BASELINE config #1 shape (srtb_config_1644-4559.cfg: 2^30 two-bit samples per block, C = 2^11, inverted
+    64 MHz band, DM = -478.80, manual zap 1418-1422 MHz) at FULL size. Too large for the CPU oracle, so
+    size-independent properties: Parseval and the DC bin of the 2^30-point R2C on the unpacked block, then the
+    whole chain: the manual-zap channels are gone, noise alone gives no 8-sigma candidates."""
+    n = 1 << 30
+    C_ = 1 << 11
+    g = torch.Generator(device="cuda").manual_seed(1644)
+    blk = torch.randint(0, 256, (n // 4,), dtype=torch.uint8, device="cuda", generator=g)
+    hist = torch.bincount(blk.to(torch.int64), minlength=256).cpu().numpy().astype(np.float64)
+    vals = np.array([[(b >> s) & 3 for s in (6, 4, 2, 0)] for b in range(256)], dtype=np.float64)
+    sum_x = float((hist[:, None] * vals).sum())
+    sum_x2 = float((hist[:, None] * vals ** 2).sum())
+    buf = torch.empty(n + 2, dtype=torch.float32, device="cuda")
+    ctx.unpack(blk, n // 4, 2, srtb_b200.FORMAT_SIMPLE, 0, [buf], n)
+    torch.cuda.synchronize()
+    assert float(buf[:1 << 20].double().sum()) == float(vals.sum(1)[blk[:1 << 18].cpu().numpy()].sum())  # exact
+    ctx.fft_r2c_inplace(buf, n)
+    torch.cuda.synchronize()
+    X = torch.view_as_complex(buf.view(-1, 2))
+    assert X.numel() == n // 2 + 1
+    assert abs(float(X[0].real) / sum_x - 1) < 1e-5 and abs(float(X[0].imag)) <= 1e-6 * sum_x
+    p = 0.0
+    for c in range(0, n // 2 + 1, 1 << 26):
+        xr = torch.view_as_real(X[c:c + (1 << 26)]).double()
+        p += 2.0 * float((xr * xr).sum())
+        del xr
+    p -= float(torch.view_as_real(X[0]).double().pow(2).sum()) + float(torch.view_as_real(X[n // 2]).double().pow(2).sum())
+    assert abs(p / (n * sum_x2) - 1) < 1e-5, p / (n * sum_x2)
+    del buf, X
+    torch.cuda.empty_cache()
+    cfg = make_block_config(n, 2, srtb_b200.FORMAT_SIMPLE, C_, -478.80, f_low=1405.0 + 64 / 2, bw=-64.0, fs=128e6,
+                            avg_thr=1.5, sk_thr=1.05, snr=8.0, maxbox=256, pairs=[(1418.0, 1422.0)])
+    res = ctx.process_block(cfg, blk, n // 4, None, on_device=True)
+    L = n // 2 // C_
+    assert res[0].time_series_count == L and res[0].detect_enabled == 1
+    zap_lo = C_ * 4 // 64                                                      # 4 of 64 MHz zapped by hand
+    assert zap_lo - 2 <= res[0].zero_count <= zap_lo + C_ // 20, res[0].zero_count
+    assert res[0].n_boxcars == 9 and list(res[0].boxcar_length[:9]) == [1 << i for i in range(9)]
+    assert sum(res[0].signal_count[b] for b in range(9)) <= 2                  # noise at 8 sigma
+
+
+def test_dispersed_pulse_full_size_config2(ctx):
+    """BASELINE config #2 at full size with a V3 injection: a 64-sample burst dispersed in
+    float64 with the inverse chirp of DM 56.778 (cyclic within the block, spread over all 2^24 samples: 0.2 counts
+    per sample under sigma-20 noise). Dedispersing at the true DM collects it into one time bin and the detector
+    flags it at 8 sigma; at DM 0 and at 2 x DM the block looks like noise."""
+    n, C_ = 1 << 24, 1 << 11
+    f_low, bw, true_dm = 1000.0, 500.0, 56.778
+    nc = n // 2
+    L = nc // C_
+    rng = np.random.default_rng(56778)
+    pulse = np.zeros(n)
+    t0 = (L // 2) * 2 * C_ + C_ - 32                                 # centred in time bin L/2
+    pulse[t0:t0 + 64] = rng.standard_normal(64) * 120
+    X = np.fft.rfft(pulse)[:nc]
+    f = np.float64(np.float32(f_low)) + np.float64(np.float32(bw) / np.float32(nc)) * np.arange(nc)
+    f_c = np.float64(np.float32(f_low) + np.float32(bw))
+    k = 4.148808e3 * 1e6 * np.float64(np.float32(true_dm)) / f * ((f - f_c) / f_c) ** 2
+    X *= np.exp(+2j * np.pi * (k - np.trunc(k)))
+    v = np.fft.irfft(np.concatenate([X, [0]]), n) + rng.standard_normal(n) * 20
+    assert np.abs(v).max() < 127
+    bb = torch.from_numpy(np.round(v).astype(np.int8).view(np.uint8)).pin_memory()
+    counts = {}
+    for dm in (true_dm, 0.0, 2 * true_dm):
+        # sk 1.25: at L = 4096 the SK estimator of pure noise scatters by ~0.07, so the config's 1.05 window would
+        # zap ~10 % of the channels (the reference's semantics); the wider window keeps this a clean S/N statement
+        cfg = make_block_config(n, -8, srtb_b200.FORMAT_SIMPLE, C_, dm, f_low=f_low, bw=bw, avg_thr=5.0, sk_thr=1.25,
+                                snr=8.0, maxbox=256)
+        series = np.zeros((32, L), np.float32)
+        res = ctx.process_block(cfg, bb, n, series, copy_all=True)[0]
+        assert res.detect_enabled == 1 and res.zero_count <= C_ // 50
+        counts[dm] = [int(res.signal_count[b]) for b in range(res.n_boxcars)]
+        if dm == true_dm:
+            assert counts[dm][0] >= 1 and int(np.argmax(series[0])) == L // 2   # boxcar 1, in the right time bin
+    assert sum(counts[0.0]) == 0 and sum(counts[2 * true_dm]) == 0, counts
+
+
+def test_stage_stats_report_time_and_algorithmic_bytes(ctx):
+    """srtb_b200_stage_stats: per-stage CUDA-event time + the algorithmic bytes of SURVEY 8d"""
+    n = 1 << 20
+    rng = np.random.default_rng(1)
+    raw = dev(rng.integers(0, 256, n, dtype=np.uint8))
+    buf = torch.empty(n + 2, dtype=torch.float32, device="cuda")
+    with pytest.raises(RuntimeError):
+        ctx.stage_stats(0)                       # nothing timed yet
+    ctx.stage_stats_enable(True)
+    ctx.unpack(raw, n, 8, srtb_b200.FORMAT_SIMPLE, 0, [buf], n)
+    ctx.fft_r2c_inplace(buf, n)
+    ctx.dedisperse(buf, n // 2, 1000.0, 1500.0, 500.0 / (n // 2), 10.0)
+    ctx.watfft_c2c_backward(buf, 2048, n // 2 // 2048)
+    ctx.stage_stats_enable(False)
+    expect = {0: n + 4 * n, 1: 8 * n, 3: 8 * n, 4: 8 * n}
+    for stage, nbytes in expect.items():
+        ms, b = ctx.stage_stats(stage)
+        assert b == nbytes and 0 < ms < 50
+    with pytest.raises(RuntimeError):
+        ctx.stage_stats(5)                       # rfi_s2 was never called
