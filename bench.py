@@ -10,7 +10,7 @@ Contract (driver): python bench.py --gpus N --steps K --warmup W [--impl referen
     C = 2^11 channels (srtb_config.cfg thresholds); N > 1 shards independent blocks across ranks
     (weak scaling, no collective on the data path);
   * `value`  = samples / time with the blocks already resident in HBM (ring of 16 distinct blocks,
-    256 MiB > L2, so successive steps never re-read a cached input); blocks alternate over 3 contexts
+    256 MiB > L2, so successive steps never re-read a cached input); blocks alternate over 4 contexts
     (CUDA streams) per GPU, two blocks in flight per context, so one block's small detector-tail kernels
     overlap the next block's FFT sweeps — every block still runs the whole chain and its result is read back;
   * `e2e`    = the same from pinned HOST buffers through srtb_b200_submit_block()/collect_block() (the
@@ -304,7 +304,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SRTB_BENCH_WORKLOAD", "config2"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-iters", type=int, default=5)
-    ap.add_argument("--contexts", type=int, default=int(os.environ.get("SRTB_BENCH_CONTEXTS", "3")),
+    ap.add_argument("--contexts", type=int, default=int(os.environ.get("SRTB_BENCH_CONTEXTS", "4")),
                     help="contexts (CUDA streams) per GPU that blocks alternate over")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
