@@ -1258,6 +1258,13 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
 }
 
 
+// Four-sweep transforms (n = L1*L2*L3*L): the rows of the last sweep are stored as [k1][k2][k3] (k3 fastest),
+// natural order needs k1 + L1*(k2 + L2*k3): swap the two digits of `rest` (rest_inner = L3; 0 or 1 = no swap).
+__device__ __forceinline__ uint32_t rest_digit_swap(uint32_t rest, uint32_t S_, uint32_t rest_inner) {
+  if (rest_inner <= 1) return rest;
+  return rest / rest_inner + (S_ / rest_inner) * (rest % rest_inner);
+}
+
 // Sixteen-points-per-thread transposing last sweep (L = 128 as 16 x 8, L = 256 as 16 x 16), T = 16 rows
 // per tile: stage 0 in the row mapping on the TMA buffer, one exchange through the rotated layout,
 // stage 1 in the column mapping, results straight from registers in natural order.
@@ -1265,7 +1272,7 @@ template <int LOGL, int T, bool FWD>
 __global__ void __launch_bounds__(T * ((1 << LOGL) / 16), 768 / (T * ((1 << LOGL) / 16)))
     fft_trans16_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, uint32_t A,
                            uint32_t S_, uint32_t L1, uint32_t k1tiles, uint32_t ntiles,
-                           const float2* __restrict__ tw) {
+                           const float2* __restrict__ tw, uint32_t rest_inner) {
   using SC = sched16<LOGL>;
   static_assert(SC::S == 2 && T == 16 && LOGL <= 8, "two radix stages, sixteen rows per tile");
   constexpr int L = 1 << LOGL, U = L / 16, BUF = tile_tma_smem<LOGL, T>::BUF;
@@ -1315,7 +1322,8 @@ __global__ void __launch_bounds__(T * ((1 << LOGL) / 16), 768 / (T * ((1 << LOGL
     {
       const uint32_t k1t = tile % k1tiles, r = tile / k1tiles;
       const uint32_t rest = r % S_, beta = r / S_;
-      float2* o = out + (((size_t)beta * A) << LOGL) + (size_t)k1t * T + (size_t)L1 * rest + t1 + (size_t)A * u1;
+      const uint32_t prest = rest_digit_swap(rest, S_, rest_inner);
+      float2* o = out + (((size_t)beta * A) << LOGL) + (size_t)k1t * T + (size_t)L1 * prest + t1 + (size_t)A * u1;
 #pragma unroll
       for (int e = 0; e < 16; e++) o[(size_t)A * e * U] = v[e];
     }
@@ -1486,7 +1494,7 @@ template <int LOGL, int T>
 __global__ void __launch_bounds__(2 * T * ((1 << LOGL) / 16), 3)
     fft_trans_r2c16_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, uint32_t A,
                                uint32_t S_, uint32_t L1, uint32_t tiles_per_rest, uint32_t ntiles,
-                               const float2* __restrict__ tw, double* __restrict__ partial) {
+                               const float2* __restrict__ tw, double* __restrict__ partial, uint32_t rest_inner) {
   constexpr bool FWD = true;
   constexpr int T2 = 2 * T;
   using SC = sched16<LOGL>;
@@ -1558,13 +1566,14 @@ __global__ void __launch_bounds__(2 * T * ((1 << LOGL) / 16), 3)
       // thread (u1, t1): primary slot t = t1 % T, output indices kk = u1 + e*U for e in [8*(t1/T), 8*(t1/T)+8)
       const int t = t1 % T, e0 = 8 * (t1 / T);
       const uint32_t k1 = k10 + t;
-      const float2 wbase = r2c_split_twiddle((size_t)k1 + (size_t)L1 * rest, M);
+      const uint32_t prest = rest_digit_swap(rest, S_, rest_inner);
+      const float2 wbase = r2c_split_twiddle((size_t)k1 + (size_t)L1 * prest, M);
 #pragma unroll
       for (int e = e0; e < e0 + 8; e++) {
         const int kk = u1 + e * U;
         const float2 hk = sm[t * LP + kk];
         const float2 hm = sm[(T2 - 1 - t) * LP + (L - 1 - kk)];
-        const size_t gk = (size_t)k1 + (size_t)L1 * rest + (size_t)A * kk;
+        const size_t gk = (size_t)k1 + (size_t)L1 * prest + (size_t)A * kk;
         const bool self_dup = last_tile && (rest > S_ - 1 - rest || (rest == S_ - 1 - rest && 2 * kk >= L));
         if (k1 == 0) {
           out[gk] = hk;  // column 0: raw H, finished by the fix-up kernel
@@ -1596,7 +1605,7 @@ __global__ void __launch_bounds__(2 * T * ((1 << LOGL) / 16), 3)
 }
 
 // column k1 = 0 of the fused split (indices that are multiples of L1, mirror = M - index), the Nyquist
-// bin, and the final mean of |X_k|^2 over k < M. One pair per thread; the last CTA to finish adds the
+// bin, and the final mean of |X_k|^2 over k < M. Pairs are dealt grid-stride; the last CTA to finish adds the
 // partials of the fused pass and of this kernel in index order.
 __global__ void __launch_bounds__(256) r2c_col0_fixup_kernel(float2* __restrict__ H, size_t M, size_t L1,
                                                               double* __restrict__ partial, unsigned nparts,
@@ -1605,9 +1614,8 @@ __global__ void __launch_bounds__(256) r2c_col0_fixup_kernel(float2* __restrict_
   __shared__ double red[8];
   __shared__ bool last;
   const size_t n = M / L1;  // column length; pairs j <-> n - j
-  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   double acc = 0.0;
-  if (j <= n / 2) {
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j <= n / 2; j += (size_t)gridDim.x * blockDim.x) {
     const size_t k = j * L1;
     const float2 hk = H[k];
     const float2 hm = (k == 0) ? hk : H[M - k];
@@ -1620,7 +1628,7 @@ __global__ void __launch_bounds__(256) r2c_col0_fixup_kernel(float2* __restrict_
     H[k] = xk;
     H[M - k] = xm;
     const float wm = (k == 0 || 2 * k == M) ? 0.f : 1.f;
-    acc = (double)((xk.x * xk.x + xk.y * xk.y) + wm * (xm.x * xm.x + xm.y * xm.y));
+    acc += (double)((xk.x * xk.x + xk.y * xk.y) + wm * (xm.x * xm.x + xm.y * xm.y));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

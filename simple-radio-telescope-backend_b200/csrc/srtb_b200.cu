@@ -544,6 +544,27 @@ static void plan3(int q, int* l1, int* l2, int* l3) {
   *l3 = last_big ? big : small;
 }
 
+// 2^27 points and above: four sweeps of L <= 256 (all on the sixteen-point kernels, each near the HBM roofline)
+// beat three sweeps with 512/1024-point columns; the last factor is 7 or 8 so the fused R2C last sweep applies.
+// 27 = 7+7+6+7, 28 = 7+7+7+7, 29 = 7+7+7+8, 30 = 8+7+7+8. SRTB_B200_FOUR_SWEEPS=0 keeps three sweeps.
+static void plan4(int q, int* l) {
+  l[3] = (q >= 29) ? 8 : 7;
+  int r = q - l[3];
+  l[0] = (r + 2) / 3;
+  l[1] = (r - l[0] + 1) / 2;
+  l[2] = r - l[0] - l[1];
+}
+static bool use_col16();
+static encode_tiled_fn get_encode_tiled();
+static bool four_sweeps(int q, const void* ptr) {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_FOUR_SWEEPS");
+    return !(e && e[0] == '0');
+  }();
+  return on && q >= 27 && q <= 30 && use_col16() && get_encode_tiled() != nullptr &&
+         (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0;
+}
+
 // sixteen-points-per-thread column kernels (radix 16 x 16 / 16 x 8) for L = 256 / 128; SRTB_B200_COL16=0
 // selects the eight-point kernels instead (A/B measurements)
 static bool use_col16() {
@@ -652,7 +673,7 @@ static int dispatch_col_raw(srtb_b200_ctx* ctx, int logl, const raw_source& src,
 
 template <int LOGL, bool FWD>
 static int launch_trans_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t batch, size_t A, size_t L1,
-                            bool* done) {
+                            bool* done, size_t rest_inner = 0) {
   constexpr int T = col_t<LOGL>::value, L = 1 << LOGL;
   *done = false;
   const size_t S = A / L1;
@@ -674,13 +695,14 @@ static int launch_trans_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, s
       unsigned grid16 = 1;
       if (int rc = persistent_grid(ctx, kern16, threads, smem16, smem16, ntiles16, &grid16)) return rc;
       kern16<<<grid16, threads, smem16, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
-                                                     (uint32_t)k1tiles16, (uint32_t)ntiles16, tw);
+                                                     (uint32_t)k1tiles16, (uint32_t)ntiles16, tw, (uint32_t)rest_inner);
       ctx->launches++;
       CK(cudaGetLastError());
       *done = true;
       return 0;
     }
   }
+  if (rest_inner > 1) return 0;  // only the sixteen-point kernel knows the four-sweep row order
   auto kern = fft_trans_tma_kernel<LOGL, T, FWD>;
   const size_t smem = tile_tma_smem<LOGL, T>::bytes(0);
   const size_t k1tiles = L1 / T, ntiles = batch * S * k1tiles;
@@ -811,6 +833,21 @@ static int fft_c2c_impl(srtb_b200_ctx* ctx, float2* x, size_t n, size_t batch) {
     if (int rc = dispatch_col<FWD>(ctx, l1, x, s, batch, L2)) return rc;
     return dispatch_trans<FWD>(ctx, l2, s, x, batch, L1, L1);
   }
+  if (four_sweeps(q, x)) {
+    int l[4];
+    plan4(q, l);
+    const size_t L1 = (size_t)1 << l[0], L2 = (size_t)1 << l[1], L3 = (size_t)1 << l[2];
+    const size_t L4 = (size_t)1 << l[3];
+    if (int rc = dispatch_col<FWD>(ctx, l[0], x, s, batch, L2 * L3 * L4)) return rc;
+    if (int rc = dispatch_col<FWD>(ctx, l[1], s, s, batch * L1, L3 * L4)) return rc;
+    if (int rc = dispatch_col<FWD>(ctx, l[2], s, s, batch * L1 * L2, L4)) return rc;
+    bool done = false;
+    int rc = (l[3] == 7) ? launch_trans_tma<7, FWD>(ctx, s, x, batch, L1 * L2 * L3, L1, &done, L3)
+                         : launch_trans_tma<8, FWD>(ctx, s, x, batch, L1 * L2 * L3, L1, &done, L3);
+    if (rc) return rc;
+    if (!done) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "fft: four-sweep plan needs the TMA last sweep");
+    return 0;
+  }
   int l1, l2, l3;
   plan3(q, &l1, &l2, &l3);
   const size_t L1 = (size_t)1 << l1, L2 = (size_t)1 << l2, L3 = (size_t)1 << l3;
@@ -867,7 +904,8 @@ static bool use_trans16() {
 
 // launch of the fused last pass + split (LOGL <= 8 keeps two [2T][L] tiles double-buffered in smem)
 template <int LOGL>
-static int launch_trans_r2c(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t L1, bool* done) {
+static int launch_trans_r2c(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t L1, bool* done,
+                            size_t rest_inner = 0) {
   constexpr int T = 8, L = 1 << LOGL;
   *done = false;
   const size_t S = A / L1;
@@ -890,10 +928,12 @@ static int launch_trans_r2c(srtb_b200_ctx* ctx, const float2* in, float2* out, s
       if (int rc = persistent_grid(ctx, kern16, threads, smem, smem, ntiles, &grid)) return rc;
       grid = std::min<unsigned>(grid, 2048);
       kern16<<<grid, threads, smem, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
-                                                  (uint32_t)tiles_per_rest, (uint32_t)ntiles, tw, ctx->partial);
+                                                  (uint32_t)tiles_per_rest, (uint32_t)ntiles, tw, ctx->partial,
+                                                  (uint32_t)rest_inner);
       launched = true;
     }
   }
+  if (!launched && rest_inner > 1) return 0;  // four-sweep row order: sixteen-point kernel only
   if (!launched) {
     auto kern = fft_trans_r2c_tma_kernel<LOGL, T>;
     if (int rc = persistent_grid(ctx, kern, 2 * pass_threads<LOGL, T>::value, smem, smem, ntiles, &grid)) return rc;
@@ -906,7 +946,7 @@ static int launch_trans_r2c(srtb_b200_ctx* ctx, const float2* in, float2* out, s
   CK(cudaGetLastError());
   {
     const size_t pairs = ((A << LOGL) / L1) / 2 + 1;
-    const unsigned fgrid = (unsigned)((pairs + 255) / 256);
+    const unsigned fgrid = (unsigned)std::min<size_t>((pairs + 255) / 256, 2048);
     if (grid + fgrid > 4096) return fail(ctx, SRTB_B200_E_SIZE, "r2c: partial buffer too small");
     r2c_col0_fixup_kernel<<<fgrid, 256, 0, ctx->stream>>>(out, A << LOGL, L1, ctx->partial, grid, ctx->ticket, ctx->mean);
   }
@@ -927,6 +967,29 @@ static int fft_r2c_with_power_mean(srtb_b200_ctx* ctx, float* d_inout, size_t n_
   const int q = ilog2(M);
   if (q >= 13 && q <= 30 && M >= 2) {
     // same factorisation as fft_c2c_impl
+    if (four_sweeps(q, d_inout) && use_trans16()) {
+      int l[4];
+      plan4(q, l);
+      if (int rc = ensure(ctx, &ctx->fft_scratch, &ctx->fft_scratch_bytes, M * sizeof(float2))) return rc;
+      float2* s = static_cast<float2*>(ctx->fft_scratch);
+      const size_t L1 = (size_t)1 << l[0], L2 = (size_t)1 << l[1], L3 = (size_t)1 << l[2], L4 = (size_t)1 << l[3];
+      bool first_done = false;
+      if (raw && raw->base) {
+        if (int rc = dispatch_col_raw(ctx, l[0], *raw, s, L2 * L3 * L4, &first_done)) return rc;
+        if (raw_used) *raw_used = first_done;
+        if (!first_done) return SRTB_B200_E_UNSUPPORTED;
+      }
+      if (!first_done)
+        if (int rc = dispatch_col<true>(ctx, l[0], H, s, 1, L2 * L3 * L4)) return rc;
+      if (int rc = dispatch_col<true>(ctx, l[1], s, s, L1, L3 * L4)) return rc;
+      if (int rc = dispatch_col<true>(ctx, l[2], s, s, L1 * L2, L4)) return rc;
+      bool done = false;
+      int rc = (l[3] == 7) ? launch_trans_r2c<7>(ctx, s, H, L1 * L2 * L3, L1, &done, L3)
+                           : launch_trans_r2c<8>(ctx, s, H, L1 * L2 * L3, L1, &done, L3);
+      if (rc) return rc;
+      if (!done) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "r2c: four-sweep plan needs the TMA last sweep");
+      return 0;
+    }
     int l1, l2, l3 = 0;
     if (q <= 20) {
       l1 = (q + 1) / 2;

@@ -146,7 +146,7 @@ def test_unpack_errors(ctx):
 # ----------------------------------------------------------------------------- FFT
 @pytest.mark.parametrize("k,batch", [(1, 5), (2, 7), (3, 300), (4, 33), (5, 9), (6, 64), (7, 3), (8, 16),
                                      (9, 5), (10, 4), (11, 3), (12, 5), (13, 3), (14, 2), (16, 2), (17, 2),
-                                     (18, 1), (20, 1), (21, 1), (22, 1), (23, 1), (25, 1)])
+                                     (18, 1), (20, 1), (21, 1), (22, 1), (23, 1), (25, 1), (27, 1)])
 @pytest.mark.parametrize("direction", [1, -1])
 def test_fft_c2c_vs_float64(ctx, k, batch, direction):
     rng = np.random.default_rng(k * 31 + batch)
@@ -174,7 +174,7 @@ def test_fft_c2c_matches_oracle_small(ctx, oracle):
         assert rel_l2(d.cpu().numpy(), oracle.fft_c2c(x, direction)) < REL_L2
 
 
-@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 12, 13, 14, 16, 17, 18, 21, 22, 24, 26, 27])
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 12, 13, 14, 16, 17, 18, 21, 22, 24, 26, 27, 28, 29])
 def test_fft_r2c_inplace_vs_float64(ctx, k):
     # input of test-fft_wrappers.cpp:127-131: uniform [-1, 1]
     rng = np.random.default_rng(233 + k)
@@ -731,3 +731,30 @@ def test_stage_stats_report_time_and_algorithmic_bytes(ctx):
         assert b == nbytes and 0 < ms < 50
     with pytest.raises(RuntimeError):
         ctx.stage_stats(5)                       # rfi_s2 was never called
+
+
+@pytest.mark.parametrize("k", [30, 31])
+def test_fft_r2c_tones_land_in_their_bins_at_full_length(ctx, k):
+    """2^30 / 2^31 real points (four-sweep plans 7+7+7+8 and 8+7+7+8 for the packed transform): too long for a host
+    FFT, so pin the OUTPUT ORDER with pure tones: cos(2 pi f t / N) must give N/2 in bin f and nothing elsewhere."""
+    n = 1 << k
+    tones = [(123456789 % (n // 2), 1.0), ((n // 2) - 7, 0.5), (5, 0.25), ((1 << (k - 3)) + 12345, 0.75)]
+    buf = torch.empty(n + 2, dtype=torch.float32, device="cuda")
+    step = 1 << 26
+    for c in range(0, n, step):
+        t = torch.arange(c, c + step, dtype=torch.int64, device="cuda")
+        acc = torch.zeros(step, dtype=torch.float64, device="cuda")
+        for f, a in tones:
+            acc += a * torch.cos((2 * np.pi / n) * ((t * f) % n).double())
+        buf[c:c + step] = acc.float()
+        del t, acc
+    ctx.fft_r2c_inplace(buf, n)
+    torch.cuda.synchronize()
+    X = torch.view_as_complex(buf.view(-1, 2))
+    for f, a in tones:
+        got = complex(X[f].cpu().numpy())
+        assert abs(got.real / (a * n / 2) - 1) < 1e-4 and abs(got.imag) < 1e-4 * a * n / 2, (f, got)
+    mag = X.abs()
+    for f, _ in tones:
+        mag[f] = 0
+    assert float(mag.max()) < 2e-5 * n / 2          # everything else is rounding noise
