@@ -291,11 +291,31 @@ def run_reference(args, w, wname):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """Keep the process's stdout for the ONE JSON line: everything else that writes to fd 1 during the run (NCCL's
+    version banner, library chatter) goes to stderr."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(text: str):
+    out = _RESULT_OUT or sys.stdout
+    out.write(text + "\n")
+    out.flush()
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -575,7 +595,7 @@ def main():
             "stages": stages,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if dist:
         dist.barrier()
         dist.destroy_process_group()
