@@ -324,8 +324,9 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SRTB_BENCH_WORKLOAD", "config2"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-iters", type=int, default=5)
-    ap.add_argument("--contexts", type=int, default=int(os.environ.get("SRTB_BENCH_CONTEXTS", "4")),
-                    help="contexts (CUDA streams) per GPU that blocks alternate over")
+    ap.add_argument("--contexts", type=int, default=int(os.environ.get("SRTB_BENCH_CONTEXTS", "0")),
+                    help="contexts (CUDA streams) per GPU that blocks alternate over (0 = 4, or 2 for blocks "
+                         "of 2^28 samples and more, whose sweeps are pure HBM streams with nothing to overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     wname = args.workload
@@ -349,6 +350,8 @@ def main():
         dist = dist_mod
 
     n = 1 << w["log2n"]
+    if args.contexts <= 0:
+        args.contexts = 4 if w["log2n"] < 28 else 2
     fmt = srtb_b200.FORMAT_BY_NAME[w["fmt"]]
     streams = srtb_b200.FORMAT_STREAMS[fmt]
     block_bytes = n * streams * abs(w["bits"]) // 8

@@ -1,0 +1,133 @@
+// srtb/pipeline/baseband_chain_pipe.hpp — the whole device chain as ONE pipe (the fused
+// composites behind the pipe API). Stands where main.cpp:170-204 chains copy_to_device -> unpack -> fft_1d_r2c ->
+// rfi_mitigation_s1 -> dedisperse -> watfft_1d_c2c -> rfi_mitigation_s2 -> signal_detect_pipe_2: takes the
+// copy_to_device_work a source pipe produced (pinned host block) and returns one write_signal_work per data stream,
+// the same objects signal_detect_pipe_2 hands to write_signal_pipe. Inside it is one
+// srtb_b200_process_block call, i.e. the fused kernels (unpack in the first FFT sweep, R2C split + power sum in
+// the last, s1 + chirp, waterfall FFT + SK + column sums), one H2D and one 1 KiB D2H per stream.
+// Throughput across blocks: start several of these pipes on their own cuda_queue (one CUDA stream + context each)
+// popping from one MPMC work queue — blocks then alternate over contexts and overlap on the GPU.
+#pragma once
+#include <cstdlib>
+#include <cstring>
+#include <optional>
+#include <stop_token>
+#include <string>
+#include <vector>
+
+#include "srtb/config.hpp"
+#include "srtb/cuda_queue.hpp"
+#include "srtb/log.hpp"
+#include "srtb/memory.hpp"
+#include "srtb/pipeline/rfi_mitigation_pipe.hpp"  // srtb::spectrum::eval_rfi_ranges
+#include "srtb/pipeline/unpack_pipe.hpp"          // resolve_format_alias
+#include "srtb/work.hpp"
+
+namespace srtb {
+namespace pipeline {
+
+/** the subset of srtb::config the device path reads, as the C ABI wants it (config.hpp:80-249) */
+struct block_config_holder {
+  srtb_b200_block_config cfg{};
+  std::vector<float> rfi_pairs;
+
+  static int format_of(std::string_view name, int bits) {
+    name = resolve_format_alias(name);
+    if (name == "simple") return SRTB_B200_FORMAT_SIMPLE;
+    if (name == "interleaved_samples_2") return SRTB_B200_FORMAT_INTERLEAVED_2;
+    if (name == "naocpsr_snap1") return bits == -8 ? SRTB_B200_FORMAT_NAOCPSR_SNAP1 : SRTB_B200_FORMAT_INTERLEAVED_2;
+    if (name == "gznupsr_a1") return SRTB_B200_FORMAT_GZNUPSR_A1_2;
+    if (name == "gznupsr_a1_4") return SRTB_B200_FORMAT_GZNUPSR_A1_4;
+    throw std::invalid_argument("[start_unpack_pipe] Unknown format name: " + std::string{name});
+  }
+  static int stream_count(int format) {
+    return format == SRTB_B200_FORMAT_SIMPLE ? 1 : (format == SRTB_B200_FORMAT_GZNUPSR_A1_4 ? 4 : 2);
+  }
+
+  /** re-read srtb::config (the reference's pipes read it on every call) */
+  void refresh() {
+    const auto& c = srtb::config;
+    cfg.baseband_input_count = c.baseband_input_count;
+    cfg.baseband_input_bits = c.baseband_input_bits;
+    cfg.baseband_format = format_of(c.baseband_format_type, c.baseband_input_bits);
+    cfg.window = SRTB_B200_WINDOW_RECTANGLE;  // default_window, fft_window.hpp:83
+    cfg.baseband_reserve_sample = c.baseband_reserve_sample ? 1 : 0;
+    cfg.baseband_freq_low = static_cast<float>(c.baseband_freq_low);
+    cfg.baseband_bandwidth = static_cast<float>(c.baseband_bandwidth);
+    cfg.baseband_sample_rate = static_cast<float>(c.baseband_sample_rate);
+    cfg.dm = static_cast<float>(c.dm);
+    cfg.mitigate_rfi_average_method_threshold = static_cast<float>(c.mitigate_rfi_average_method_threshold);
+    cfg.mitigate_rfi_spectral_kurtosis_threshold = static_cast<float>(c.mitigate_rfi_spectral_kurtosis_threshold);
+    cfg.spectrum_channel_count = c.spectrum_channel_count;
+    cfg.signal_detect_signal_noise_threshold = static_cast<float>(c.signal_detect_signal_noise_threshold);
+    cfg.signal_detect_channel_threshold = static_cast<float>(c.signal_detect_channel_threshold);
+    cfg.signal_detect_max_boxcar_length = c.signal_detect_max_boxcar_length;
+    rfi_pairs.clear();
+    for (const auto& r : srtb::spectrum::eval_rfi_ranges(c.mitigate_rfi_freq_list)) {
+      rfi_pairs.push_back(r.first);
+      rfi_pairs.push_back(r.second);
+    }
+    cfg.rfi_freq_pairs = rfi_pairs.data();
+    cfg.n_rfi_freq_pairs = rfi_pairs.size() / 2;
+  }
+};
+
+class baseband_chain_pipe {
+ protected:
+  srtb::cuda_queue q;
+  block_config_holder holder;
+
+ public:
+  explicit baseband_chain_pipe(srtb::cuda_queue q_, bool keep_every_spectrum_ = false)
+      : q{q_}, keep_every_spectrum{keep_every_spectrum_} {}
+
+  std::optional<std::vector<srtb::work::write_signal_work>> operator()(std::stop_token,
+                                                                       srtb::work::copy_to_device_work in_work) {
+    holder.refresh();
+    const auto& cfg = holder.cfg;
+    const int streams = block_config_holder::stream_count(cfg.baseband_format);
+    const size_t Nc = cfg.baseband_input_count / 2;
+    const size_t C = std::min<size_t>(cfg.spectrum_channel_count, Nc), L = Nc / C;
+    cuda_check(cudaSetDevice(q.device()), "cudaSetDevice");
+    auto h_series = srtb::host_allocator.allocate_shared<srtb::real>((size_t)streams * SRTB_B200_MAX_BOXCARS * L);
+    srtb_b200_detect_result res[4];
+    const int n = srtb_b200_process_block(q.ctx(), &cfg, in_work.baseband_data.baseband_ptr.get(),
+                                          in_work.baseband_data.baseband_input_bytes, res, h_series.get(), 0);
+    q.check(n);
+    std::vector<srtb::work::write_signal_work> out(static_cast<size_t>(n));
+    for (int s = 0; s < n; s++) {
+      auto& w = out[static_cast<size_t>(s)];
+      w.copy_parameter_from(in_work);
+      w.data_stream_id = in_work.data_stream_id * static_cast<uint32_t>(streams) + static_cast<uint32_t>(s);
+      w.count = L;
+      w.batch_size = C;
+      w.zero_count = res[s].zero_count;
+      srtb::real* base = h_series.get() + (size_t)s * SRTB_B200_MAX_BOXCARS * L;
+      for (int b = 0; b < res[s].n_boxcars; b++) {
+        if (res[s].signal_count[b] == 0) continue;
+        srtb::work::time_series_holder h;
+        h.time_series_length = res[s].series_length[b];
+        h.boxcar_length = res[s].boxcar_length[b];
+        h.signal_count = res[s].signal_count[b];
+        h.h_time_series = std::shared_ptr<srtb::real>(h_series, base + (size_t)b * L);
+        w.time_series.push_back(h);
+      }
+      // the dynamic spectrum lives in context scratch and is overwritten by the next block: keep a copy for the
+      // sink when it will be looked at (a candidate, or always if the caller wants every spectrum)
+      if (!w.time_series.empty() || keep_every_spectrum) {
+        auto d_spec = srtb::device_allocator.allocate_shared<srtb::complex<srtb::real>>(C * L);
+        cuda_check(cudaMemcpyAsync(d_spec.get(), srtb_b200_block_spectrum(q.ctx(), s),
+                                   C * L * sizeof(srtb::complex<srtb::real>), cudaMemcpyDeviceToDevice, q.stream()),
+                   "spectrum copy");
+        w.ptr = d_spec;
+      }
+    }
+    q.wait();
+    return std::optional{std::move(out)};
+  }
+
+  bool keep_every_spectrum = false;
+};
+
+}  // namespace pipeline
+}  // namespace srtb

@@ -4,18 +4,21 @@
 //                  -> rfi_mitigation_s2 -> signal_detect_pipe_2 -> (sink: prints one JSON line per work)
 // Input: a raw baseband file (--input) cut into blocks of baseband_input_count samples per stream.
 // Used by tests/test_gpu_pipeline.py, which compares the printed results with the CPU oracle.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "srtb/config.hpp"
 #include "srtb/cuda_queue.hpp"
 #include "srtb/memory.hpp"
+#include "srtb/pipeline/baseband_chain_pipe.hpp"
 #include "srtb/pipeline/copy_to_device_pipe.hpp"
 #include "srtb/pipeline/dedisperse_pipe.hpp"
 #include "srtb/pipeline/fft_pipe.hpp"
@@ -59,7 +62,11 @@ struct sink_out_functor {
                       std::ios::binary);
       f.write(host.data(), (std::streamsize)host.size());
     }
-    std::cout << line << std::endl;
+    {
+      static std::mutex print_mutex;  // several fused chain pipes may drain into this sink at once
+      std::lock_guard<std::mutex> lock(print_mutex);
+      std::cout << line << std::endl;
+    }
     (*done)++;
   }
 };
@@ -128,9 +135,21 @@ int main(int argc, char** argv) {
   if (write_candidates) sink.writer = std::make_shared<write_signal_pipe>(q);
 
   std::vector<std::jthread> threads;
+  const int fused = std::atoi(arg(argc, argv, "--fused", "0"));
+  if (fused > 0) {
+    // the whole device chain as one pipe (fused kernels), `fused` of them on their own queue each, all fed from
+    // the same MPMC queue: blocks alternate over the contexts and overlap on the GPU
+    for (int i = 0; i < fused; i++) {
+      srtb::cuda_queue qi = (i == 0) ? q : srtb::cuda_queue{q.device()};
+      threads.push_back(start_pipe<baseband_chain_pipe>(queue_in_functor{copy_q}, multiple_works_out_functor{sink}, qi,
+                                                        !dump.empty()));
+    }
+  } else {
   threads.push_back(start_pipe<copy_to_device_pipe>(queue_in_functor{copy_q}, queue_out_functor{unpack_q}, q));
   threads.push_back(start_unpack_pipe(cfg.baseband_format_type, queue_in_functor{unpack_q}, queue_out_functor{r2c_q}, q));
-  if (!composite) {
+  }
+  if (fused > 0) {
+  } else if (!composite) {
     threads.push_back(start_pipe<fft_1d_r2c_pipe>(queue_in_functor{r2c_q}, queue_out_functor{s1_q}, q));
     threads.push_back(start_pipe<rfi_mitigation_s1_pipe>(queue_in_functor{s1_q}, queue_out_functor{dd_q}, q));
     threads.push_back(start_pipe<dedisperse_pipe>(queue_in_functor{dd_q}, queue_out_functor{wat_q}, q));
@@ -147,6 +166,7 @@ int main(int argc, char** argv) {
   }
 
   int blocks = 0;
+  const auto t_start = std::chrono::steady_clock::now();
   auto feed = [&](auto& source, bool renumber) {
     while (auto w = source(std::stop_token{}, srtb::work::dummy_work{})) {
       if (renumber) w->udp_packet_counter = (uint64_t)blocks;  // deterministic file names / JSON keys for the test
@@ -181,7 +201,13 @@ int main(int argc, char** argv) {
     read_file_pipe reader;
     feed(reader, true);
   }
-  while (done->load() < blocks * (int)streams) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+  while (done->load() < blocks * (int)streams) std::this_thread::sleep_for(std::chrono::microseconds(200));
+  {
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    std::fprintf(stderr, "[pipeline_main] %d block(s) x %zu stream(s) of 2^%d samples in %.3f s = %.2f Gsamples/s (host wall clock, file read included)\n",
+                 blocks, streams, std::atoi(arg(argc, argv, "--log2n", "20")), dt,
+                 (double)blocks * (double)streams * (double)cfg.baseband_input_count / dt / 1e9);
+  }
   for (auto& t : threads) t.request_stop();
   threads.clear();
   srtb::device_allocator.deallocate_all_free_ptrs();

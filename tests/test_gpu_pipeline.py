@@ -118,6 +118,37 @@ def test_pipeline_udp_shaped_with_packet_loss(tmp_path, oracle):
         _check_work(w, prefix, holed.reshape(-1), oracle, n, C_, dm)
 
 
+@pytest.mark.parametrize("fused", [1, 3])
+def test_pipeline_fused_chain_pipe(tmp_path, oracle, fused):
+    """the device chain as ONE pipe (baseband_chain_pipe = srtb_b200_process_block behind the pipe
+    API), one or three of them on their own queues fed from one MPMC queue. Same checks as the per-stage pipeline."""
+    _build()
+    logn, C_, dm = 18, 64, 0.0
+    n = 1 << logn
+    blocks = [_block(n, s) for s in (31, 32, 33, 34, 35)]
+    works, prefix = _run(tmp_path, "simple", np.concatenate(blocks), logn, C_, dm, 0, extra=("--fused", str(fused)))
+    assert sorted(w["block"] for w in works) == list(range(5))
+    detected = 0
+    for w in works:
+        assert w["stream"] == 0
+        detected += _check_work(w, prefix, blocks[w["block"]], oracle, n, C_, dm)
+    assert detected > 0
+
+
+def test_pipeline_fused_chain_pipe_dual_pol(tmp_path, oracle):
+    _build()
+    logn, C_, dm = 16, 16, 0.0
+    n = 1 << logn
+    a, b = _block(n, 41), _block(n, 42)
+    raw = np.empty(2 * n, np.int8)
+    raw.reshape(-1, 4)[:, 0:2] = a.reshape(-1, 2)
+    raw.reshape(-1, 4)[:, 2:4] = b.reshape(-1, 2)
+    works, prefix = _run(tmp_path, "naocpsr_snap1", raw, logn, C_, dm, 0, extra=("--fused", "1"))
+    assert sorted((w["block"], w["stream"]) for w in works) == [(0, 0), (0, 1)]
+    for w in works:
+        _check_work(w, prefix, (a, b)[w["stream"]], oracle, n, C_, dm)
+
+
 def test_pipeline_dual_pol_fanout(tmp_path, oracle):
     """naocpsr_snap1: one unpack work fans out into two fft works with data_stream_id 2*id + s
     (unpack_pipe.hpp:249-258)"""
