@@ -166,7 +166,7 @@ int main(int argc, char** argv) {
   }
 
   int blocks = 0;
-  const auto t_start = std::chrono::steady_clock::now();
+  auto t_start = std::chrono::steady_clock::now();
   auto feed = [&](auto& source, bool renumber) {
     while (auto w = source(std::stop_token{}, srtb::work::dummy_work{})) {
       if (renumber) w->udp_packet_counter = (uint64_t)blocks;  // deterministic file names / JSON keys for the test
@@ -196,6 +196,21 @@ int main(int argc, char** argv) {
     };
     if (streams == 2) run(io::backend_registry::naocpsr_snap1{});
     else run(io::backend_registry::fastmb_roach2{});
+  } else if (std::atoi(arg(argc, argv, "--preload", "0")) != 0) {
+    // device-path throughput without host file I/O in the timed region: read every block into pinned memory
+    // first, then replay the same works --repeat times (each replay is still H2D + the whole chain + D2H)
+    read_file_pipe reader;
+    std::vector<srtb::work::copy_to_device_work> preloaded;
+    while (auto w = reader(std::stop_token{}, srtb::work::dummy_work{})) preloaded.push_back(*w);
+    const int repeat = std::atoi(arg(argc, argv, "--repeat", "1"));
+    t_start = std::chrono::steady_clock::now();
+    for (int r = 0; r < repeat; r++)
+      for (auto w : preloaded) {
+        w.udp_packet_counter = (uint64_t)blocks;
+        while (copy_q->read_available() >= 8) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        copy_q->push(w);
+        blocks++;
+      }
   } else {
     // source: read_file_pipe (pinned host block, zero padded tail, overlap-save rewind by nsamps_reserved)
     read_file_pipe reader;
