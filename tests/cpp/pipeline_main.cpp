@@ -219,7 +219,7 @@ int main(int argc, char** argv) {
   while (done->load() < blocks * (int)streams) std::this_thread::sleep_for(std::chrono::microseconds(200));
   {
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-    std::fprintf(stderr, "[pipeline_main] %d block(s) x %zu stream(s) of 2^%d samples in %.3f s = %.2f Gsamples/s (host wall clock, file read included)\n",
+    std::fprintf(stderr, "[pipeline_main] %d block(s) x %zu stream(s) of 2^%d samples in %.3f s = %.2f Gsamples/s (host wall clock: source + H2D + chain + D2H)\n",
                  blocks, streams, std::atoi(arg(argc, argv, "--log2n", "20")), dt,
                  (double)blocks * (double)streams * (double)cfg.baseband_input_count / dt / 1e9);
   }
