@@ -663,6 +663,28 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value,
 }
 
 
+// K12 chirp factor (S/coherent_dedispersion.hpp:133-150 phase_factor_v3): f = f_min + df*i in fp64,
+// k = (D*1e6*dm)/f * ((f-f_c)/f_c)^2, factor = exp(-2 pi i frac(k)); used by dedisperse_kernel and by the
+// waterfall kernel that fuses s1 + chirp into its load (CHIRP = true below).
+__device__ __forceinline__ float2 chirp_factor(double f_min, double df, double inv_fc, double f_c,
+                                               double ddm, unsigned i) {
+  // 1/f by __drcp_rn (correctly rounded) and (f - f_c) * (1/f_c): each differs from the reference's
+  // true divisions by <= 1 ulp of fp64, i.e. <= |k| * 2.2e-16 cycles of phase
+  const double f = fma(df, (double)i, f_min);
+  const double q = (f - f_c) * inv_fc;
+  const double k = (ddm * __drcp_rn(f)) * (q * q);
+  const float frac = (float)(k - trunc(k));
+  float s, c;
+  sincospif(-2.0f * frac, &s, &c);
+  return make_float2(c, s);
+}
+
+struct row_chirp_params {
+  double f_min, df, inv_fc, f_c, ddm;
+  const float* mean;      // mean |X|^2 of the block (s1 statistic), finalised by the preceding kernel
+  float threshold, coef;  // s1: zap above threshold * mean, scale the rest by coef
+};
+
 // ---------------------------------------------------------------------------------
 // Row pass with sixteen points per thread (radix-16 stages: L = 4096 as 16^3, 2048 as 16*16*8,
 // 1024 as 16*16*4, 256 as 16*16): three stages and five CTA barriers per 4096-point row instead of
@@ -735,10 +757,10 @@ __device__ __forceinline__ void stage_compute16_row(float2 (&v)[16], int u, cons
   }
 }
 
-template <int LOGL, int T, bool FWD, bool SK = false>
+template <int LOGL, int T, bool FWD, bool SK = false, bool CHIRP = false>
 __global__ void __launch_bounds__(((1 << LOGL) / 16) * T, 3)
     fft_row16_tma_kernel(const float2* __restrict__ in, float2* __restrict__ out, size_t nrows,
-                         const float2* __restrict__ tw, row_sk_params skp) {
+                         const float2* __restrict__ tw, row_sk_params skp, row_chirp_params cp) {
   using SC = sched16<LOGL>;
   constexpr int L = 1 << LOGL, U = L / 16, S = SC::S, BUF = row16_smem<LOGL, T>::BUF;
   static_assert(S == 2 || S == 3, "64 <= L <= 4096");
@@ -792,6 +814,19 @@ __global__ void __launch_bounds__(((1 << LOGL) / 16) * T, 3)
     int oidx[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) v[e] = valid ? sm[u + e * U] : make_float2(0.f, 0.f);
+    if constexpr (CHIRP) {
+      // rfi_mitigation_s1 (zap + normalise, rfi_mitigation_pipe.hpp:66-79) and the dedispersion chirp
+      // (coherent_dedispersion.hpp:223-237) applied to the spectrum on its way into the waterfall FFT
+      const float limit = cp.threshold * __ldg(cp.mean);
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        float2 a = v[e];
+        if (a.x * a.x + a.y * a.y > limit) a = make_float2(0.f, 0.f);
+        else a = make_float2(a.x * cp.coef, a.y * cp.coef);
+        const float2 w = chirp_factor(cp.f_min, cp.df, cp.inv_fc, cp.f_c, cp.ddm, (unsigned)((row << LOGL) + u + e * U));
+        v[e] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+      }
+    }
     stage_compute16_row<LOGL, SC::logr(0), 0, FWD>(v, u, ctw, oidx);
     __syncthreads();  // every linear read done before the swizzled layout overwrites the buffer
 #pragma unroll

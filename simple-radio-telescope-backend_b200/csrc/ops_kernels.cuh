@@ -540,18 +540,7 @@ __global__ void __launch_bounds__(256) rfi_zero_ranges_kernel(float2* __restrict
 // f = f_min + df*i in fp64 (f32 inputs promoted), k = (D*1e6*dm)/f * ((f-f_c)/f_c)^2,
 // phi = -2 pi frac(k); the sincos is taken as sincospi(-2 frac) in fp32.
 // ------------------------------------------------------------------------------
-__device__ __forceinline__ float2 chirp_factor(double f_min, double df, double inv_fc, double f_c,
-                                               double ddm, unsigned i) {
-  // 1/f by __drcp_rn (correctly rounded) and (f - f_c) * (1/f_c): each differs from the reference's
-  // true divisions by <= 1 ulp of fp64, i.e. <= |k| * 2.2e-16 cycles of phase
-  const double f = fma(df, (double)i, f_min);
-  const double q = (f - f_c) * inv_fc;
-  const double k = (ddm * __drcp_rn(f)) * (q * q);
-  const float frac = (float)(k - trunc(k));
-  float s, c;
-  sincospif(-2.0f * frac, &s, &c);
-  return make_float2(c, s);
-}
+// chirp_factor() lives in fft_engine.cuh (shared with the fused waterfall kernel)
 
 // S1 = true fuses K10 (zap + normalise, rfi_mitigation_pipe.hpp:66-79) in front of the chirp: used by
 // srtb_b200_process_block, where the s1 and dedisperse pipes run back to back on one stream.

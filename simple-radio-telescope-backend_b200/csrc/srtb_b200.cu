@@ -438,7 +438,7 @@ static int launch_row(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t 
       if (int rc = persistent_grid(ctx, kern, threads, smem, smem, ntiles, &grid)) return rc;
       const float2* tw = nullptr;
       if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
-      kern<<<grid, threads, smem, ctx->stream>>>(in, out, nrows, tw, row_sk_params{});
+      kern<<<grid, threads, smem, ctx->stream>>>(in, out, nrows, tw, row_sk_params{}, row_chirp_params{});
       ctx->launches++;
       CK(cudaGetLastError());
       return 0;
@@ -1161,6 +1161,25 @@ extern "C" int srtb_b200_dedisperse(srtb_b200_ctx* ctx, void* d_x, size_t count,
 
 // s1 (mean -> zap/normalise) and the chirp in two kernels instead of three: power sum, then one
 // fused apply + chirp sweep, then the manual zap (zero * chirp = zero, so the order is equivalent)
+// mitigate_rfi_manual (rfi_mitigation.hpp:97-158): zero the listed bin ranges, 16 ranges per launch
+static int zero_bin_ranges(srtb_b200_ctx* ctx, float2* x, const std::vector<size_t>& bins) {
+  for (size_t r0 = 0; r0 < bins.size() / 2; r0 += 16) {
+    bin_ranges br;
+    const size_t nr = std::min<size_t>(16, bins.size() / 2 - r0);
+    size_t longest = 1;
+    for (size_t r = 0; r < nr; r++) {
+      br.lo[r] = bins[2 * (r0 + r)];
+      br.hi[r] = bins[2 * (r0 + r) + 1];
+      longest = std::max<size_t>(longest, br.hi[r] - br.lo[r] + 1);
+    }
+    dim3 g(grid_for(ctx, longest, 256), (unsigned)nr);
+    rfi_zero_ranges_kernel<<<g, 256, 0, ctx->stream>>>(x, br);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
 static int rfi_s1_dedisperse_fused(srtb_b200_ctx* ctx, float2* x, size_t count, float avg_threshold, float coef,
                                    const std::vector<size_t>& bins, float f_min, float f_c, float df, float dm,
                                    bool mean_ready, const float2* src = nullptr) {
@@ -1177,21 +1196,7 @@ static int rfi_s1_dedisperse_fused(srtb_b200_ctx* ctx, float2* x, size_t count, 
       src, x, count, (double)f_min, (double)df, (double)f_c, ddm, ctx->mean, avg_threshold, coef);
   ctx->launches++;
   CK(cudaGetLastError());
-  for (size_t r0 = 0; r0 < bins.size() / 2; r0 += 16) {
-    bin_ranges br;
-    const size_t nr = std::min<size_t>(16, bins.size() / 2 - r0);
-    size_t longest = 1;
-    for (size_t r = 0; r < nr; r++) {
-      br.lo[r] = bins[2 * (r0 + r)];
-      br.hi[r] = bins[2 * (r0 + r) + 1];
-      longest = std::max<size_t>(longest, br.hi[r] - br.lo[r] + 1);
-    }
-    dim3 g(grid_for(ctx, longest, 256), (unsigned)nr);
-    rfi_zero_ranges_kernel<<<g, 256, 0, ctx->stream>>>(x, br);
-    ctx->launches++;
-    CK(cudaGetLastError());
-  }
-  return 0;
+  return zero_bin_ranges(ctx, x, bins);
 }
 
 extern "C" size_t srtb_b200_nsamps_reserved(size_t baseband_input_count, size_t spectrum_channel_count,
@@ -1303,13 +1308,26 @@ static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t 
 // watfft (backward C2C of every channel row) with spectral kurtosis + the detector's partial column
 // sums fused into its epilogue: the dynamic spectrum is written once and not read again until the
 // candidate sink. Used by process_block when one CTA holds a whole row (L = 512 .. 4096).
+// s1 + chirp folded into the waterfall kernel's load (process_block, L = 1024..4096): SRTB_B200_FUSE_CHIRP=0 keeps
+// the separate dedisperse kernel
+static bool use_fused_chirp() {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_FUSE_CHIRP");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+static bool chirp_fusable(size_t time_count) {
+  return use_fused_chirp() && use_row16() && (time_count == 1024 || time_count == 2048 || time_count == 4096);
+}
+
 template <int LOGL>
 static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, float lo_, float hi_, size_t ts_count,
-                            size_t* chunks_out) {
+                            size_t* chunks_out, const row_chirp_params* chirp = nullptr) {
   if constexpr (has_row16<LOGL>::value && LOGL >= 10) {
     if (use_row16()) {
       constexpr int T16 = row16_t<LOGL>::value, threads = ((1 << LOGL) / 16) * T16;
-      auto kern = fft_row16_tma_kernel<LOGL, T16, false, true>;
+      auto kern = chirp ? fft_row16_tma_kernel<LOGL, T16, false, true, true> : fft_row16_tma_kernel<LOGL, T16, false, true, false>;
       constexpr size_t smem = row16_smem<LOGL, T16>::bytes;
       const size_t ntiles = (chan_count + T16 - 1) / T16;
       unsigned grid = 1;
@@ -1321,13 +1339,14 @@ static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, fl
       const float2* tw = nullptr;
       if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
       row_sk_params p{lo_, hi_, ctx->colsum_partial, (unsigned)ts_count};
-      kern<<<grid, threads, smem, ctx->stream>>>(x, x, chan_count, tw, p);
+      kern<<<grid, threads, smem, ctx->stream>>>(x, x, chan_count, tw, p, chirp ? *chirp : row_chirp_params{});
       ctx->launches++;
       CK(cudaGetLastError());
       *chunks_out = grid;
       return 0;
     }
   }
+  if (chirp) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "watfft: fused chirp needs the sixteen-point row kernel");
   constexpr int T = row_t<LOGL>::value;
   auto kern = fft_row_tma_kernel<LOGL, T, false, true>;
   constexpr size_t smem = row_tma_smem<LOGL, T>::bytes;
@@ -1352,7 +1371,7 @@ static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, fl
 
 static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_t time_count, size_t chan_count,
                                   size_t time_reserved_count, float sk_threshold, float snr, float chan_thr,
-                                  size_t max_boxcar) {
+                                  size_t max_boxcar, const row_chirp_params* chirp = nullptr) {
   const size_t ts_count = (time_count <= time_reserved_count) ? time_count : time_count - time_reserved_count;
   if (int rc = detect_prepare(ctx, slot, time_count, 1)) return rc;
   CK(cudaMemsetAsync(ctx->d_res + slot, 0, sizeof(detect_dev_result), ctx->stream));
@@ -1363,10 +1382,10 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
   size_t chunks = 0;
   int rc = 0;
   switch (ilog2(time_count)) {
-    case 9: rc = watfft_sk_launch<9>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks); break;
-    case 10: rc = watfft_sk_launch<10>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks); break;
-    case 11: rc = watfft_sk_launch<11>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks); break;
-    default: rc = watfft_sk_launch<12>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks); break;
+    case 9: rc = watfft_sk_launch<9>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp); break;
+    case 10: rc = watfft_sk_launch<10>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp); break;
+    case 11: rc = watfft_sk_launch<11>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp); break;
+    default: rc = watfft_sk_launch<12>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp); break;
   }
   if (rc) return rc;
   return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
@@ -1540,11 +1559,27 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
       }
       if (rc) return rc;
     }
+    const bool aligned = (reinterpret_cast<uintptr_t>(buf) & 15u) == 0;
+    if (chirp_fusable(L) && aligned) {
+      // manual zap on the raw spectrum (0 stays 0 through s1 and the chirp), then ONE kernel: s1 + chirp on load,
+      // waterfall FFT, SK, partial column sums
+      if (int rc = zero_bin_ranges(ctx, reinterpret_cast<float2*>(buf), bins)) return rc;
+      constexpr double D = 4.148808e3;  // coherent_dedispersion.hpp:67
+      row_chirp_params cp{(double)f_min, (double)df, 1.0 / (double)f_c, (double)f_c, (D * 1e6) * (double)cfg->dm,
+                          ctx->mean, cfg->mitigate_rfi_average_method_threshold, coef};
+      if (int rc = watfft_sk_detect_fused(ctx, s, reinterpret_cast<float2*>(buf), L, batch, reserved,
+                                          cfg->mitigate_rfi_spectral_kurtosis_threshold,
+                                          cfg->signal_detect_signal_noise_threshold,
+                                          cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length,
+                                          &cp))
+        return rc;
+      continue;
+    }
     if (int rc = rfi_s1_dedisperse_fused(ctx, reinterpret_cast<float2*>(buf), Nc,
                                          cfg->mitigate_rfi_average_method_threshold, coef, bins, f_min, f_c, df, cfg->dm,
                                          /*mean_ready=*/true))
       return rc;
-    if (sk_detect_fusable(L) && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0) {
+    if (sk_detect_fusable(L) && aligned) {
       // waterfall FFT + SK + partial column sums in one kernel, then the small detector tail
       if (int rc = watfft_sk_detect_fused(ctx, s, reinterpret_cast<float2*>(buf), L, batch, reserved,
                                           cfg->mitigate_rfi_spectral_kurtosis_threshold,
