@@ -59,9 +59,11 @@ struct srtb_b200_ctx {
   size_t slot_L[SRTB_B200_RING_SLOTS] = {0};
   bool slot_busy[SRTB_B200_RING_SLOTS] = {false};
   uint64_t submit_count = 0;
-  // DM sweep working copy of the spectrum
+  // DM sweep working copy of the spectrum, per-trial result headers
   void* sweep_buf = nullptr;
   size_t sweep_buf_bytes = 0;
+  void* sweep_res = nullptr;
+  size_t sweep_res_bytes = 0;
   // optional per-stage timing (srtb_b200_stage_stats)
   bool stats_on = false;
   cudaEvent_t stat_ev[SRTB_B200_STAGE_COUNT][2] = {};
@@ -192,6 +194,7 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   cudaFreeHost(ctx->h_res);
   cudaFree(ctx->d_baseband);
   cudaFree(ctx->sweep_buf);
+  cudaFree(ctx->sweep_res);
   for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) {
     cudaFree(ctx->slot_baseband[i]);
     if (ctx->slot_h2d[i]) cudaEventDestroy(ctx->slot_h2d[i]);
@@ -1323,7 +1326,8 @@ static bool chirp_fusable(size_t time_count) {
 
 template <int LOGL>
 static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, float lo_, float hi_, size_t ts_count,
-                            size_t* chunks_out, const row_chirp_params* chirp = nullptr) {
+                            size_t* chunks_out, const row_chirp_params* chirp = nullptr, const float2* src = nullptr) {
+  if (!src) src = x;  // in place unless the input spectrum is kept (DM sweep)
   if constexpr (has_row16<LOGL>::value && LOGL >= 10) {
     if (use_row16()) {
       constexpr int T16 = row16_t<LOGL>::value, threads = ((1 << LOGL) / 16) * T16;
@@ -1339,14 +1343,14 @@ static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, fl
       const float2* tw = nullptr;
       if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
       row_sk_params p{lo_, hi_, ctx->colsum_partial, (unsigned)ts_count};
-      kern<<<grid, threads, smem, ctx->stream>>>(x, x, chan_count, tw, p, chirp ? *chirp : row_chirp_params{});
+      kern<<<grid, threads, smem, ctx->stream>>>(src, x, chan_count, tw, p, chirp ? *chirp : row_chirp_params{});
       ctx->launches++;
       CK(cudaGetLastError());
       *chunks_out = grid;
       return 0;
     }
   }
-  if (chirp) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "watfft: fused chirp needs the sixteen-point row kernel");
+  if (chirp || src != x) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "watfft: fused chirp needs the sixteen-point row kernel");
   constexpr int T = row_t<LOGL>::value;
   auto kern = fft_row_tma_kernel<LOGL, T, false, true>;
   constexpr size_t smem = row_tma_smem<LOGL, T>::bytes;
@@ -1371,7 +1375,8 @@ static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, fl
 
 static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_t time_count, size_t chan_count,
                                   size_t time_reserved_count, float sk_threshold, float snr, float chan_thr,
-                                  size_t max_boxcar, const row_chirp_params* chirp = nullptr) {
+                                  size_t max_boxcar, const row_chirp_params* chirp = nullptr,
+                                  const float2* src = nullptr) {
   const size_t ts_count = (time_count <= time_reserved_count) ? time_count : time_count - time_reserved_count;
   if (int rc = detect_prepare(ctx, slot, time_count, 1)) return rc;
   CK(cudaMemsetAsync(ctx->d_res + slot, 0, sizeof(detect_dev_result), ctx->stream));
@@ -1382,10 +1387,10 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
   size_t chunks = 0;
   int rc = 0;
   switch (ilog2(time_count)) {
-    case 9: rc = watfft_sk_launch<9>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp); break;
-    case 10: rc = watfft_sk_launch<10>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp); break;
-    case 11: rc = watfft_sk_launch<11>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp); break;
-    default: rc = watfft_sk_launch<12>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp); break;
+    case 9: rc = watfft_sk_launch<9>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp, src); break;
+    case 10: rc = watfft_sk_launch<10>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp, src); break;
+    case 11: rc = watfft_sk_launch<11>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp, src); break;
+    default: rc = watfft_sk_launch<12>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp, src); break;
   }
   if (rc) return rc;
   return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
@@ -1691,33 +1696,53 @@ extern "C" int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b
   const float coef = srtb_b200_norm_coefficient(Nc, cfg->spectrum_channel_count);
   const float df = cfg->baseband_bandwidth / static_cast<float>(Nc);
   const float f_min = cfg->baseband_freq_low, f_c = f_min + cfg->baseband_bandwidth;
+  // every trial's result header is parked on the device and fetched once at the end: no host sync per trial
+  if (int rc = ensure(ctx, &ctx->sweep_res, &ctx->sweep_res_bytes, n_dm * streams * sizeof(detect_dev_result))) return rc;
+  detect_dev_result* d_sweep = static_cast<detect_dev_result*>(ctx->sweep_res);
+  const bool fuse_chirp = chirp_fusable(L);
   for (int s = 0; s < streams; s++) {
     float* buf = ctx->stream_buf[s];
     if (int rc = fft_r2c_with_power_mean(ctx, buf, N)) return rc;  // leaves mean(|X|^2) in ctx->mean
+    const bool fused = fuse_chirp && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0;
+    if (fused)  // the manual zap does not depend on the DM: once, on the kept spectrum
+      if (int rc = zero_bin_ranges(ctx, reinterpret_cast<float2*>(buf), bins)) return rc;
     for (size_t j = 0; j < n_dm; j++) {
       const size_t reserved = srtb_b200_nsamps_reserved(N, cfg->spectrum_channel_count, cfg->baseband_freq_low,
                                                         cfg->baseband_bandwidth, cfg->baseband_sample_rate, h_dms[j],
                                                         cfg->baseband_reserve_sample) / batch;
-      if (int rc = rfi_s1_dedisperse_fused(ctx, W, Nc, cfg->mitigate_rfi_average_method_threshold, coef, bins, f_min,
-                                           f_c, df, h_dms[j], /*mean_ready=*/true, reinterpret_cast<const float2*>(buf)))
-        return rc;
-      if (sk_detect_fusable(L)) {
+      if (fused) {
+        constexpr double D = 4.148808e3;
+        row_chirp_params cp{(double)f_min, (double)df, 1.0 / (double)f_c, (double)f_c, (D * 1e6) * (double)h_dms[j],
+                            ctx->mean, cfg->mitigate_rfi_average_method_threshold, coef};
         if (int rc = watfft_sk_detect_fused(ctx, 0, W, L, batch, reserved, cfg->mitigate_rfi_spectral_kurtosis_threshold,
                                             cfg->signal_detect_signal_noise_threshold,
-                                            cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length))
+                                            cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length,
+                                            &cp, reinterpret_cast<const float2*>(buf)))
           return rc;
       } else {
-        if (int rc = srtb_b200_watfft_c2c_backward(ctx, W, L, batch)) return rc;
-        if (int rc = srtb_b200_rfi_s2_sk(ctx, W, L, batch, cfg->mitigate_rfi_spectral_kurtosis_threshold, nullptr)) return rc;
-        if (int rc = detect_enqueue(ctx, 0, W, L, batch, reserved, cfg->signal_detect_signal_noise_threshold,
-                                    cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length))
+        if (int rc = rfi_s1_dedisperse_fused(ctx, W, Nc, cfg->mitigate_rfi_average_method_threshold, coef, bins, f_min,
+                                             f_c, df, h_dms[j], /*mean_ready=*/true, reinterpret_cast<const float2*>(buf)))
           return rc;
+        if (sk_detect_fusable(L)) {
+          if (int rc = watfft_sk_detect_fused(ctx, 0, W, L, batch, reserved, cfg->mitigate_rfi_spectral_kurtosis_threshold,
+                                              cfg->signal_detect_signal_noise_threshold,
+                                              cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length))
+            return rc;
+        } else {
+          if (int rc = srtb_b200_watfft_c2c_backward(ctx, W, L, batch)) return rc;
+          if (int rc = srtb_b200_rfi_s2_sk(ctx, W, L, batch, cfg->mitigate_rfi_spectral_kurtosis_threshold, nullptr)) return rc;
+          if (int rc = detect_enqueue(ctx, 0, W, L, batch, reserved, cfg->signal_detect_signal_noise_threshold,
+                                      cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length))
+            return rc;
+        }
       }
-      CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(detect_dev_result), cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
-      std::memcpy(h_results + j * streams + s, ctx->h_res, sizeof(srtb_b200_detect_result));
+      CK(cudaMemcpyAsync(d_sweep + j * streams + s, ctx->d_res, sizeof(detect_dev_result), cudaMemcpyDeviceToDevice,
+                         ctx->stream));
     }
   }
+  static_assert(sizeof(detect_dev_result) == sizeof(srtb_b200_detect_result), "result layout");
+  CK(cudaMemcpyAsync(h_results, d_sweep, n_dm * streams * sizeof(detect_dev_result), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
   return streams;
 }
 
