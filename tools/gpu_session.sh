@@ -13,7 +13,7 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_${T
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --stage-iters 1 > gpurun_out/ncu_bench_${TAG}.log 2>&1
 # full capture of the FFT pass kernels + the heaviest elementwise kernels of one step
-ncu --set full --clock-control none --import-source on -k regex:'fft_.*kernel|dedisperse_kernel|r2c_post_kernel|sk_colsum_kernel' \
+ncu --set full --clock-control none --import-source on -k regex:"fft_.*kernel|dedisperse_kernel" \
     -s 36 -c 10 -o gpurun_out/prof_${TAG} -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline --stage-iters 1 > gpurun_out/ncu_full_${TAG}.log 2>&1
 # per-stage capture: every per-pipe kernel once + one fused block (feeds profiles/traffic.json)
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off -o gpurun_out/prof_stages_${TAG} -f python tools/stage_once.py > gpurun_out/ncu_stages_${TAG}.log 2>&1
