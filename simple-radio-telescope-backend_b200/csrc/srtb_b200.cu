@@ -578,9 +578,22 @@ static bool use_col16() {
   return on;
 }
 
-template <int LOGL, bool FWD>
+// wide tiles (32 neighbouring columns = 256-byte segments) for the 128-point column sweep of very long transforms,
+// whose row stride is megabytes: fewer DRAM page openings / TLB entries per byte. SRTB_B200_WIDE_COL=0 disables.
+static bool wide_col(size_t A, size_t L, size_t B) {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_WIDE_COL");
+    return !(e && e[0] == '0');
+  }();
+  return on && B >= ((size_t)1 << 14) && A * L * B >= ((size_t)1 << 26);
+}
+
+template <int LOGL, bool FWD, int TT = col_t<LOGL>::value>
 static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t B, bool* done) {
-  constexpr int T = col_t<LOGL>::value, L = 1 << LOGL;
+  constexpr int T = TT, L = 1 << LOGL;
+  if constexpr (LOGL == 7 && TT == col_t<LOGL>::value) {
+    if (use_col16() && wide_col(A, L, B)) return launch_col_tma<LOGL, FWD, 32>(ctx, in, out, A, B, done);
+  }
   *done = false;
   if ((reinterpret_cast<uintptr_t>(in) & 15u) || A * L >= ((size_t)1 << 31) || B >= ((size_t)1 << 31)) return 0;
   tensor_map_blob tm;
@@ -623,9 +636,12 @@ struct raw_source {
   bool is_signed = true;
 };
 
-template <int LOGL, int RAW>
+template <int LOGL, int RAW, int TT = col_t<LOGL>::value>
 static int launch_col_tma_raw(srtb_b200_ctx* ctx, const raw_source& src, float2* out, size_t B, bool* done) {
-  constexpr int T = col_t<LOGL>::value, L = 1 << LOGL;
+  constexpr int T = TT, L = 1 << LOGL;
+  if constexpr (LOGL == 7 && TT == col_t<LOGL>::value) {
+    if (use_col16() && wide_col(1, L, B)) return launch_col_tma_raw<LOGL, RAW, 32>(ctx, src, out, B, done);
+  }
   *done = false;
   if ((reinterpret_cast<uintptr_t>(src.base) & 15u) || B >= ((size_t)1 << 29)) return 0;
   tensor_map_blob tm;
