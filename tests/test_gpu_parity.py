@@ -473,7 +473,8 @@ def synth_baseband(n, seed, tone=True, pulse=True):
     return np.clip(np.round(v), -127, 127).astype(np.int8)
 
 
-@pytest.mark.parametrize("logn,C_,dm", [(16, 16, 0.0), (20, 256, 10.0), (18, 128, 0.5), (17, 128, 0.0)])
+@pytest.mark.parametrize("logn,C_,dm", [(16, 16, 0.0), (20, 256, 10.0), (18, 128, 0.5), (17, 128, 0.0),
+                                        (24, 2048, 56.778)])     # the last one: BASELINE config #2 at full size
 def test_chain_vs_oracle(ctx, oracle, logn, C_, dm):
     n = 1 << logn
     bb = synth_baseband(n, seed=logn)
