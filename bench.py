@@ -89,6 +89,9 @@ STAGE_KERNELS = {
 }
 
 
+_NCU_US = {}   # per-stage sum of kernel durations in the same committed capture (no launch / event overhead)
+
+
 def stage_traffic():
     """per-stage DRAM bytes (read + write) per launch from the committed ncu capture, or {}"""
     import re
@@ -108,6 +111,7 @@ def stage_traffic():
             for stage, pat in STAGE_KERNELS.items():
                 if re.search(pat, k["kernel"]):
                     out[stage] = out.get(stage, 0.0) + k["dram_read"] + k["dram_write"]
+                    _NCU_US[stage] = _NCU_US.get(stage, 0.0) + k.get("time_us", 0.0)
         return out, d.get("tag")
     except Exception:
         return {}, None
@@ -533,6 +537,9 @@ def main():
         for k_, v_ in traffic.items():
             if k_ in stages:
                 stages[k_]["dram_traffic"] = v_
+                if _NCU_US.get(k_):   # offline: kernel time under ncu (cold cache), for comparison with the live `ms`
+                    stages[k_]["ncu_kernel_us"] = _NCU_US[k_]
+                    stages[k_]["ncu_frac"] = stages[k_]["bytes"] / (_NCU_US[k_] * 1e-6) / 1e9 / peak
         roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak,
                     "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic.get(dom),
                     "traffic_source": (f"ncu --set full capture profiles/{traffic_tag}_summary.md (dram read+write of the "

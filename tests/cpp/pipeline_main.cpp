@@ -145,10 +145,12 @@ int main(int argc, char** argv) {
                                                         !dump.empty()));
     }
   } else {
-  threads.push_back(start_pipe<copy_to_device_pipe>(queue_in_functor{copy_q}, queue_out_functor{unpack_q}, q));
-  threads.push_back(start_unpack_pipe(cfg.baseband_format_type, queue_in_functor{unpack_q}, queue_out_functor{r2c_q}, q));
+    threads.push_back(start_pipe<copy_to_device_pipe>(queue_in_functor{copy_q}, queue_out_functor{unpack_q}, q));
+    threads.push_back(
+        start_unpack_pipe(cfg.baseband_format_type, queue_in_functor{unpack_q}, queue_out_functor{r2c_q}, q));
   }
   if (fused > 0) {
+    // nothing else to start: the chain pipes drain straight into the sink
   } else if (!composite) {
     threads.push_back(start_pipe<fft_1d_r2c_pipe>(queue_in_functor{r2c_q}, queue_out_functor{s1_q}, q));
     threads.push_back(start_pipe<rfi_mitigation_s1_pipe>(queue_in_functor{s1_q}, queue_out_functor{dd_q}, q));
