@@ -116,8 +116,6 @@ int main(int argc, char** argv) {
   if (cfg.baseband_format_type == "naocpsr_snap1" || cfg.baseband_format_type == "interleaved_samples_2" ||
       cfg.baseband_format_type == "gznupsr_a1")
     streams = 2;
-  const size_t block_bytes =
-      cfg.baseband_input_count * static_cast<size_t>(std::abs(cfg.baseband_input_bits)) / 8 * streams;
 
   srtb::cuda_queue q{std::atoi(arg(argc, argv, "--device", "0"))};
 
