@@ -10,7 +10,7 @@ Contract (driver): python bench.py --gpus N --steps K --warmup W [--impl referen
     C = 2^11 channels (srtb_config.cfg thresholds); N > 1 shards independent blocks across ranks
     (weak scaling, no collective on the data path);
   * `value`  = samples / time with the blocks already resident in HBM (ring of 16 distinct blocks,
-    256 MiB > L2, so successive steps never re-read a cached input); blocks alternate over 4 contexts
+    256 MiB > L2, so successive steps never re-read a cached input); blocks alternate over 6 contexts
     (CUDA streams) per GPU, two blocks in flight per context, so one block's small detector-tail kernels
     overlap the next block's FFT sweeps — every block still runs the whole chain and its result is read back;
   * `e2e`    = the same from pinned HOST buffers through srtb_b200_submit_block()/collect_block() (the
@@ -329,8 +329,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--stage-iters", type=int, default=5)
     ap.add_argument("--contexts", type=int, default=int(os.environ.get("SRTB_BENCH_CONTEXTS", "0")),
-                    help="contexts (CUDA streams) per GPU that blocks alternate over (0 = 4, or 2 for blocks "
-                         "of 2^28 samples and more, whose sweeps are pure HBM streams with nothing to overlap)")
+                    help="contexts (CUDA streams) per GPU that blocks alternate over (0 = 6 up to 2^24-sample blocks, 4 up "
+                         "to 2^27, 2 above: long sweeps are pure HBM streams with little left to overlap)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     wname = args.workload
@@ -355,7 +355,7 @@ def main():
 
     n = 1 << w["log2n"]
     if args.contexts <= 0:
-        args.contexts = 4 if w["log2n"] < 28 else 2
+        args.contexts = 6 if w["log2n"] <= 24 else (4 if w["log2n"] < 28 else 2)
     fmt = srtb_b200.FORMAT_BY_NAME[w["fmt"]]
     streams = srtb_b200.FORMAT_STREAMS[fmt]
     block_bytes = n * streams * abs(w["bits"]) // 8
