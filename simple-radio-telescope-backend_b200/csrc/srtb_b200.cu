@@ -482,16 +482,15 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static encode_tiled_fn get_encode_tiled() {
-  static encode_tiled_fn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // resolved once; function-local static initialisation is thread-safe (contexts may be driven from several threads)
+  static const encode_tiled_fn fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<encode_tiled_fn>(p);
-  }
+      return reinterpret_cast<encode_tiled_fn>(p);
+    return static_cast<encode_tiled_fn>(nullptr);
+  }();
   return fn;
 }
 
