@@ -10,6 +10,7 @@
 #pragma once
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <optional>
 #include <stop_token>
 #include <string>
@@ -76,27 +77,91 @@ class baseband_chain_pipe {
  protected:
   srtb::cuda_queue q;
   block_config_holder holder;
+  struct pending_block {
+    int ticket;
+    srtb::work::copy_to_device_work work;
+  };
+  std::deque<pending_block> pending;  // blocks in the pinned-host ring of this queue's context
 
  public:
-  explicit baseband_chain_pipe(srtb::cuda_queue q_, bool keep_every_spectrum_ = false)
-      : q{q_}, keep_every_spectrum{keep_every_spectrum_} {}
+  /** ring_depth > 1: blocks go through srtb_b200_submit_block / collect_block (block k's H2D overlaps block k-1's
+   *  compute; results lag the input by ring_depth - 1 works and an idle tick from idle_queue_in_functor flushes).
+   *  ring_depth <= 1: one synchronous srtb_b200_process_block per work. */
+  explicit baseband_chain_pipe(srtb::cuda_queue q_, bool keep_every_spectrum_ = false, int ring_depth_ = 1)
+      : q{q_}, keep_every_spectrum{keep_every_spectrum_},
+        ring_depth{keep_every_spectrum_ ? 1 : std::min(ring_depth_, (int)SRTB_B200_RING_SLOTS)} {}
 
-  std::optional<std::vector<srtb::work::write_signal_work>> operator()(std::stop_token,
-                                                                       srtb::work::copy_to_device_work in_work) {
+  using out_type = std::vector<srtb::work::write_signal_work>;
+
+  std::optional<out_type> operator()(std::stop_token, srtb::work::copy_to_device_work in_work) {
+    cuda_check(cudaSetDevice(q.device()), "cudaSetDevice");
+    const bool idle_tick = (in_work.count == 0 && !in_work.baseband_data.baseband_ptr);
+    out_type out;
+    if (ring_depth <= 1) {
+      if (!idle_tick) run_synchronously(in_work, out);
+      return std::optional{std::move(out)};
+    }
+    if (!idle_tick) {
+      holder.refresh();
+      const int ticket = srtb_b200_submit_block(q.ctx(), &holder.cfg, in_work.baseband_data.baseband_ptr.get(),
+                                                in_work.baseband_data.baseband_input_bytes);
+      q.check(ticket);
+      pending.push_back({ticket, std::move(in_work)});
+    }
+    while (!pending.empty() && (idle_tick || (int)pending.size() >= ring_depth)) {
+      pending_block p = std::move(pending.front());
+      pending.pop_front();
+      srtb_b200_detect_result res[4];
+      const int n = srtb_b200_collect_block(q.ctx(), p.ticket, res);
+      q.check(n);
+      bool hit = false;
+      for (int s = 0; s < n; s++)
+        for (int b = 0; b < res[s].n_boxcars; b++) hit = hit || res[s].signal_count[b] > 0;
+      if (hit) {
+        // the ring keeps result headers only (its work buffers belong to the next block by now): a candidate's time
+        // series and dynamic spectrum come from running that block once more (deterministic chain; hits are rare)
+        run_synchronously(p.work, out);
+      } else {
+        append_headers(p.work, res, n, out);
+      }
+    }
+    return std::optional{std::move(out)};
+  }
+
+  bool keep_every_spectrum = false;
+  int ring_depth = 1;
+
+ protected:
+  void append_headers(const srtb::work::copy_to_device_work& in_work, const srtb_b200_detect_result* res, int n,
+                      out_type& out) {
+    const auto& cfg = holder.cfg;
+    const int streams = block_config_holder::stream_count(cfg.baseband_format);
+    const size_t Nc = cfg.baseband_input_count / 2;
+    const size_t C = std::min<size_t>(cfg.spectrum_channel_count, Nc), L = Nc / C;
+    for (int s = 0; s < n; s++) {
+      srtb::work::write_signal_work w;
+      w.copy_parameter_from(in_work);
+      w.data_stream_id = in_work.data_stream_id * static_cast<uint32_t>(streams) + static_cast<uint32_t>(s);
+      w.count = L;
+      w.batch_size = C;
+      w.zero_count = res[s].zero_count;
+      out.push_back(std::move(w));
+    }
+  }
+
+  void run_synchronously(const srtb::work::copy_to_device_work& in_work, out_type& out) {
     holder.refresh();
     const auto& cfg = holder.cfg;
     const int streams = block_config_holder::stream_count(cfg.baseband_format);
     const size_t Nc = cfg.baseband_input_count / 2;
     const size_t C = std::min<size_t>(cfg.spectrum_channel_count, Nc), L = Nc / C;
-    cuda_check(cudaSetDevice(q.device()), "cudaSetDevice");
     auto h_series = srtb::host_allocator.allocate_shared<srtb::real>((size_t)streams * SRTB_B200_MAX_BOXCARS * L);
     srtb_b200_detect_result res[4];
     const int n = srtb_b200_process_block(q.ctx(), &cfg, in_work.baseband_data.baseband_ptr.get(),
                                           in_work.baseband_data.baseband_input_bytes, res, h_series.get(), 0);
     q.check(n);
-    std::vector<srtb::work::write_signal_work> out(static_cast<size_t>(n));
     for (int s = 0; s < n; s++) {
-      auto& w = out[static_cast<size_t>(s)];
+      srtb::work::write_signal_work w;
       w.copy_parameter_from(in_work);
       w.data_stream_id = in_work.data_stream_id * static_cast<uint32_t>(streams) + static_cast<uint32_t>(s);
       w.count = L;
@@ -121,12 +186,10 @@ class baseband_chain_pipe {
                    "spectrum copy");
         w.ptr = d_spec;
       }
+      out.push_back(std::move(w));
     }
     q.wait();
-    return std::optional{std::move(out)};
   }
-
-  bool keep_every_spectrum = false;
 };
 
 }  // namespace pipeline

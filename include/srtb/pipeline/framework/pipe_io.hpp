@@ -33,6 +33,29 @@ class queue_in_functor {
   }
 };
 
+/** like queue_in_functor, but hands the pipe a default-constructed work (count == 0: an "idle tick") when nothing
+ *  arrived for `idle_polls` polls — lets a pipe that keeps blocks in flight (baseband_chain_pipe) flush them when the
+ *  stream pauses or ends. Not in the reference (its pipes hold no state across works). */
+template <typename QueuePtr>
+class idle_queue_in_functor {
+  QueuePtr q_;
+  size_t idle_polls_;
+  using Work = typename std::pointer_traits<QueuePtr>::element_type::work_type;
+
+ public:
+  explicit idle_queue_in_functor(QueuePtr q, size_t idle_polls = 200) : q_{q}, idle_polls_{idle_polls} {}
+  std::optional<Work> operator()(std::stop_token st) {
+    Work w;
+    size_t polls = 0;
+    while (!q_->pop(w)) {
+      if (st.stop_requested()) return std::nullopt;
+      if (++polls >= idle_polls_) return Work{};
+      std::this_thread::sleep_for(std::chrono::nanoseconds(srtb::config.thread_query_work_wait_time));
+    }
+    return w;
+  }
+};
+
 template <typename QueuePtr>
 class queue_out_functor {
   QueuePtr q_;

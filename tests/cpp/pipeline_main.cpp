@@ -134,13 +134,14 @@ int main(int argc, char** argv) {
 
   std::vector<std::jthread> threads;
   const int fused = std::atoi(arg(argc, argv, "--fused", "0"));
+  const int ring_depth = std::atoi(arg(argc, argv, "--ring", "1"));  // > 1: submit/collect ring inside each chain pipe
   if (fused > 0) {
     // the whole device chain as one pipe (fused kernels), `fused` of them on their own queue each, all fed from
     // the same MPMC queue: blocks alternate over the contexts and overlap on the GPU
     for (int i = 0; i < fused; i++) {
       srtb::cuda_queue qi = (i == 0) ? q : srtb::cuda_queue{q.device()};
-      threads.push_back(start_pipe<baseband_chain_pipe>(queue_in_functor{copy_q}, multiple_works_out_functor{sink}, qi,
-                                                        !dump.empty()));
+      threads.push_back(start_pipe<baseband_chain_pipe>(idle_queue_in_functor{copy_q}, multiple_works_out_functor{sink}, qi,
+                                                        !dump.empty(), ring_depth));
     }
   } else {
     threads.push_back(start_pipe<copy_to_device_pipe>(queue_in_functor{copy_q}, queue_out_functor{unpack_q}, q));

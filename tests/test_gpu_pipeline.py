@@ -135,6 +135,28 @@ def test_pipeline_fused_chain_pipe(tmp_path, oracle, fused):
     assert detected > 0
 
 
+def test_pipeline_fused_chain_pipe_ring_equals_synchronous(tmp_path):
+    """baseband_chain_pipe over the submit/collect ring (H2D of block k overlaps block k-1; headers from the ring,
+    a candidate's series by re-running the block) must report exactly what the synchronous pipe reports."""
+    _build()
+    logn, C_ = 18, 64
+    n = 1 << logn
+    blocks = [_block(n, s) for s in range(51, 58)]
+    inp = tmp_path / "bb_ring.bin"
+    np.concatenate(blocks).tofile(inp)
+    outs = []
+    for extra in (("--fused", "1"), ("--fused", "1", "--ring", "3"), ("--fused", "2", "--ring", "2")):
+        cmd = [str(BIN), "--input", str(inp), "--log2n", str(logn), "--bits", "-8", "--format", "simple", "--channels",
+               str(C_), "--dm", "0", "--avg-thr", "5", "--sk-thr", "1.3", "--snr", "6", "--max-boxcar", "64", *extra]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        works = sorted((json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")), key=lambda w: w["block"])
+        assert [w["block"] for w in works] == list(range(7))
+        outs.append([(w["zero_count"], [(s_["boxcar"], s_["count"], s_["length"]) for s_ in w["series"]]) for w in works])
+    assert outs[0] == outs[1] == outs[2]
+    assert any(series for _, series in outs[0])                       # the bursts are candidates
+
+
 def test_pipeline_fused_chain_pipe_dual_pol(tmp_path, oracle):
     _build()
     logn, C_, dm = 16, 16, 0.0

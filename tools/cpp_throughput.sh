@@ -11,7 +11,7 @@ with open("/dev/shm/srtb_bb.bin", "wb") as f:
         f.write(np.roll(blk, i * 4099).tobytes())
 PY
 COMMON="--input /dev/shm/srtb_bb.bin --log2n 24 --bits -8 --format simple --channels 2048 --dm 56.778 --avg-thr 5 --sk-thr 1.05 --snr 8 --max-boxcar 256"
-for mode in "--composite 0" "--composite 1" "--fused 1" "--fused 3" "--fused 4"; do
+for mode in "--composite 0" "--composite 1" "--fused 1" "--fused 1 --ring 3" "--fused 2 --ring 3" "--fused 3" "--fused 4"; do
   echo "== $mode"; SRTB_LOG_LEVEL=1 ./tests/cpp/pipeline_main $COMMON $mode --preload 1 --repeat 16 2>&1 >/dev/null | grep pipeline_main
 done
 rm -f /dev/shm/srtb_bb.bin
