@@ -759,3 +759,55 @@ def test_fft_r2c_tones_land_in_their_bins_at_full_length(ctx, k):
     for f, _ in tones:
         mag[f] = 0
     assert float(mag.max()) < 2e-5 * n / 2          # everything else is rounding noise
+
+
+@pytest.mark.parametrize("bits,logn,C_,window,reserve,dm", [
+    (2, 16, 32, 0, 0, 0.0),        # the shipped J1644 width, small block
+    (4, 15, 8, 0, 0, 0.3),
+    (1, 16, 16, 0, 0, 0.0),
+    (8, 16, 16, 0, 0, 0.0),        # unsigned 8-bit: the uint8 variant of the fused raw first sweep
+    (16, 14, 16, 0, 0, 0.0),
+    (-16, 14, 4, 0, 0, 0.1),
+    (-8, 15, 16, 2, 0, 0.0),       # hamming window: unpack cannot be fused into the FFT
+    (-8, 18, 16, 0, 1, 0.02),      # baseband_reserve_sample: the detector trims the smeared tail
+    (-8, 10, 2048, 0, 0, 0.0),     # more channels than bins: batch = Nc, one time sample per channel
+    (-8, 13, 2, 0, 0, 0.0),        # L = 2048 rows, two channels
+])
+def test_chain_odd_configs_vs_oracle(ctx, oracle, bits, logn, C_, window, reserve, dm):
+    """process_block against the oracle chain over the corners of the configuration space the reference accepts
+    (unpack_pipe.hpp:72-127 widths, fft_window.hpp windows, reserve_sample, spectrum_channel_count > Nc)."""
+    n = 1 << logn
+    rng = np.random.default_rng(abs(bits) * 100 + logn)
+    ab = abs(bits)
+    if ab < 8:
+        raw = rng.integers(0, 256, n * ab // 8, dtype=np.uint8)
+    elif ab == 8:
+        v = np.clip(np.round(rng.standard_normal(n) * 20), -127, 127)
+        v[n // 2:n // 2 + 64] += np.round(rng.standard_normal(64) * 60)
+        v = np.clip(v, -127, 127)
+        raw = (v.astype(np.int8).view(np.uint8) if bits < 0 else (v + 128).astype(np.uint8))
+    else:
+        v = np.round(rng.standard_normal(n) * 2000)
+        raw = (v.astype(np.int16) if bits < 0 else (v + 32768).astype(np.uint16)).view(np.uint8)
+    cfg = make_block_config(n, bits, srtb_b200.FORMAT_SIMPLE, C_, dm, avg_thr=5.0, sk_thr=1.3, snr=6.0, maxbox=32)
+    cfg.window = window
+    cfg.baseband_reserve_sample = reserve
+    work, eres, eseries, _ = oracle.chain(raw, oracle_chain_config(cfg))
+    nc = n // 2
+    Cb = min(C_, nc)
+    L = nc // Cb
+    h_series = np.zeros((srtb_b200.MAX_BOXCARS, L), np.float32)
+    res = ctx.process_block(cfg, torch.from_numpy(raw.copy()).pin_memory(), raw.size, h_series, copy_all=True)
+    assert len(res) == 1
+    got = _from_device_ptr(ctx.block_spectrum_ptr(0), nc).reshape(Cb, L)
+    espec = work[:n].view(np.complex64).reshape(Cb, L)
+    gzap, ezap = np.all(got == 0, axis=1), np.all(espec == 0, axis=1)
+    assert (gzap != ezap).sum() <= max(1, Cb // 200), "SK zap decisions differ beyond borderline channels"
+    same = gzap == ezap
+    if np.linalg.norm(espec[same]) > 0:
+        assert rel_l2(got[same], espec[same]) < 5 * REL_L2
+    assert res[0].time_series_count == eres.time_series_count
+    if np.array_equal(gzap, ezap):
+        assert res[0].zero_count == eres.zero_count and res[0].detect_enabled == eres.detect_enabled
+        if res[0].detect_enabled:
+            _compare_detect(res[0], eres, h_series, eseries, 6.0)
