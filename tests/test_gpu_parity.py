@@ -811,3 +811,41 @@ def test_chain_odd_configs_vs_oracle(ctx, oracle, bits, logn, C_, window, reserv
         assert res[0].zero_count == eres.zero_count and res[0].detect_enabled == eres.detect_enabled
         if res[0].detect_enabled:
             _compare_detect(res[0], eres, h_series, eseries, 6.0)
+
+
+@pytest.mark.parametrize("fmt_name,bits,streams", [("INTERLEAVED_2", 8, 2), ("INTERLEAVED_2", -8, 2),
+                                                   ("NAOCPSR_SNAP1", -8, 2), ("GZNUPSR_A1_2", 8, 2),
+                                                   ("GZNUPSR_A1_4", 8, 4)])
+def test_process_block_equals_per_pipe_composition(ctx, fmt_name, bits, streams):
+    """Every multi-stream board format through the fused process_block (raw first sweep for the two-stream 8-bit
+    layouts, fused last sweep, fused s1 + chirp + waterfall + SK) against the SAME block pushed through the seven
+    per-pipe entry points, each of which is pinned to the oracle elsewhere in this file."""
+    fmt = getattr(srtb_b200, "FORMAT_" + fmt_name)
+    n, C_, dm = 1 << 17, 16, 0.05
+    nc, L = n // 2, n // 2 // C_
+    rng = np.random.default_rng(streams * 10 + abs(bits))
+    v = np.clip(np.round(rng.standard_normal(n * streams) * 18), -100, 100).astype(np.int8)
+    raw = v.view(np.uint8) if bits < 0 else (v.astype(np.int16) + 128).astype(np.uint8)
+    cfg = make_block_config(n, bits, fmt, C_, dm, avg_thr=5.0, sk_thr=1.3, snr=6.0, maxbox=64)
+    hs = np.zeros((streams, srtb_b200.MAX_BOXCARS, L), np.float32)
+    res = ctx.process_block(cfg, torch.from_numpy(raw.copy()).pin_memory(), raw.size, hs, copy_all=True)
+    assert len(res) == streams
+    fused = [_from_device_ptr(ctx.block_spectrum_ptr(s_), nc).reshape(C_, L).copy() for s_ in range(streams)]
+    bufs = [torch.zeros(n + 2, dtype=torch.float32, device="cuda") for _ in range(streams)]
+    ctx.unpack(dev(raw), raw.size, bits, fmt, 0, bufs, n)
+    coef = srtb_b200.norm_coefficient(nc, C_)
+    f_min, bw = np.float32(1000.0), np.float32(500.0)
+    for s_ in range(streams):
+        b = bufs[s_]
+        ctx.fft_r2c_inplace(b, n)
+        ctx.rfi_s1(b, nc, 5.0, coef, [])
+        ctx.dedisperse(b, nc, float(f_min), float(f_min + bw), float(bw / np.float32(nc)), dm)
+        ctx.watfft_c2c_backward(b, L, C_)
+        ctx.rfi_s2_sk(b, L, C_, 1.3)
+        series = np.zeros((srtb_b200.MAX_BOXCARS, L), np.float32)
+        r = ctx.signal_detect(b, L, C_, 0, 6.0, 0.9, 64, series, copy_all=True)
+        ref = b[:n].cpu().numpy().view(np.complex64).reshape(C_, L)
+        gz, rz = np.all(fused[s_] == 0, axis=1), np.all(ref == 0, axis=1)
+        assert np.array_equal(gz, rz)
+        assert rel_l2(fused[s_][~gz], ref[~rz]) < REL_L2
+        _compare_detect(res[s_], r, hs[s_], series, 6.0)
