@@ -40,6 +40,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 import numpy as np  # noqa: E402
 
+SRTB_RING_SLOTS = 3   # SRTB_B200_RING_SLOTS in include/srtb_b200.h
 METRIC = "Gsamples/s 8-bit baseband through full dedisperse chain"
 UNIT = "Gsamples/s"
 
@@ -401,14 +402,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, finish=None):
+    def timed(fn, steps, finish=None, body=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for st in extra_streams:
             st.wait_stream(stream)
-        for i in range(steps):
-            fn(i)
+        if body:
+            body(steps)
+        else:
+            for i in range(steps):
+                fn(i)
         if finish:
             finish()
         for st in extra_streams:
@@ -444,6 +448,29 @@ def main():
         while dtickets:
             _dcollect()
 
+    def device_body(steps):
+        """one host thread per context (ctypes releases the GIL inside the C calls): the ~10 launches per block are
+        enqueued in parallel, so a slow host core does not cap the device-resident figure. Context c takes blocks
+        c, c + n, c + 2n, ... and keeps two in flight."""
+        found = [0] * len(ctxs)
+
+        def worker(ci):
+            c, mine, det = ctxs[ci], [], 0
+            for i in range(ci, steps, len(ctxs)):
+                mine.append(c.submit_block_device(cfg, dev_blocks[i % ring], block_bytes))
+                if len(mine) >= 2:
+                    det += sum(int(r.signal_count[b]) for r in c.collect_block(mine.pop(0)) for b in range(r.n_boxcars))
+            while mine:
+                det += sum(int(r.signal_count[b]) for r in c.collect_block(mine.pop(0)) for b in range(r.n_boxcars))
+            found[ci] = det
+
+        workers = [threading.Thread(target=worker, args=(ci,)) for ci in range(len(ctxs))]
+        for t_ in workers:
+            t_.start()
+        for t_ in workers:
+            t_.join()
+        detections[0] += sum(found)
+
     # e2e goes through the pipelined ingest API (pinned-host ring): block i's H2D runs on the copy stream
     # while block i-1 computes; every block's detector result is read back on the host
     tickets = []
@@ -464,14 +491,19 @@ def main():
             _collect()
 
     # ---- device-resident throughput (`value`)
-    for i in range(args.warmup):
+    # untimed warm-up: at least W steps, and enough that EVERY context has seen every ring slot once (first use
+    # allocates scratch, builds twiddle tables and sets kernel attributes: cudaMalloc would stall the timed region)
+    warm = max(args.warmup, (SRTB_RING_SLOTS + 1) * len(ctxs))
+    for i in range(warm):
         step_device(i)
     drain_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = sum(c.launch_count for c in ctxs)
-    ms_total = timed(step_device, args.steps, drain_device)
+    # one host thread per context was measured slower and erratic under the GIL (100..136 vs a steady 139): opt-in only
+    threaded = len(ctxs) > 1 and os.environ.get("SRTB_BENCH_THREADS", "0") == "1"
+    ms_total = timed(step_device, args.steps, drain_device, body=device_body if threaded else None)
     launches = sum(c.launch_count for c in ctxs) - l0
     if rank == 0 and not sampler.rows:
         sampler.snapshot()          # short run: take one sample while the GPU is still under load
@@ -480,7 +512,7 @@ def main():
     value = samples_per_step / (ms_per_step * 1e-3) / 1e9
 
     # ---- end to end from pinned host memory (`e2e`)
-    for i in range(args.warmup):
+    for i in range(warm):
         step_e2e(i)
     drain_e2e()
     e2e_runs = [timed(step_e2e, args.steps, drain_e2e) / args.steps for _ in range(3)]
@@ -595,7 +627,8 @@ def main():
                                    f"{abs(w['bits'])}-bit {w['fmt']}, C=2^11, DM={w['dm']}, full RFI + detect",
                        "parallelism": f"block-sharded x{world} (no collective)",
                        "l2": f"inputs larger than L2: ring of {ring} distinct blocks ({ring * block_bytes >> 20} MiB)",
-                       "contexts_per_gpu": len(ctxs), "detections": detections[0]},
+                       "contexts_per_gpu": len(ctxs), "submit_threads_per_gpu": len(ctxs) if threaded else 1, "warmup_steps_run": warm,
+                       "detections": detections[0]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "runs_ms_per_step": e2e_runs, "note": "median of three runs of K steps each",
