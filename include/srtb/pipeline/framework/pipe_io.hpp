@@ -16,6 +16,28 @@
 namespace srtb {
 namespace pipeline {
 
+/** how a pipe thread waits on an empty (or full) queue: spin briefly — a block spends tens of microseconds per
+ *  stage on a B200, while sleep_for(1 us) really sleeps ~60 us (timer slack) — then fall back to the reference's
+ *  sleep of thread_query_work_wait_time ns (pipe_io.hpp:45). */
+struct queue_backoff {
+  static constexpr int spin_limit = 2048;
+  int spins = 0;
+  /** returns true when this wait ended in a real sleep (used to count idle polls) */
+  bool wait() {
+    if (spins < spin_limit) {
+      spins++;
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#else
+      std::this_thread::yield();
+#endif
+      return false;
+    }
+    std::this_thread::sleep_for(std::chrono::nanoseconds(srtb::config.thread_query_work_wait_time));
+    return true;
+  }
+};
+
 template <typename QueuePtr>
 class queue_in_functor {
   QueuePtr q_;
@@ -25,9 +47,10 @@ class queue_in_functor {
   explicit queue_in_functor(QueuePtr q) : q_{q} {}
   std::optional<Work> operator()(std::stop_token st) {
     Work w;
+    queue_backoff backoff;
     while (!q_->pop(w)) {
       if (st.stop_requested()) return std::nullopt;
-      std::this_thread::sleep_for(std::chrono::nanoseconds(srtb::config.thread_query_work_wait_time));
+      backoff.wait();
     }
     return w;
   }
@@ -43,14 +66,15 @@ class idle_queue_in_functor {
   using Work = typename std::pointer_traits<QueuePtr>::element_type::work_type;
 
  public:
-  explicit idle_queue_in_functor(QueuePtr q, size_t idle_polls = 200) : q_{q}, idle_polls_{idle_polls} {}
+  explicit idle_queue_in_functor(QueuePtr q, size_t idle_polls = 4) : q_{q}, idle_polls_{idle_polls} {}
   std::optional<Work> operator()(std::stop_token st) {
     Work w;
     size_t polls = 0;
+    queue_backoff backoff;
     while (!q_->pop(w)) {
       if (st.stop_requested()) return std::nullopt;
-      if (++polls >= idle_polls_) return Work{};
-      std::this_thread::sleep_for(std::chrono::nanoseconds(srtb::config.thread_query_work_wait_time));
+      if (polls >= idle_polls_) return Work{};
+      if (backoff.wait()) polls++;
     }
     return w;
   }
@@ -64,9 +88,10 @@ class queue_out_functor {
  public:
   explicit queue_out_functor(QueuePtr q) : q_{q} {}
   void operator()(std::stop_token st, Work w) {
+    queue_backoff backoff;
     while (!q_->push(w)) {
       if (st.stop_requested()) return;
-      std::this_thread::sleep_for(std::chrono::nanoseconds(srtb::config.thread_query_work_wait_time));
+      backoff.wait();
     }
   }
 };

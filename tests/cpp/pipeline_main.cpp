@@ -208,7 +208,7 @@ int main(int argc, char** argv) {
     for (int r = 0; r < repeat; r++)
       for (auto w : preloaded) {
         w.udp_packet_counter = (uint64_t)blocks;
-        while (copy_q->read_available() >= 8) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        while (copy_q->read_available() >= 8) std::this_thread::yield();
         copy_q->push(w);
         blocks++;
       }
@@ -217,7 +217,7 @@ int main(int argc, char** argv) {
     read_file_pipe reader;
     feed(reader, true);
   }
-  while (done->load() < blocks * (int)streams) std::this_thread::sleep_for(std::chrono::microseconds(200));
+  while (done->load() < blocks * (int)streams) std::this_thread::yield();
   {
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     std::fprintf(stderr, "[pipeline_main] %d block(s) x %zu stream(s) of 2^%d samples in %.3f s = %.2f Gsamples/s (host wall clock: source + H2D + chain + D2H)\n",
