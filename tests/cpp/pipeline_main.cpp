@@ -144,7 +144,11 @@ int main(int argc, char** argv) {
                                                         !dump.empty(), ring_depth));
     }
   } else {
-    threads.push_back(start_pipe<copy_to_device_pipe>(queue_in_functor{copy_q}, queue_out_functor{unpack_q}, q));
+    // the H2D copy gets its own queue (stream): block k+1 crosses PCIe while block k computes; the hand-over is the
+    // pipe's own wait() (drop-in contract: the work is complete when the pipe returns)
+    // (not in the stream-ordered composite mode, where pipes do not wait and must share one stream)
+    srtb::cuda_queue q_copy = composite ? q : srtb::cuda_queue{q.device()};
+    threads.push_back(start_pipe<copy_to_device_pipe>(queue_in_functor{copy_q}, queue_out_functor{unpack_q}, q_copy));
     threads.push_back(
         start_unpack_pipe(cfg.baseband_format_type, queue_in_functor{unpack_q}, queue_out_functor{r2c_q}, q));
   }
