@@ -164,3 +164,58 @@ def test_signal_detect_pipe(oracle, C_, L, maxbox, reserve):
     assert set(exp) - set(got) <= {bc for bc, b in exp.items() if res.signal_count[b] <= 1}
     assert len(got) > 0
     assert ref.count_signal(series[0, :int(res.series_length[0])], snr) == res.signal_count[0]
+
+
+@pytest.mark.parametrize("logn,C_,dm,bits", [(14, 16, 0.0, -8), (15, 32, 0.02, -8), (14, 8, 0.0, 2)])
+def test_whole_chain_composition(oracle, logn, C_, dm, bits):
+    """The reference's pipes composed as main.cpp:170-204 wires them (unpack -> R2C -> drop Nyquist -> s1 pipe ->
+    dedisperse pipe -> waterfall FFT -> s2 pipe -> signal_detect_pipe_2), each stage being the reference's OWN code
+    through the shim, against the oracle's one-call chain: pins sizes, the Nyquist drop, the [C][L] row layout, the
+    normalisation coefficient and the detector's view of the spectrum — not only the stages in isolation."""
+    import oracle_lib
+    n = 1 << logn
+    nc, L = n // 2, n // 2 // C_
+    rng = np.random.default_rng(logn * 7 + C_)
+    if bits == -8:
+        v = np.clip(np.round(rng.standard_normal(n) * 20), -127, 127)
+        v[n // 2:n // 2 + 32] += np.round(rng.standard_normal(32) * 90)
+        raw = np.clip(v, -127, 127).astype(np.int8).view(np.uint8)
+    else:
+        raw = rng.integers(0, 256, n * bits // 8, dtype=np.uint8)
+    f_low, bw, fs = 1000.0, 500.0, 1e9
+    avg_thr, sk_thr, snr, chan_thr, maxbox = 5.0, 1.3, 6.0, 0.9, 32
+    # --- the reference, stage by stage
+    x = ref.unpack(raw, n, bits)
+    spec = ref.fft_r2c(x)[:nc]                                   # fft_pipe.hpp:75-77: count = N/2
+    spec = ref.rfi_s1_pipe(spec, avg_thr, C_, f_low, bw, "1200-1201")
+    spec = ref.dedisperse_pipe(spec, f_low, bw, dm)
+    spec = ref.watfft(spec, L, C_)
+    spec = ref.rfi_s2_pipe(spec, L, C_, sk_thr).reshape(C_, L)
+    holders = ref.signal_detect_pipe(spec.reshape(-1), L, C_, n, False, f_low, bw, fs, dm, snr, chan_thr, maxbox)
+    # --- the oracle chain
+    import ctypes as CT
+    cfg = oracle_lib.ChainConfig()
+    cfg.baseband_input_count, cfg.baseband_input_bits, cfg.window = n, bits, 0
+    cfg.baseband_freq_low, cfg.baseband_bandwidth, cfg.baseband_sample_rate, cfg.dm = f_low, bw, fs, dm
+    cfg.baseband_reserve_sample = 0
+    cfg.rfi_average_threshold, cfg.rfi_sk_threshold = avg_thr, sk_thr
+    cfg.spectrum_channel_count = C_
+    cfg.snr_threshold, cfg.channel_threshold, cfg.max_boxcar_length = snr, chan_thr, maxbox
+    arr = (CT.c_float * 2)(1200.0, 1201.0)
+    cfg.rfi_pairs, cfg.n_rfi_pairs = CT.cast(arr, CT.POINTER(CT.c_float)), 1
+    work, res, series, _ = oracle.chain(raw, cfg)
+    ospec = work[:n].view(np.complex64).reshape(C_, L)
+    rz, oz = np.all(spec == 0, axis=1), np.all(ospec == 0, axis=1)
+    assert (rz != oz).sum() <= 1                                  # SK border only
+    same = rz == oz
+    assert rel(ospec[same], spec[same]) < 2e-7                    # same arithmetic; reduction order is the runtime's
+    if np.array_equal(rz, oz):
+        assert res.zero_count == int(np.sum(np.abs(spec[:, 0]) ** 2 == 0))
+        got = {h["boxcar"]: h for h in holders}
+        for b in range(res.n_boxcars):
+            bc = int(res.boxcar_length[b])
+            if res.signal_count[b] > 1:
+                assert bc in got and abs(got[bc]["count"] - int(res.signal_count[b])) <= 1
+        for bc, h in got.items():
+            b = [i for i in range(res.n_boxcars) if res.boxcar_length[i] == bc][0]
+            assert h["length"] == res.series_length[b]
