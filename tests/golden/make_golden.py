@@ -69,6 +69,34 @@ def main():
         g[f"det_series_{h['boxcar']}"] = h["series"]
     np.savez_compressed(HERE / "srtb_golden.npz", **g)
     print("wrote", HERE / "srtb_golden.npz", sum(v.nbytes for v in g.values()), "bytes in", len(g), "arrays")
+    chain_golden(ref)
+
+
+def chain_golden(ref):
+    """One block through the reference's pipes composed as main.cpp:170-204 wires them (every stage = the reference's
+    own code through the shim): the fixture the GPU box checks srtb_b200_process_block against."""
+    rng = np.random.default_rng(20260922)
+    n, C_, dm = 1 << 15, 16, 0.0
+    nc, L = n // 2, n // 2 // C_
+    v = np.clip(np.round(rng.standard_normal(n) * 20), -127, 127)
+    v[n // 2:n // 2 + 48] += np.round(rng.standard_normal(48) * 90)
+    raw = np.clip(v, -127, 127).astype(np.int8).view(np.uint8)
+    f_low, bw, fs, avg_thr, sk_thr, snr, chan_thr, maxbox = 1000.0, 500.0, 1e9, 5.0, 1.3, 6.0, 0.9, 64
+    spec = ref.fft_r2c(ref.unpack(raw, n, -8))[:nc]
+    spec = ref.rfi_s1_pipe(spec, avg_thr, C_, f_low, bw, "1200-1201")
+    spec = ref.dedisperse_pipe(spec, f_low, bw, dm)
+    spec = ref.watfft(spec, L, C_)
+    spec = ref.rfi_s2_pipe(spec, L, C_, sk_thr)
+    hs = ref.signal_detect_pipe(spec, L, C_, n, False, f_low, bw, fs, dm, snr, chan_thr, maxbox)
+    g = {"raw": raw, "params": np.array([n, C_, dm, f_low, bw, fs, avg_thr, sk_thr, snr, chan_thr, maxbox], np.float64),
+         "freq_pairs": np.array([1200.0, 1201.0], np.float32), "spectrum": spec.reshape(C_, L),
+         "zero_count": np.array([int(np.sum(np.abs(spec.reshape(C_, L)[:, 0]) ** 2 == 0))], np.int64),
+         "det_boxcar": np.array([h["boxcar"] for h in hs], np.int64),
+         "det_count": np.array([h["count"] for h in hs], np.int64),
+         "det_length": np.array([h["length"] for h in hs], np.int64)}
+    np.savez_compressed(HERE / "srtb_chain_golden.npz", **g)
+    print("wrote", HERE / "srtb_chain_golden.npz", sum(v_.nbytes for v_ in g.values()), "bytes;",
+          "candidates at boxcars", g["det_boxcar"].tolist(), "counts", g["det_count"].tolist())
 
 
 if __name__ == "__main__":

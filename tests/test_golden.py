@@ -130,3 +130,70 @@ def test_gpu_stages_golden(ctx):
         assert res.signal_count[b] == cnt and res.series_length[b] == ln
         gold = G[f"det_series_{bc}"]
         assert np.abs(h[b, :ln] - gold).max() < 2e-6 * np.abs(gold).max() * np.sqrt(float(bc)) + 1e-3
+
+
+CHAIN = np.load(Path(__file__).resolve().parent / "golden" / "srtb_chain_golden.npz")
+
+
+def _chain_params():
+    n, C_, dm, f_low, bw, fs, avg_thr, sk_thr, snr, chan_thr, maxbox = CHAIN["params"]
+    return int(n), int(C_), float(dm), float(f_low), float(bw), float(fs), float(avg_thr), float(sk_thr), float(snr), \
+        float(chan_thr), int(maxbox)
+
+
+def _check_chain(spec, zero_count, counts_by_boxcar, lengths_by_boxcar):
+    gold = CHAIN["spectrum"]
+    gz, ez = np.all(spec == 0, axis=1), np.all(gold == 0, axis=1)
+    assert np.array_equal(gz, ez)
+    assert rel(spec[~gz], gold[~ez]) < 5e-6
+    assert zero_count == int(CHAIN["zero_count"][0])
+    for bc, cnt, ln in zip(CHAIN["det_boxcar"], CHAIN["det_count"], CHAIN["det_length"]):
+        assert lengths_by_boxcar[int(bc)] == int(ln)
+        assert abs(counts_by_boxcar[int(bc)] - int(cnt)) <= 1
+
+
+def test_oracle_chain_golden(oracle):
+    """the oracle's one-call chain against the reference's own pipes composed as main.cpp wires them"""
+    import ctypes as CT
+    import oracle_lib
+    n, C_, dm, f_low, bw, fs, avg_thr, sk_thr, snr, chan_thr, maxbox = _chain_params()
+    cfg = oracle_lib.ChainConfig()
+    cfg.baseband_input_count, cfg.baseband_input_bits, cfg.window = n, -8, 0
+    cfg.baseband_freq_low, cfg.baseband_bandwidth, cfg.baseband_sample_rate, cfg.dm = f_low, bw, fs, dm
+    cfg.rfi_average_threshold, cfg.rfi_sk_threshold, cfg.spectrum_channel_count = avg_thr, sk_thr, C_
+    cfg.snr_threshold, cfg.channel_threshold, cfg.max_boxcar_length = snr, chan_thr, maxbox
+    arr = (CT.c_float * 2)(*CHAIN["freq_pairs"].tolist())
+    cfg.rfi_pairs, cfg.n_rfi_pairs = CT.cast(arr, CT.POINTER(CT.c_float)), 1
+    work, res, _, _ = oracle.chain(CHAIN["raw"], cfg)
+    L = n // 2 // C_
+    _check_chain(work[:n].view(np.complex64).reshape(C_, L), int(res.zero_count),
+                 {int(res.boxcar_length[b]): int(res.signal_count[b]) for b in range(res.n_boxcars)},
+                 {int(res.boxcar_length[b]): int(res.series_length[b]) for b in range(res.n_boxcars)})
+
+
+@pytest.mark.gpu
+def test_gpu_chain_golden(ctx):
+    """srtb_b200_process_block (fused kernels) against the same reference-generated fixture: the GPU box has no
+    /root/reference, the committed vectors carry the reference's own outputs there"""
+    import ctypes as CT
+    import torch
+    import srtb_b200
+    n, C_, dm, f_low, bw, fs, avg_thr, sk_thr, snr, chan_thr, maxbox = _chain_params()
+    cfg = srtb_b200.BlockConfig()
+    cfg.baseband_input_count, cfg.baseband_input_bits, cfg.baseband_format, cfg.window = n, -8, srtb_b200.FORMAT_SIMPLE, 0
+    cfg.baseband_freq_low, cfg.baseband_bandwidth, cfg.baseband_sample_rate, cfg.dm = f_low, bw, fs, dm
+    cfg.mitigate_rfi_average_method_threshold, cfg.mitigate_rfi_spectral_kurtosis_threshold = avg_thr, sk_thr
+    cfg.spectrum_channel_count = C_
+    cfg.signal_detect_signal_noise_threshold, cfg.signal_detect_channel_threshold = snr, chan_thr
+    cfg.signal_detect_max_boxcar_length = maxbox
+    arr = (CT.c_float * 2)(*CHAIN["freq_pairs"].tolist())
+    cfg.rfi_freq_pairs, cfg.n_rfi_freq_pairs = CT.cast(arr, CT.POINTER(CT.c_float)), 1
+    res = ctx.process_block(cfg, torch.from_numpy(CHAIN["raw"].copy()).pin_memory(), n, None)[0]
+    nc, L = n // 2, n // 2 // C_
+    out = np.empty(nc, np.complex64)
+    cudart = CT.CDLL("libcudart.so")
+    cudart.cudaMemcpy.argtypes = [CT.c_void_p, CT.c_void_p, CT.c_size_t, CT.c_int]
+    assert cudart.cudaMemcpy(out.ctypes.data, ctx.block_spectrum_ptr(0), out.nbytes, 2) == 0
+    _check_chain(out.reshape(C_, L), int(res.zero_count),
+                 {int(res.boxcar_length[b]): int(res.signal_count[b]) for b in range(res.n_boxcars)},
+                 {int(res.boxcar_length[b]): int(res.series_length[b]) for b in range(res.n_boxcars)})
