@@ -3,8 +3,9 @@
 // rfi_mitigation_s1 -> dedisperse -> watfft_1d_c2c -> rfi_mitigation_s2 -> signal_detect_pipe_2: takes the
 // copy_to_device_work a source pipe produced (pinned host block) and returns one write_signal_work per data stream,
 // the same objects signal_detect_pipe_2 hands to write_signal_pipe. Inside it is one
-// srtb_b200_process_block call, i.e. the fused kernels (unpack in the first FFT sweep, R2C split + power sum in
-// the last, s1 + chirp, waterfall FFT + SK + column sums), one H2D and one 1 KiB D2H per stream.
+// srtb_b200_submit_block_ex / collect_block_ex pair per block, i.e. the fused kernels (unpack in the first FFT
+// sweep, R2C split + power sum in the last, s1 + chirp + waterfall FFT + SK + column sums in one kernel), one H2D,
+// one 1 KiB D2H per stream, and the positive boxcar series written to pinned host memory by the detector kernel.
 // Throughput across blocks: start several of these pipes on their own cuda_queue (one CUDA stream + context each)
 // popping from one MPMC work queue — blocks then alternate over contexts and overlap on the GPU.
 #pragma once
@@ -79,17 +80,26 @@ class baseband_chain_pipe {
   block_config_holder holder;
   struct pending_block {
     int ticket;
+    int streams;
+    size_t C, L;
     srtb::work::copy_to_device_work work;
+    // what the block leaves behind, owned by the work items it turns into (zero copy, like the reference's d_in):
+    std::vector<std::shared_ptr<srtb::complex<srtb::real>>> d_spectrum;  // per stream: N + 2 floats, [C][L] when done
+    std::shared_ptr<srtb::real> h_series;                                 // pinned [streams][MAX_BOXCARS][L]
   };
   std::deque<pending_block> pending;  // blocks in the pinned-host ring of this queue's context
 
  public:
-  /** ring_depth > 1: blocks go through srtb_b200_submit_block / collect_block (block k's H2D overlaps block k-1's
-   *  compute; results lag the input by ring_depth - 1 works and an idle tick from idle_queue_in_functor flushes).
-   *  ring_depth <= 1: one synchronous srtb_b200_process_block per work. */
+  /** ring_depth blocks are kept in flight through srtb_b200_submit_block_ex / collect_block_ex (block k's H2D
+   *  overlaps block k-1's compute; results lag the input by ring_depth - 1 works and an idle tick from
+   *  idle_queue_in_functor flushes). ring_depth <= 1: every work is collected before operator() returns.
+   *  Every write_signal_work carries its dynamic spectrum (work.ptr) and the host series of its positive boxcars,
+   *  exactly what signal_detect_pipe_2 forwards (signal_detect_pipe.hpp:347-366,405-441): write_signal_pipe's
+   *  "neighbour of a positive" rule (write_signal_pipe.hpp:102-115) therefore sees a spectrum on negatives too.
+   *  keep_every_spectrum is kept for source compatibility; spectra are always kept now. */
   explicit baseband_chain_pipe(srtb::cuda_queue q_, bool keep_every_spectrum_ = false, int ring_depth_ = 1)
       : q{q_}, keep_every_spectrum{keep_every_spectrum_},
-        ring_depth{keep_every_spectrum_ ? 1 : std::min(ring_depth_, (int)SRTB_B200_RING_SLOTS)} {}
+        ring_depth{std::max(1, std::min(ring_depth_, (int)SRTB_B200_RING_SLOTS))} {}
 
   using out_type = std::vector<srtb::work::write_signal_work>;
 
@@ -97,34 +107,8 @@ class baseband_chain_pipe {
     cuda_check(cudaSetDevice(q.device()), "cudaSetDevice");
     const bool idle_tick = (in_work.count == 0 && !in_work.baseband_data.baseband_ptr);
     out_type out;
-    if (ring_depth <= 1) {
-      if (!idle_tick) run_synchronously(in_work, out);
-      return std::optional{std::move(out)};
-    }
-    if (!idle_tick) {
-      holder.refresh();
-      const int ticket = srtb_b200_submit_block(q.ctx(), &holder.cfg, in_work.baseband_data.baseband_ptr.get(),
-                                                in_work.baseband_data.baseband_input_bytes);
-      q.check(ticket);
-      pending.push_back({ticket, std::move(in_work)});
-    }
-    while (!pending.empty() && (idle_tick || (int)pending.size() >= ring_depth)) {
-      pending_block p = std::move(pending.front());
-      pending.pop_front();
-      srtb_b200_detect_result res[4];
-      const int n = srtb_b200_collect_block(q.ctx(), p.ticket, res);
-      q.check(n);
-      bool hit = false;
-      for (int s = 0; s < n; s++)
-        for (int b = 0; b < res[s].n_boxcars; b++) hit = hit || res[s].signal_count[b] > 0;
-      if (hit) {
-        // the ring keeps result headers only (its work buffers belong to the next block by now): a candidate's time
-        // series and dynamic spectrum come from running that block once more (deterministic chain; hits are rare)
-        run_synchronously(p.work, out);
-      } else {
-        append_headers(p.work, res, n, out);
-      }
-    }
+    if (!idle_tick) submit(std::move(in_work));
+    while (!pending.empty() && (idle_tick || (int)pending.size() >= ring_depth)) collect_front(out);
     return std::optional{std::move(out)};
   }
 
@@ -132,63 +116,54 @@ class baseband_chain_pipe {
   int ring_depth = 1;
 
  protected:
-  void append_headers(const srtb::work::copy_to_device_work& in_work, const srtb_b200_detect_result* res, int n,
-                      out_type& out) {
-    const auto& cfg = holder.cfg;
-    const int streams = block_config_holder::stream_count(cfg.baseband_format);
-    const size_t Nc = cfg.baseband_input_count / 2;
-    const size_t C = std::min<size_t>(cfg.spectrum_channel_count, Nc), L = Nc / C;
-    for (int s = 0; s < n; s++) {
-      srtb::work::write_signal_work w;
-      w.copy_parameter_from(in_work);
-      w.data_stream_id = in_work.data_stream_id * static_cast<uint32_t>(streams) + static_cast<uint32_t>(s);
-      w.count = L;
-      w.batch_size = C;
-      w.zero_count = res[s].zero_count;
-      out.push_back(std::move(w));
-    }
-  }
-
-  void run_synchronously(const srtb::work::copy_to_device_work& in_work, out_type& out) {
+  void submit(srtb::work::copy_to_device_work in_work) {
     holder.refresh();
     const auto& cfg = holder.cfg;
-    const int streams = block_config_holder::stream_count(cfg.baseband_format);
-    const size_t Nc = cfg.baseband_input_count / 2;
-    const size_t C = std::min<size_t>(cfg.spectrum_channel_count, Nc), L = Nc / C;
-    auto h_series = srtb::host_allocator.allocate_shared<srtb::real>((size_t)streams * SRTB_B200_MAX_BOXCARS * L);
+    pending_block p;
+    p.streams = block_config_holder::stream_count(cfg.baseband_format);
+    const size_t N = cfg.baseband_input_count, Nc = N / 2;
+    p.C = std::min<size_t>(cfg.spectrum_channel_count, Nc);
+    p.L = p.C ? Nc / p.C : 0;
+    srtb_b200_block_outputs outputs{};
+    for (int s = 0; s < p.streams; s++) {
+      p.d_spectrum.push_back(srtb::device_allocator.allocate_shared<srtb::complex<srtb::real>>(Nc + 1));
+      outputs.d_spectrum[s] = reinterpret_cast<float*>(p.d_spectrum.back().get());
+    }
+    p.h_series = srtb::host_allocator.allocate_shared<srtb::real>((size_t)p.streams * SRTB_B200_MAX_BOXCARS * p.L);
+    outputs.h_series = p.h_series.get();
+    p.ticket = srtb_b200_submit_block_ex(q.ctx(), &cfg, in_work.baseband_data.baseband_ptr.get(),
+                                         in_work.baseband_data.baseband_input_bytes, /*on_device=*/0, &outputs);
+    q.check(p.ticket);
+    p.work = std::move(in_work);
+    pending.push_back(std::move(p));
+  }
+
+  void collect_front(out_type& out) {
+    pending_block p = std::move(pending.front());
+    pending.pop_front();
     srtb_b200_detect_result res[4];
-    const int n = srtb_b200_process_block(q.ctx(), &cfg, in_work.baseband_data.baseband_ptr.get(),
-                                          in_work.baseband_data.baseband_input_bytes, res, h_series.get(), 0);
+    const int n = srtb_b200_collect_block_ex(q.ctx(), p.ticket, res, nullptr, nullptr);
     q.check(n);
     for (int s = 0; s < n; s++) {
       srtb::work::write_signal_work w;
-      w.copy_parameter_from(in_work);
-      w.data_stream_id = in_work.data_stream_id * static_cast<uint32_t>(streams) + static_cast<uint32_t>(s);
-      w.count = L;
-      w.batch_size = C;
+      w.copy_parameter_from(p.work);
+      w.data_stream_id = p.work.data_stream_id * static_cast<uint32_t>(p.streams) + static_cast<uint32_t>(s);
+      w.count = p.L;
+      w.batch_size = p.C;
       w.zero_count = res[s].zero_count;
-      srtb::real* base = h_series.get() + (size_t)s * SRTB_B200_MAX_BOXCARS * L;
+      w.ptr = p.d_spectrum[s];
+      srtb::real* base = p.h_series.get() + (size_t)s * SRTB_B200_MAX_BOXCARS * p.L;
       for (int b = 0; b < res[s].n_boxcars; b++) {
         if (res[s].signal_count[b] == 0) continue;
         srtb::work::time_series_holder h;
         h.time_series_length = res[s].series_length[b];
         h.boxcar_length = res[s].boxcar_length[b];
         h.signal_count = res[s].signal_count[b];
-        h.h_time_series = std::shared_ptr<srtb::real>(h_series, base + (size_t)b * L);
+        h.h_time_series = std::shared_ptr<srtb::real>(p.h_series, base + (size_t)b * p.L);
         w.time_series.push_back(h);
-      }
-      // the dynamic spectrum lives in context scratch and is overwritten by the next block: keep a copy for the
-      // sink when it will be looked at (a candidate, or always if the caller wants every spectrum)
-      if (!w.time_series.empty() || keep_every_spectrum) {
-        auto d_spec = srtb::device_allocator.allocate_shared<srtb::complex<srtb::real>>(C * L);
-        cuda_check(cudaMemcpyAsync(d_spec.get(), srtb_b200_block_spectrum(q.ctx(), s),
-                                   C * L * sizeof(srtb::complex<srtb::real>), cudaMemcpyDeviceToDevice, q.stream()),
-                   "spectrum copy");
-        w.ptr = d_spec;
       }
       out.push_back(std::move(w));
     }
-    q.wait();
   }
 };
 

@@ -197,13 +197,34 @@ int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b200_block_c
  * dedicated copy stream while the previous block computes and returns a ticket (>= 0);
  * collect waits for that block and fills h_results[stream] (returns the stream count).
  * Up to SRTB_B200_RING_SLOTS blocks may be in flight; h_baseband must stay valid (and should be
- * pinned) until its block is collected. Time series are not returned on this path. */
+ * pinned) until its block is collected.
+ *
+ * What a block leaves behind is what signal_detect_pipe_2 attaches to its write_signal_work
+ * (pipeline/signal_detect_pipe.hpp:347-366,405-423,431-441; work.hpp:240-260):
+ *   - the dynamic spectrum [C][L] of every stream, in that stream's working buffer (the reference forwards d_in);
+ *   - the host copy of every boxcar series whose count_signal is positive, written straight from the detector
+ *     kernel into pinned host memory at [stream][boxcar index][L] (nothing crosses PCIe for a negative block).
+ * srtb_b200_block_outputs lets the caller own those buffers (a pipe hands them to its work item, zero copy);
+ * members left NULL use buffers owned by the ring slot, valid until that slot is submitted again
+ * (SRTB_B200_RING_SLOTS - 1 further submissions). */
 #define SRTB_B200_RING_SLOTS 3
+typedef struct {
+  float* d_spectrum[4]; /* per stream: device buffer of baseband_input_count + 2 floats, 16-byte aligned        */
+  float* h_series;      /* pinned (cudaMallocHost / cudaHostRegister) host buffer,
+                           [streams][SRTB_B200_MAX_BOXCARS][L] floats; only positive series are written          */
+} srtb_b200_block_outputs;
 int srtb_b200_submit_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
                            const void* h_baseband, size_t baseband_bytes);
 int srtb_b200_submit_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
                                   const void* d_baseband, size_t baseband_bytes); /* input already in HBM */
+int srtb_b200_submit_block_ex(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, const void* baseband,
+                              size_t baseband_bytes, int on_device, const srtb_b200_block_outputs* outputs /* or NULL */);
 int srtb_b200_collect_block(srtb_b200_ctx* ctx, int ticket, srtb_b200_detect_result* h_results);
+/* h_series (optional): receives the block's series buffer; d_spectrum (optional): const void*[4], the streams' spectra */
+int srtb_b200_collect_block_ex(srtb_b200_ctx* ctx, int ticket, srtb_b200_detect_result* h_results,
+                               const float** h_series, const void** d_spectrum);
+/* test hook: preset the ring's submission counter (ticket wrap-around test); the ring must be empty */
+int srtb_b200_debug_set_submit_count(srtb_b200_ctx* ctx, uint64_t value);
 /* device pointer of stream s's dynamic spectrum after process_block (valid until next call) */
 const void* srtb_b200_block_spectrum(const srtb_b200_ctx* ctx, int stream);
 

@@ -870,10 +870,14 @@ __global__ void __launch_bounds__(1024) detect_scan_kernel(float* __restrict__ t
 }
 
 // K19 + K21: one CTA per boxcar length 2^blockIdx.x: series, variance, threshold, count.
+// host_out (optional): pinned host memory [MAX_BOXCARS][row_stride] that receives, straight from this kernel, the
+// series of every boxcar with a positive count — the reference attaches the host copy of a series to the work only
+// when count_signal is positive (signal_detect_pipe.hpp:347-366,405-423); negative blocks cost no PCIe traffic.
 __global__ void __launch_bounds__(1024) detect_boxcar_kernel(float* __restrict__ series, size_t row_stride,
                                                              const float* __restrict__ acc,
                                                              size_t ts_count, float snr,
-                                                             detect_dev_result* __restrict__ res) {
+                                                             detect_dev_result* __restrict__ res,
+                                                             float* __restrict__ host_out) {
   __shared__ double smd[32];
   __shared__ float s_thr;
   const int nb = blockIdx.x;
@@ -908,6 +912,16 @@ __global__ void __launch_bounds__(1024) detect_boxcar_kernel(float* __restrict__
     if (v[i] > thr) cnt += 1.0;
   cnt = block_sum<double>(cnt, smd);
   if (tid == 0) res->signal_count[nb] = (unsigned long long)cnt;
+  if (host_out) {
+    __shared__ int s_hit;
+    if (tid == 0) s_hit = cnt > 0.0 ? 1 : 0;
+    __syncthreads();
+    if (s_hit) {
+      float* h = host_out + (size_t)nb * row_stride;
+      for (size_t i = tid; i < n; i += nt) h[i] = v[i];
+      __threadfence_system();
+    }
+  }
 }
 
 }  // namespace srtb_b200

@@ -17,6 +17,7 @@
 
 #include "../../include/srtb_b200.h"
 #include "fft_engine.cuh"
+#include "fft_bigrow.cuh"
 #include "ops_kernels.cuh"
 
 using namespace srtb_b200;
@@ -34,6 +35,7 @@ struct srtb_b200_ctx {
   // FFT
   float2* tw[13] = {nullptr};
   std::map<int, float2*> bigtw;  // log2(n_i) -> [3 << q]
+  float2* bigrow_tab[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [logl - 13][forward] whole-row kernel tables
   void* fft_scratch = nullptr;
   size_t fft_scratch_bytes = 0;
   // s1
@@ -58,6 +60,14 @@ struct srtb_b200_ctx {
   int slot_streams[SRTB_B200_RING_SLOTS] = {0};
   size_t slot_L[SRTB_B200_RING_SLOTS] = {0};
   bool slot_busy[SRTB_B200_RING_SLOTS] = {false};
+  int slot_ticket[SRTB_B200_RING_SLOTS] = {0};
+  // per-slot outputs: ctx-owned working buffers / pinned series unless the caller supplied its own (submit_block_ex)
+  float* slot_stream_buf[SRTB_B200_RING_SLOTS][4] = {};
+  size_t slot_stream_elems[SRTB_B200_RING_SLOTS] = {0};
+  float* slot_h_series[SRTB_B200_RING_SLOTS] = {nullptr};
+  size_t slot_h_series_elems[SRTB_B200_RING_SLOTS] = {0};
+  float* slot_out_spectrum[SRTB_B200_RING_SLOTS][4] = {};
+  float* slot_out_series[SRTB_B200_RING_SLOTS] = {nullptr};
   uint64_t submit_count = 0;
   // DM sweep working copy of the spectrum, per-trial result headers
   void* sweep_buf = nullptr;
@@ -69,6 +79,8 @@ struct srtb_b200_ctx {
   cudaEvent_t stat_ev[SRTB_B200_STAGE_COUNT][2] = {};
   double stat_bytes[SRTB_B200_STAGE_COUNT] = {};
   bool stat_have[SRTB_B200_STAGE_COUNT] = {};
+  // ring path: pinned host destination [streams][MAX_BOXCARS][L] of the current block's positive series (else null)
+  float* host_series_dst = nullptr;
   // process_block
   void* d_baseband = nullptr;
   size_t d_baseband_bytes = 0;
@@ -169,7 +181,7 @@ int srtb_b200_ctx_create(int device, void* cuda_stream, srtb_b200_ctx** out) {
   if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_res, sizeof(detect_dev_result) * 4 * (1 + SRTB_B200_RING_SLOTS));
   if (e != cudaSuccess) {
     const std::string msg = std::string("ctx_create: ") + cudaGetErrorString(e);
-    delete ctx;
+    srtb_b200_ctx_destroy(ctx);  // frees whatever was allocated before the failure
     return fail(nullptr, SRTB_B200_E_CUDA, msg);
   }
   *out = ctx;
@@ -183,6 +195,8 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   for (auto& p : ctx->tw)
     if (p) cudaFree(p);
   for (auto& kv : ctx->bigtw) cudaFree(kv.second);
+  for (auto& a : ctx->bigrow_tab)
+    for (auto& p : a) cudaFree(p);
   cudaFree(ctx->fft_scratch);
   cudaFree(ctx->partial);
   cudaFree(ctx->ticket);
@@ -197,6 +211,8 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   cudaFree(ctx->sweep_res);
   for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) {
     cudaFree(ctx->slot_baseband[i]);
+    for (auto& p : ctx->slot_stream_buf[i]) cudaFree(p);
+    if (ctx->slot_h_series[i]) cudaFreeHost(ctx->slot_h_series[i]);
     if (ctx->slot_h2d[i]) cudaEventDestroy(ctx->slot_h2d[i]);
     if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
   }
@@ -294,6 +310,17 @@ extern "C" int srtb_b200_unpack(srtb_b200_ctx* ctx, const void* d_in, size_t in_
     return fail(ctx, SRTB_B200_E_INVALID, "unpack: in_bytes too small for out_count");
   for (int s = 0; s < streams; s++)
     if (!d_out[s]) return fail(ctx, SRTB_B200_E_INVALID, "unpack: null output stream");
+  if (streams > 1) {
+    // the multi-stream kernels move 8/16-byte words: the board formats are int8 only, whole 4-sample words, and
+    // every buffer 16-byte aligned (the single-stream path has a scalar fall-back, these do not)
+    if ((format == SRTB_B200_FORMAT_GZNUPSR_A1_2 || format == SRTB_B200_FORMAT_GZNUPSR_A1_4) && abits != 8)
+      return fail(ctx, SRTB_B200_E_UNSUPPORTED, "gznupsr_a1 requires 8-bit samples, got baseband_input_bits = " + std::to_string(bits));
+    if ((format == SRTB_B200_FORMAT_GZNUPSR_A1_2 || format == SRTB_B200_FORMAT_GZNUPSR_A1_4) && (out_count & 3))
+      return fail(ctx, SRTB_B200_E_SIZE, "gznupsr_a1: samples per stream must be a multiple of 4, got " + std::to_string(out_count));
+    bool aligned = (reinterpret_cast<uintptr_t>(d_in) & 15u) == 0;
+    for (int s = 0; s < streams; s++) aligned = aligned && (reinterpret_cast<uintptr_t>(d_out[s]) & 15u) == 0;
+    if (!aligned) return fail(ctx, SRTB_B200_E_INVALID, "unpack: multi-stream formats need 16-byte aligned input and output buffers");
+  }
   CK(cudaSetDevice(ctx->device));
   switch (format) {
     case SRTB_B200_FORMAT_SIMPLE:
@@ -809,6 +836,75 @@ static int dispatch_trans(srtb_b200_ctx* ctx, int logl, const float2* in, float2
   return fail(ctx, SRTB_B200_E_SIZE, "fft: unsupported last-pass length 2^" + std::to_string(logl));
 }
 
+// ---- whole-row waterfall kernel (fft_bigrow.cuh): rows of 2^13 / 2^14 points held in one CTA's shared memory.
+// SRTB_B200_BIGROW=0 keeps the two-sweep column + transposing plan for these lengths (A/B measurements).
+static bool use_bigrow() {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_BIGROW");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <int LOGL>
+static int get_bigrow_tables(srtb_b200_ctx* ctx, bool fwd, const float2** out) {
+  using C = bigrow<LOGL>;
+  float2*& d = ctx->bigrow_tab[LOGL - 13][fwd ? 1 : 0];
+  if (!d) {
+    std::vector<float2> h(C::TABN);
+    const double sgn = fwd ? -1.0 : 1.0;
+    auto w = [&](size_t n, size_t e) {
+      const double a = sgn * 2.0 * M_PI * (double)(e % n) / (double)n;
+      return make_float2((float)std::cos(a), (float)std::sin(a));
+    };
+    for (int j = 0; j < C::B1; j++) h[j] = w(C::L, j);
+    for (int i = 1; i < 16; i++)
+      for (int j = 0; j < C::B2; j++) h[C::B1 + (i - 1) * C::B2 + j] = w(C::B1, (size_t)i * j);
+    for (int i = 1; i < 16; i++)
+      for (int j = 0; j < C::R3; j++) h[C::B1 + 15 * C::B2 + (i - 1) * C::R3 + j] = w(C::B2, (size_t)i * j);
+    CK(cudaMalloc(&d, h.size() * sizeof(float2)));
+    CK(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  *out = d;
+  return 0;
+}
+
+// sk != nullptr: SK + column sums in the epilogue (sk->partial is filled in here); chirp != nullptr: s1 + chirp on load
+template <int LOGL, bool FWD>
+static int launch_bigrow(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t nrows, row_sk_params* sk,
+                         const row_chirp_params* chirp, size_t* chunks_out) {
+  using C = bigrow<LOGL>;
+  if (nrows >= ((size_t)1 << 31)) return fail(ctx, SRTB_B200_E_SIZE, "fft: too many rows");
+  const float2* tabs = nullptr;
+  if (int rc = get_bigrow_tables<LOGL>(ctx, FWD, &tabs)) return rc;
+  unsigned grid = 1;
+  auto go = [&](auto kern, bool with_sk) -> int {
+    const size_t smem = C::bytes(with_sk);
+    if (int rc = persistent_grid(ctx, kern, C::NT, smem, smem, nrows, &grid)) return rc;
+    row_sk_params p{};
+    if (with_sk) {
+      size_t have = ctx->colsum_partial_elems * sizeof(float);
+      if (int rc = ensure(ctx, reinterpret_cast<void**>(&ctx->colsum_partial), &have, (size_t)grid * sk->ts_count * sizeof(float)))
+        return rc;
+      ctx->colsum_partial_elems = have / sizeof(float);
+      sk->partial = ctx->colsum_partial;
+      p = *sk;
+    }
+    kern<<<grid, C::NT, smem, ctx->stream>>>(in, out, (unsigned)nrows, tabs, p, chirp ? *chirp : row_chirp_params{});
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (chunks_out) *chunks_out = grid;
+    return 0;
+  };
+  if constexpr (!FWD) {
+    if (sk && chirp) return go(fft_bigrow_kernel<LOGL, false, true, true>, true);
+    if (sk) return go(fft_bigrow_kernel<LOGL, false, true, false>, true);
+  }
+  if (sk || chirp) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "fft: fused epilogue exists for the backward transform only");
+  return go(fft_bigrow_kernel<LOGL, FWD, false, false>, false);
+}
+
 // L = 2 or 4: one thread per row
 template <bool FWD>
 __global__ void tiny_fft_kernel(float2* x, int logl, size_t nrows) {
@@ -840,6 +936,11 @@ static int fft_c2c_impl(srtb_b200_ctx* ctx, float2* x, size_t n, size_t batch) {
     return 0;
   }
   if (q <= 12) return dispatch_row<FWD>(ctx, q, x, x, batch);
+  if ((q == 13 || q == 14) && use_bigrow() && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+    // one sweep: the whole row in shared memory (in place: a CTA reads its row completely before it stores it)
+    return q == 13 ? launch_bigrow<13, FWD>(ctx, x, x, batch, nullptr, nullptr, nullptr)
+                   : launch_bigrow<14, FWD>(ctx, x, x, batch, nullptr, nullptr, nullptr);
+  }
   if (q > 30) return fail(ctx, SRTB_B200_E_SIZE, "fft: length above 2^30 not supported");
   if (batch * n > ((size_t)1 << 32) * 4)
     return fail(ctx, SRTB_B200_E_SIZE, "fft: batch * length too large");
@@ -1286,6 +1387,7 @@ static int detect_prepare(srtb_b200_ctx* ctx, int slot, size_t time_count, size_
 // column-sum reduction over `chunks` partial rows, zero count, scan, boxcar ladder
 static int detect_tail(srtb_b200_ctx* ctx, int slot, const float2* x, size_t time_count, size_t chan_count,
                        size_t ts_count, size_t chunks, float snr, float chan_thr, size_t max_boxcar) {
+  float* const host_series = ctx->host_series_dst ? ctx->host_series_dst + (size_t)slot * SRTB_B200_MAX_BOXCARS * time_count : nullptr;
   colsum_final_kernel<<<(unsigned)((ts_count + 31) / 32), 1024, 0, ctx->stream>>>(
       ctx->colsum_partial, ts_count, chunks, ctx->series[slot], x, time_count, chan_count, ctx->d_res + slot);
   ctx->launches++;
@@ -1298,7 +1400,7 @@ static int detect_tail(srtb_b200_ctx* ctx, int slot, const float2* x, size_t tim
   unsigned max_nb = 1;
   for (size_t b = 2; b <= max_boxcar && b < ts_count && max_nb < SRTB_B200_MAX_BOXCARS; b *= 2) max_nb++;
   detect_boxcar_kernel<<<max_nb, 1024, 0, ctx->stream>>>(ctx->series[slot], time_count, ctx->acc, ts_count, snr,
-                                                         ctx->d_res + slot);
+                                                         ctx->d_res + slot, host_series);
   ctx->launches++;
   CK(cudaGetLastError());
   ctx->slot_time_count[slot] = time_count;
@@ -1336,7 +1438,9 @@ static bool use_fused_chirp() {
   return on;
 }
 static bool chirp_fusable(size_t time_count) {
-  return use_fused_chirp() && use_row16() && (time_count == 1024 || time_count == 2048 || time_count == 4096);
+  if (!use_fused_chirp()) return false;
+  if (time_count == 8192 || time_count == 16384) return use_bigrow();
+  return use_row16() && (time_count == 1024 || time_count == 2048 || time_count == 4096);
 }
 
 template <int LOGL>
@@ -1401,6 +1505,34 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
   const float lo_ = lo * ((M_ - 1) / (M_ + 1)) + 1, hi_ = hi * ((M_ - 1) / (M_ + 1)) + 1;
   size_t chunks = 0;
   int rc = 0;
+  if (time_count == 8192 || time_count == 16384) {
+    row_sk_params p{lo_, hi_, nullptr, (unsigned)ts_count};
+    row_chirp_params cpv{};
+    if (chirp) {
+      cpv = *chirp;
+      // 1/f of a bin comes from Newton steps off the reciprocal of the bin B1 = L/16 below: n steps leave a relative
+      // error of (B1 df / f)^(2^n), i.e. |k| times that in cycles of phase. Keep it below 1e-9 cycles (fp32 resolves
+      // 6e-8); widely spaced bins (short test blocks) take more steps or the exact reciprocal of every bin.
+      const double fa = std::min(std::fabs(cpv.f_min), std::fabs(cpv.f_c));
+      const double delta = (double)(time_count / 16) * std::fabs(cpv.df) / fa;
+      const double q = (cpv.f_c - cpv.f_min) * cpv.inv_fc;
+      const double kmax = std::max(1.0, std::fabs(cpv.ddm) / fa * q * q);
+      cpv.newton = 0;
+      double err = delta;
+      for (int n = 1; n <= 3; n++) {
+        err *= err;
+        if (err * kmax < 1e-9) {
+          cpv.newton = n;
+          break;
+        }
+      }
+    }
+    const float2* s_ = src ? src : x;
+    rc = (time_count == 8192) ? launch_bigrow<13, false>(ctx, s_, x, chan_count, &p, chirp ? &cpv : nullptr, &chunks)
+                              : launch_bigrow<14, false>(ctx, s_, x, chan_count, &p, chirp ? &cpv : nullptr, &chunks);
+    if (rc) return rc;
+    return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
+  }
   switch (ilog2(time_count)) {
     case 9: rc = watfft_sk_launch<9>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp, src); break;
     case 10: rc = watfft_sk_launch<10>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp, src); break;
@@ -1415,6 +1547,10 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
 // when a row fits the per-thread register tile (L = 512 .. 4096)
 static bool sk_detect_fusable(size_t time_count) {
   return time_count == 512 || time_count == 1024 || time_count == 2048 || time_count == 4096;
+}
+// waterfall FFT + SK + column sums in one kernel (no chirp): the row kernels above plus the whole-row kernel
+static bool watfft_sk_fusable(size_t time_count) {
+  return sk_detect_fusable(time_count) || ((time_count == 8192 || time_count == 16384) && use_bigrow());
 }
 static int sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_t time_count, size_t chan_count,
                            size_t time_reserved_count, float sk_threshold, float snr, float chan_thr,
@@ -1495,26 +1631,40 @@ static int format_streams(int format) {
 
 // enqueue every stage of one block on ctx->stream (no host sync); results land in
 // ctx->h_res[res_base .. res_base + streams) once the stream reaches the final D2H copy
+// (re)allocate one set of per-stream working buffers of N + 2 floats (the in-place buffer of the reference's works,
+// unpack_pipe.hpp:65-67) owned by the ctx
+static int ensure_stream_bufs(srtb_b200_ctx* ctx, float* (&bufs)[4], size_t* elems, size_t N, int streams) {
+  if (*elems < N + 2) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto& p : bufs) {
+      if (p) CK(cudaFree(p));
+      p = nullptr;
+    }
+    *elems = 0;
+  }
+  for (int s = 0; s < streams; s++)
+    if (!bufs[s]) {
+      cudaError_t e = cudaMalloc(&bufs[s], (N + 2) * sizeof(float));
+      if (e != cudaSuccess) return fail(ctx, SRTB_B200_E_NOMEM, "process_block: stream buffer alloc failed");
+    }
+  *elems = N + 2;
+  return 0;
+}
+
+// bufs[s]: working buffer of stream s (N + 2 floats, 16-byte aligned for the fused routes) — holds the dynamic
+// spectrum [C][L] when the block is done. host_series (optional): pinned host memory that receives positive series.
 static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, const void* d_baseband,
-                         size_t baseband_bytes, int res_base, int* streams_out, size_t* L_out) {
+                         size_t baseband_bytes, int res_base, int* streams_out, size_t* L_out, float* const* bufs,
+                         float* host_series) {
   const int streams = format_streams(cfg->baseband_format);
   if (!streams) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "process_block: unknown format");
   const size_t N = cfg->baseband_input_count;
   if (N < 2 || !is_pow2(N)) return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(N));
-  if (ctx->stream_buf_elems < N + 2) {
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (auto& p : ctx->stream_buf) {
-      if (p) CK(cudaFree(p));
-      p = nullptr;
-    }
-    ctx->stream_buf_elems = 0;
-  }
-  for (int s = 0; s < streams; s++)
-    if (!ctx->stream_buf[s]) {
-      cudaError_t e = cudaMalloc(&ctx->stream_buf[s], (N + 2) * sizeof(float));
-      if (e != cudaSuccess) return fail(ctx, SRTB_B200_E_NOMEM, "process_block: stream buffer alloc failed");
-    }
-  ctx->stream_buf_elems = N + 2;
+  struct series_dst_scope {  // detect_tail reads ctx->host_series_dst; it is only meaningful inside this call
+    srtb_b200_ctx* c;
+    ~series_dst_scope() { c->host_series_dst = nullptr; }
+  } series_scope_{ctx};
+  ctx->host_series_dst = host_series;
   // unpack: fused into the first FFT pass when the samples are 8-bit and every complex point of a
   // stream is one fixed-size byte group (simple, "1 1 2 2", "1 2 1 2"); otherwise the unpack kernel
   raw_source raw[4];
@@ -1542,7 +1692,7 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
     if (unpacked) return 0;
     unpacked = true;
     return srtb_b200_unpack(ctx, d_baseband, baseband_bytes, cfg->baseband_input_bits, cfg->baseband_format,
-                            cfg->window, ctx->stream_buf, N);
+                            cfg->window, bufs, N);
   };
   if (!fuse_unpack)
     if (int rc = ensure_unpacked()) return rc;
@@ -1568,12 +1718,16 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
                                                     cfg->baseband_reserve_sample) /
                           batch;
   for (int s = 0; s < streams; s++) {
-    float* buf = ctx->stream_buf[s];
+    float* buf = bufs[s];
     {
       int rc = SRTB_B200_E_UNSUPPORTED;
       if (fuse_unpack && !unpacked) rc = fft_r2c_with_power_mean(ctx, buf, N, &raw[s], nullptr);
       if (rc == SRTB_B200_E_UNSUPPORTED) {
-        // this size/alignment cannot take the fused route: unpack all streams once, then the plain R2C
+        // this size/alignment cannot take the fused route: unpack all streams once, then the plain R2C. The route is a
+        // property of the block (same size and base pointer for every stream), so it can only change on stream 0;
+        // later it would overwrite finished streams with their unpacked input
+        if (fuse_unpack && !unpacked && s > 0)
+          return fail(ctx, SRTB_B200_E_UNSUPPORTED, "process_block: fused unpack refused stream " + std::to_string(s) + " after accepting stream 0");
         if (int rc2 = ensure_unpacked()) return rc2;
         rc = fft_r2c_with_power_mean(ctx, buf, N);
       }
@@ -1599,7 +1753,7 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
                                          cfg->mitigate_rfi_average_method_threshold, coef, bins, f_min, f_c, df, cfg->dm,
                                          /*mean_ready=*/true))
       return rc;
-    if (sk_detect_fusable(L) && aligned) {
+    if (watfft_sk_fusable(L) && aligned) {
       // waterfall FFT + SK + partial column sums in one kernel, then the small detector tail
       if (int rc = watfft_sk_detect_fused(ctx, s, reinterpret_cast<float2*>(buf), L, batch, reserved,
                                           cfg->mitigate_rfi_spectral_kurtosis_threshold,
@@ -1638,7 +1792,11 @@ extern "C" int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b20
   CK(cudaSetDevice(ctx->device));
   int streams = 0;
   size_t L = 0;
-  if (int rc = block_enqueue(ctx, cfg, d_baseband, baseband_bytes, 0, &streams, &L)) return rc;
+  if (format_streams(cfg->baseband_format) && cfg->baseband_input_count >= 2)
+    if (int rc = ensure_stream_bufs(ctx, ctx->stream_buf, &ctx->stream_buf_elems, cfg->baseband_input_count,
+                                    format_streams(cfg->baseband_format)))
+      return rc;
+  if (int rc = block_enqueue(ctx, cfg, d_baseband, baseband_bytes, 0, &streams, &L, ctx->stream_buf, nullptr)) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   for (int s = 0; s < streams; s++)
     if (int rc = detect_collect(ctx, s, h_results + s, h_series ? h_series + (size_t)s * SRTB_B200_MAX_BOXCARS * L : nullptr, copy_all))
@@ -1676,20 +1834,7 @@ extern "C" int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b
     CK(cudaMemcpyAsync(ctx->d_baseband, baseband, baseband_bytes, cudaMemcpyHostToDevice, ctx->stream));
     d_baseband = ctx->d_baseband;
   }
-  if (ctx->stream_buf_elems < N + 2) {
-    CK(cudaStreamSynchronize(ctx->stream));
-    for (auto& p : ctx->stream_buf) {
-      if (p) CK(cudaFree(p));
-      p = nullptr;
-    }
-    ctx->stream_buf_elems = 0;
-  }
-  for (int s = 0; s < streams; s++)
-    if (!ctx->stream_buf[s]) {
-      cudaError_t e = cudaMalloc(&ctx->stream_buf[s], (N + 2) * sizeof(float));
-      if (e != cudaSuccess) return fail(ctx, SRTB_B200_E_NOMEM, "dm_sweep: stream buffer alloc failed");
-    }
-  ctx->stream_buf_elems = N + 2;
+  if (int rc = ensure_stream_bufs(ctx, ctx->stream_buf, &ctx->stream_buf_elems, N, streams)) return rc;
   const size_t Nc = N / 2;
   const size_t batch = std::min<size_t>(cfg->spectrum_channel_count, Nc);
   if (batch == 0 || !is_pow2(batch)) return fail(ctx, SRTB_B200_E_SIZE, "spectrum_channel_count must be a power of 2");
@@ -1738,7 +1883,7 @@ extern "C" int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b
         if (int rc = rfi_s1_dedisperse_fused(ctx, W, Nc, cfg->mitigate_rfi_average_method_threshold, coef, bins, f_min,
                                              f_c, df, h_dms[j], /*mean_ready=*/true, reinterpret_cast<const float2*>(buf)))
           return rc;
-        if (sk_detect_fusable(L)) {
+        if (watfft_sk_fusable(L)) {
           if (int rc = watfft_sk_detect_fused(ctx, 0, W, L, batch, reserved, cfg->mitigate_rfi_spectral_kurtosis_threshold,
                                               cfg->signal_detect_signal_noise_threshold,
                                               cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length))
@@ -1761,67 +1906,118 @@ extern "C" int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b
   return streams;
 }
 
+// tickets wrap at a multiple of the slot count, so ticket % SRTB_B200_RING_SLOTS is always the slot that was used
+static inline int ring_ticket(uint64_t submit_count) {
+  return (int)(submit_count % ((uint64_t)SRTB_B200_RING_SLOTS << 28));
+}
+extern "C" int srtb_b200_debug_set_submit_count(srtb_b200_ctx* ctx, uint64_t value) {
+  if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "debug_set_submit_count: ctx is null");
+  for (int i = 0; i < SRTB_B200_RING_SLOTS; i++)
+    if (ctx->slot_busy[i]) return fail(ctx, SRTB_B200_E_INVALID, "debug_set_submit_count: ring not empty");
+  ctx->submit_count = value;
+  return 0;
+}
+
 // ---- pipelined ingest: the pinned-host ring of SURVEY section 8e -------------------------------
 // submit() copies block k on a dedicated copy stream while block k-1 computes; collect() waits for
 // one block's results. Up to SRTB_B200_RING_SLOTS blocks may be in flight.
-extern "C" int srtb_b200_submit_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
-                                      const void* h_baseband, size_t baseband_bytes) {
-  if (!ctx || !cfg || !h_baseband) return fail(ctx, SRTB_B200_E_INVALID, "submit_block: null argument");
+extern "C" int srtb_b200_submit_block_ex(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, const void* baseband,
+                                         size_t baseband_bytes, int on_device, const srtb_b200_block_outputs* outputs) {
+  if (!ctx || !cfg || !baseband) return fail(ctx, SRTB_B200_E_INVALID, "submit_block: null argument");
   CK(cudaSetDevice(ctx->device));
   const int slot = (int)(ctx->submit_count % SRTB_B200_RING_SLOTS);
   if (ctx->slot_busy[slot]) return fail(ctx, SRTB_B200_E_INVALID, "submit_block: ring full, collect a block first");
-  if (!ctx->copy_stream) {
-    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) {
-      CK(cudaEventCreateWithFlags(&ctx->slot_h2d[i], cudaEventDisableTiming));
+  const int streams = format_streams(cfg->baseband_format);
+  if (!streams) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "process_block: unknown format");
+  const size_t N = cfg->baseband_input_count;
+  if (N < 2 || !is_pow2(N)) return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(N));
+  if (!ctx->slot_done[slot])
+    for (int i = 0; i < SRTB_B200_RING_SLOTS; i++)
       if (!ctx->slot_done[i]) CK(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
+  // outputs: the caller's buffers (the work's own buffer, as in the reference) or this slot's ctx-owned ones
+  float* bufs[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool user_spec = outputs && outputs->d_spectrum[0];
+  if (user_spec) {
+    for (int s = 0; s < streams; s++) {
+      if (!outputs->d_spectrum[s]) return fail(ctx, SRTB_B200_E_INVALID, "submit_block: d_spectrum given for some streams only");
+      bufs[s] = outputs->d_spectrum[s];
     }
+  } else {
+    if (int rc = ensure_stream_bufs(ctx, ctx->slot_stream_buf[slot], &ctx->slot_stream_elems[slot], N, streams)) return rc;
+    for (int s = 0; s < streams; s++) bufs[s] = ctx->slot_stream_buf[slot][s];
   }
-  if (int rc = ensure(ctx, &ctx->slot_baseband[slot], &ctx->slot_baseband_bytes[slot], baseband_bytes)) return rc;
-  CK(cudaMemcpyAsync(ctx->slot_baseband[slot], h_baseband, baseband_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-  CK(cudaEventRecord(ctx->slot_h2d[slot], ctx->copy_stream));
-  CK(cudaStreamWaitEvent(ctx->stream, ctx->slot_h2d[slot], 0));
-  if (int rc = block_enqueue(ctx, cfg, ctx->slot_baseband[slot], baseband_bytes, 4 * (1 + slot), &ctx->slot_streams[slot],
-                             &ctx->slot_L[slot]))
+  const size_t Nc = N / 2;
+  const size_t batch = std::min<size_t>(cfg->spectrum_channel_count ? cfg->spectrum_channel_count : 1, Nc);
+  const size_t L = Nc / batch;
+  float* h_series = outputs ? outputs->h_series : nullptr;
+  if (!h_series) {
+    const size_t need = (size_t)streams * SRTB_B200_MAX_BOXCARS * L;
+    if (ctx->slot_h_series_elems[slot] < need) {
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (ctx->slot_h_series[slot]) CK(cudaFreeHost(ctx->slot_h_series[slot]));
+      ctx->slot_h_series[slot] = nullptr;
+      ctx->slot_h_series_elems[slot] = 0;
+      if (cudaMallocHost(&ctx->slot_h_series[slot], need * sizeof(float)) != cudaSuccess)
+        return fail(ctx, SRTB_B200_E_NOMEM, "submit_block: pinned series buffer alloc failed");
+      ctx->slot_h_series_elems[slot] = need;
+    }
+    h_series = ctx->slot_h_series[slot];
+  }
+  const void* d_baseband = baseband;
+  if (!on_device) {
+    if (!ctx->copy_stream) {
+      CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) CK(cudaEventCreateWithFlags(&ctx->slot_h2d[i], cudaEventDisableTiming));
+    }
+    if (int rc = ensure(ctx, &ctx->slot_baseband[slot], &ctx->slot_baseband_bytes[slot], baseband_bytes)) return rc;
+    CK(cudaMemcpyAsync(ctx->slot_baseband[slot], baseband, baseband_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CK(cudaEventRecord(ctx->slot_h2d[slot], ctx->copy_stream));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->slot_h2d[slot], 0));
+    d_baseband = ctx->slot_baseband[slot];
+  }
+  if (int rc = block_enqueue(ctx, cfg, d_baseband, baseband_bytes, 4 * (1 + slot), &ctx->slot_streams[slot],
+                             &ctx->slot_L[slot], bufs, h_series))
     return rc;
   CK(cudaEventRecord(ctx->slot_done[slot], ctx->stream));
+  for (int s = 0; s < 4; s++) ctx->slot_out_spectrum[slot][s] = bufs[s];
+  ctx->slot_out_series[slot] = h_series;
   ctx->slot_busy[slot] = true;
-  const int ticket = (int)(ctx->submit_count & 0x3fffffff);
+  const int ticket = ring_ticket(ctx->submit_count);
+  ctx->slot_ticket[slot] = ticket;
   ctx->submit_count++;
   return ticket;
+}
+
+extern "C" int srtb_b200_submit_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
+                                      const void* h_baseband, size_t baseband_bytes) {
+  return srtb_b200_submit_block_ex(ctx, cfg, h_baseband, baseband_bytes, 0, nullptr);
 }
 
 // same ring, input already on the device (no copy): lets a device-resident producer keep the GPU fed
 extern "C" int srtb_b200_submit_block_device(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
                                              const void* d_baseband, size_t baseband_bytes) {
-  if (!ctx || !cfg || !d_baseband) return fail(ctx, SRTB_B200_E_INVALID, "submit_block_device: null argument");
-  CK(cudaSetDevice(ctx->device));
-  const int slot = (int)(ctx->submit_count % SRTB_B200_RING_SLOTS);
-  if (ctx->slot_busy[slot]) return fail(ctx, SRTB_B200_E_INVALID, "submit_block: ring full, collect a block first");
-  if (!ctx->slot_done[slot]) {
-    for (int i = 0; i < SRTB_B200_RING_SLOTS; i++)
-      if (!ctx->slot_done[i]) CK(cudaEventCreateWithFlags(&ctx->slot_done[i], cudaEventDisableTiming));
-  }
-  if (int rc = block_enqueue(ctx, cfg, d_baseband, baseband_bytes, 4 * (1 + slot), &ctx->slot_streams[slot],
-                             &ctx->slot_L[slot]))
-    return rc;
-  CK(cudaEventRecord(ctx->slot_done[slot], ctx->stream));
-  ctx->slot_busy[slot] = true;
-  const int ticket = (int)(ctx->submit_count & 0x3fffffff);
-  ctx->submit_count++;
-  return ticket;
+  return srtb_b200_submit_block_ex(ctx, cfg, d_baseband, baseband_bytes, 1, nullptr);
 }
 
-extern "C" int srtb_b200_collect_block(srtb_b200_ctx* ctx, int ticket, srtb_b200_detect_result* h_results) {
+extern "C" int srtb_b200_collect_block_ex(srtb_b200_ctx* ctx, int ticket, srtb_b200_detect_result* h_results,
+                                          const float** h_series, const void** d_spectrum) {
   if (!ctx || !h_results || ticket < 0) return fail(ctx, SRTB_B200_E_INVALID, "collect_block: bad argument");
   const int slot = ticket % SRTB_B200_RING_SLOTS;
-  if (!ctx->slot_busy[slot]) return fail(ctx, SRTB_B200_E_INVALID, "collect_block: nothing submitted under this ticket");
+  if (!ctx->slot_busy[slot] || ctx->slot_ticket[slot] != ticket)
+    return fail(ctx, SRTB_B200_E_INVALID, "collect_block: nothing submitted under this ticket");
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventSynchronize(ctx->slot_done[slot]));
   const int streams = ctx->slot_streams[slot];
   std::memcpy(h_results, ctx->h_res + 4 * (1 + slot), sizeof(srtb_b200_detect_result) * streams);
+  if (h_series) *h_series = ctx->slot_out_series[slot];
+  if (d_spectrum)
+    for (int s = 0; s < 4; s++) d_spectrum[s] = s < streams ? ctx->slot_out_spectrum[slot][s] : nullptr;
   ctx->slot_busy[slot] = false;
   return streams;
+}
+
+extern "C" int srtb_b200_collect_block(srtb_b200_ctx* ctx, int ticket, srtb_b200_detect_result* h_results) {
+  return srtb_b200_collect_block_ex(ctx, ticket, h_results, nullptr, nullptr);
 }
 
 extern "C" const void* srtb_b200_block_spectrum(const srtb_b200_ctx* ctx, int stream) {

@@ -66,6 +66,11 @@ class BlockConfig(C.Structure):
     ]
 
 
+class BlockOutputs(C.Structure):
+    """srtb_b200_block_outputs: caller-owned outputs of a ring submission (members may be NULL)"""
+    _fields_ = [("d_spectrum", C.c_void_p * 4), ("h_series", C.c_void_p)]
+
+
 class SrtbError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"srtb_b200 error {code}: {message}")
@@ -104,6 +109,9 @@ SYMBOLS = {
     "srtb_b200_submit_block": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ]),
     "srtb_b200_submit_block_device": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ]),
     "srtb_b200_collect_block": (_I, [_P, _I, C.POINTER(DetectResult)]),
+    "srtb_b200_submit_block_ex": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, _I, C.POINTER(BlockOutputs)]),
+    "srtb_b200_collect_block_ex": (_I, [_P, _I, C.POINTER(DetectResult), C.POINTER(_P), C.POINTER(_P)]),
+    "srtb_b200_debug_set_submit_count": (_I, [_P, C.c_uint64]),
     "srtb_b200_block_spectrum": (_P, [_P, _I]),
 }
 
@@ -253,6 +261,28 @@ class Context:
         res = (DetectResult * 4)()
         n = self._ck(self.lib.srtb_b200_collect_block(self.h, ticket, res))
         return [res[i] for i in range(n)]
+
+    def submit_block_ex(self, cfg: BlockConfig, baseband, nbytes: int, on_device: bool = False, d_spectrum=None,
+                        h_series=None) -> int:
+        """ring submission with caller-owned outputs: d_spectrum = per-stream device buffers of N + 2 floats (the
+        dynamic spectrum stays there), h_series = pinned host buffer [streams][MAX_BOXCARS][L] for positive series"""
+        out = BlockOutputs()
+        for i, t in enumerate(d_spectrum or []):
+            out.d_spectrum[i] = _ptr(t)
+        out.h_series = _ptr(h_series)
+        return self._ck(self.lib.srtb_b200_submit_block_ex(self.h, C.byref(cfg), _ptr(baseband), nbytes,
+                                                           int(on_device), C.byref(out)))
+
+    def collect_block_ex(self, ticket: int):
+        """(results, host pointer of the series buffer, [device pointers of the streams' dynamic spectra])"""
+        res = (DetectResult * 4)()
+        series = C.c_void_p()
+        spec = (C.c_void_p * 4)()
+        n = self._ck(self.lib.srtb_b200_collect_block_ex(self.h, ticket, res, C.byref(series), spec))
+        return [res[i] for i in range(n)], series.value, [spec[i] for i in range(n)]
+
+    def debug_set_submit_count(self, value: int):
+        self._ck(self.lib.srtb_b200_debug_set_submit_count(self.h, value))
 
     def block_spectrum_ptr(self, stream: int) -> int:
         return self.lib.srtb_b200_block_spectrum(self.h, stream)

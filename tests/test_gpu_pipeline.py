@@ -136,8 +136,9 @@ def test_pipeline_fused_chain_pipe(tmp_path, oracle, fused):
 
 
 def test_pipeline_fused_chain_pipe_ring_equals_synchronous(tmp_path):
-    """baseband_chain_pipe over the submit/collect ring (H2D of block k overlaps block k-1; headers from the ring,
-    a candidate's series by re-running the block) must report exactly what the synchronous pipe reports."""
+    """baseband_chain_pipe over the submit/collect ring (H2D of block k overlaps block k-1; result headers, the
+    positive boxcar series and the dynamic spectrum all come from the ring slot — no block is run twice) must report
+    exactly what the synchronous pipe reports, series included (their peaks are printed by the sink)."""
     _build()
     logn, C_ = 18, 64
     n = 1 << logn
@@ -152,7 +153,8 @@ def test_pipeline_fused_chain_pipe_ring_equals_synchronous(tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         works = sorted((json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")), key=lambda w: w["block"])
         assert [w["block"] for w in works] == list(range(7))
-        outs.append([(w["zero_count"], [(s_["boxcar"], s_["count"], s_["length"]) for s_ in w["series"]]) for w in works])
+        outs.append([(w["zero_count"], [(s_["boxcar"], s_["count"], s_["length"], s_["peak"]) for s_ in w["series"]])
+                     for w in works])
     assert outs[0] == outs[1] == outs[2]
     assert any(series for _, series in outs[0])                       # the bursts are candidates
 
