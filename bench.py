@@ -6,20 +6,24 @@ reference CPU path timed on the same box.
 
 Contract (driver): python bench.py --gpus N --steps K --warmup W [--impl reference]
   * a "step" = one block of synthetic baseband through the whole chain on each rank;
-  * workload = BASELINE.json configs[1]: 2^24-sample blocks, 8-bit, one stream, single DM,
-    C = 2^11 channels (srtb_config.cfg thresholds); N > 1 shards independent blocks across ranks
-    (weak scaling, no collective on the data path);
-  * `value`  = samples / time with the blocks already resident in HBM (ring of 16 distinct blocks,
-    256 MiB > L2, so successive steps never re-read a cached input); blocks alternate over 6 contexts
-    (CUDA streams) per GPU, two blocks in flight per context, so one block's small detector-tail kernels
-    overlap the next block's FFT sweeps — every block still runs the whole chain and its result is read back;
+  * workload = BASELINE.json configs[2], the J1644-4559 shape the north star names: dual-polarisation
+    8-bit, 2^26 samples per stream per block, 400 MHz, DM 562.05, C = 2^11 channels (rows of 2^14 time
+    samples), manual zap list, SK and the boxcar detector; one block in two of the ring carries an injected
+    dispersed pulse, so the candidate path (host series from the detector kernel) is inside the timed region.
+    N > 1 shards independent blocks across ranks (weak scaling, no collective on the data path);
+    `secondary` repeats value / e2e on BASELINE configs[1] (2^24 samples, one stream);
+  * `value`  = samples / time with the blocks already resident in HBM (ring of distinct blocks larger than L2);
+    blocks alternate over `contexts_per_gpu` contexts (CUDA streams), two blocks in flight per context;
+    `single_context` is the same through ONE context (the reference drives one queue per device);
   * `e2e`    = the same from pinned HOST buffers through srtb_b200_submit_block()/collect_block() (the
     pinned-host ring: H2D of block i overlaps the compute of block i-1); every block's H2D and the D2H
-    of its detector result are inside the timed region;
-  * `roofline` = dominant stage: algorithmic bytes / CUDA-event time vs the measured
-    copy peak (MEASURED_PEAKS.json hbm_gbs, else 6650 fallback); `stages` has every stage;
-  * `cpu_baseline` = the CPU oracle (port of the reference operators, OpenMP, all host cores) on one
-    block of the same workload (rank 0, N = 1 only).
+    of its detector result (and of positive series) are inside the timed region;
+  * `roofline` = dominant per-pipe stage: algorithmic bytes / CUDA-event time vs the measured
+    copy peak (MEASURED_PEAKS.json hbm_gbs, else 6650 fallback); `stages` has every stage; `fused` times the
+    kernel groups the block path really launches against the bytes THEY must move; `roofline.chain` states the
+    unfused algorithmic bytes, the launched kernels' sweep bytes and (when a capture is committed) measured DRAM bytes;
+  * `cpu_baseline` = the CPU oracle (port of the reference operators, OpenMP, all host cores) on a bounded
+    sample of the same workload (rank 0, N = 1 only).
 --impl reference times that CPU path alone (rank 0) with the same JSON shape.
 """
 from __future__ import annotations
@@ -58,6 +62,28 @@ WORKLOADS = {
 }
 
 STAGES = ["unpack", "fft_r2c", "rfi_s1", "dedisperse", "watfft", "rfi_s2", "signal_detect"]
+FORMAT_STREAM_COUNT = {"simple": 1, "naocpsr_snap1": 2, "interleaved_samples_2": 2, "gznupsr_a1": 2, "gznupsr_a1_4": 4}
+
+
+def workload_string(wname: str, w: dict) -> str:
+    """identical in both arms (the driver compares them)"""
+    streams = FORMAT_STREAM_COUNT[w["fmt"]]
+    return (f"{wname}: 2^{w['log2n']}-sample blocks x{streams} stream(s), {abs(w['bits'])}-bit {w['fmt']}, "
+            f"C=2^11, DM={w['dm']}, full RFI + detect")
+
+
+def sweep_bytes_per_sample(w: dict) -> float:
+    """bytes the kernels process_block launches for this workload MUST move per input sample (every sweep reads and
+    writes its tile once): fused first sweep b/8 + 4, every further R2C sweep 8, then either the one-kernel
+    waterfall (8) or, for rows longer than 2^14, chirp sweep 8 + two waterfall sweeps 16 + SK 4 + column sums 4"""
+    q = w["log2n"] - 1                      # complex points of the packed transform
+    r2c_sweeps = 1 if q <= 12 else (2 if q <= 20 else (3 if q <= 26 else 4))
+    rows = (1 << q) // w["channels"]
+    first = (abs(w["bits"]) / 8 + 4) if abs(w["bits"]) == 8 and w["fmt"] in ("simple", "naocpsr_snap1", "interleaved_samples_2") \
+        else (abs(w["bits"]) / 8 + 4 + 8)   # separate unpack kernel, then the first sweep
+    waterfall = 8 if 1024 <= rows <= 16384 else 8 + 16 + 4 + 4
+    return first + 8 * (r2c_sweeps - 1) + waterfall
+
 
 
 def stage_bytes(n: int, bits: int) -> dict:
@@ -88,6 +114,19 @@ STAGE_KERNELS = {
     "rfi_s2": r"^sk_kernel",
     "signal_detect": r"^(colsum_|detect_)",
 }
+
+
+def measured_dram_bytes_per_sample(wname: str):
+    """DRAM bytes (read + write) of one fused block per input sample from the committed ncu capture of this workload
+    (profiles/traffic_<workload>.json, written by tools/summarize_profiles.py), or None"""
+    p = ROOT / "profiles" / f"traffic_{wname}.json"
+    if not p.exists():
+        return None
+    try:
+        d = json.loads(p.read_text())
+        return float(d["block_dram_bytes"]) / float(d["block_samples"])
+    except Exception:
+        return None
 
 
 _NCU_US = {}   # per-stage sum of kernel durations in the same committed capture (no launch / event overhead)
@@ -131,6 +170,62 @@ def synth_block(n_samples: int, streams: int, seed: int, bits: int = -8) -> np.n
     mid = (n_samples * streams) // 2
     v[mid:mid + 2048] *= 4.0
     return np.clip(np.rint(v), -127, 127).astype(np.int8)
+
+
+def dispersed_pulse(n: int, w: dict, amp: float = 1000.0, t0_frac: float = 0.37) -> np.ndarray:
+    """float32 time series whose R2C spectrum is amp * conj(chirp) * delay(t0): dedispersion with the workload's DM
+    folds it back into one impulse at sample t0 (the V3 "pulse" of SURVEY §8d). Per-sample amplitude is
+    amp / sqrt(n) << 1 count: it rides on the noise as dither and survives the 8-bit quantisation statistically."""
+    import scipy.fft as sfft
+    nc = n // 2
+    f_min, bw = np.float32(w["f_low"]), np.float32(w["bw"])
+    f_c = float(np.float32(f_min + bw))
+    df = float(np.float32(bw / np.float32(nc)))
+    spec = np.zeros(nc + 1, np.complex64)
+    step = min(nc, 1 << 18)                        # cache-sized chunks, buffers reused (fresh pages are slow here)
+    t0 = int(n * t0_frac)
+    k = np.empty(step, np.float64)
+    f = np.empty(step, np.float64)
+    g = np.empty(step, np.float64)
+    base = np.arange(step, dtype=np.float64)
+    cs = np.empty(step, np.complex128)
+    c_dm = (4.148808e3 * 1e6) * float(np.float32(w["dm"]))
+    for a in range(0, nc, step):
+        np.add(base, float(a), out=k)
+        np.multiply(k, df, out=f)
+        f += float(f_min)                          # f = f_min + df * k
+        np.subtract(f, f_c, out=g)
+        g /= f_c
+        g *= g
+        g /= f
+        g *= c_dm                                  # kk = D * dm / f * ((f - f_c) / f_c)^2
+        g -= np.floor(g)
+        k *= float(t0)
+        np.fmod(k, float(n), out=k)
+        k /= float(n)
+        g -= k                                     # phase in cycles: +chirp (inverse of dedispersion), delay t0
+        g *= 2 * np.pi
+        cs.real = np.cos(g)
+        cs.imag = np.sin(g)
+        spec[a:a + step] = amp * cs
+    return sfft.irfft(spec, n=n, workers=min(16, os.cpu_count() or 1)).astype(np.float32)
+
+
+def synth_block_with_pulse(n: int, streams: int, seed: int, w: dict) -> np.ndarray:
+    """synth_block plus the same dispersed pulse in every stream (8-bit formats only), re-quantised"""
+    rng = np.random.default_rng(0x53525442 + seed)
+    pulse = dispersed_pulse(n, w)
+    out = np.empty(n * streams, np.int8)
+    for s_ in range(streams):
+        v = rng.standard_normal(n, dtype=np.float32) * 20.0 + pulse
+        q = np.clip(np.rint(v), -127, 127).astype(np.int8)
+        if streams == 1:
+            out[:] = q
+        elif w["fmt"] == "naocpsr_snap1":           # "1 1 2 2"
+            out.reshape(-1, 4)[:, 2 * s_:2 * s_ + 2] = q.reshape(-1, 2)
+        else:                                        # "1 2 1 2"
+            out.reshape(-1, streams)[:, s_] = q
+    return out
 
 
 class ClockSampler:
@@ -273,7 +368,7 @@ def run_reference(args, w, wname):
     if rank != 0:
         return 0
     n = 1 << w["log2n"]
-    streams = 2 if w["fmt"] != "simple" else 1
+    streams = FORMAT_STREAM_COUNT[w["fmt"]]
     sample_n = min(n, 1 << 24)      # one step = one block of at most 2^24 samples per stream
     for _ in range(args.warmup):
         cpu_chain_seconds(w, min(sample_n, 1 << 20), 1, 1)
@@ -285,8 +380,7 @@ def run_reference(args, w, wname):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp64 chirp phase)",
         "data": "synthetic",
-        "config": {"workload": f"{wname}: 2^{w['log2n']}-sample blocks x{streams} stream(s), "
-                               f"{abs(w['bits'])}-bit, C=2^11, DM={w['dm']}",
+        "config": {"workload": workload_string(wname, w),
                    "sample": f"each step = one block of 2^{int(np.log2(sample_n))} samples/stream"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{args.steps} block(s) of 2^{int(np.log2(sample_n))} samples x{streams} "
@@ -319,19 +413,150 @@ def emit(text: str):
     out.flush()
 
 
+def default_contexts(w: dict) -> int:
+    """contexts (CUDA streams) per GPU that blocks alternate over: short blocks leave gaps between their kernels that
+    other blocks fill; long sweeps are pure HBM streams with little left to overlap"""
+    return 6 if w["log2n"] <= 24 else (4 if w["log2n"] < 28 else 2)
+
+
+class Harness:
+    """one workload on this rank's GPU: contexts, ring of distinct synthetic blocks (host pinned + device copies),
+    device-resident and end-to-end stepping through the ring API"""
+
+    def __init__(self, torch, srtb_b200, wname, w, n_contexts, rank, local_rank, inject_pulse):
+        self.torch, self.srtb = torch, srtb_b200
+        self.wname, self.w = wname, w
+        self.n = 1 << w["log2n"]
+        self.fmt = srtb_b200.FORMAT_BY_NAME[w["fmt"]]
+        self.streams = srtb_b200.FORMAT_STREAMS[self.fmt]
+        self.block_bytes = self.n * self.streams * abs(w["bits"]) // 8
+        self.ring = max(2, min(16, (288 << 20) // self.block_bytes))      # > L2 (126 MB) of distinct input
+        self.stream = torch.cuda.current_stream()
+        self.extra_streams = [torch.cuda.Stream() for _ in range(max(0, n_contexts - 1))]
+        self.ctxs = [srtb_b200.Context(local_rank, self.stream.cuda_stream)] + \
+                    [srtb_b200.Context(local_rank, st.cuda_stream) for st in self.extra_streams]
+        self.pairs = srtb_b200.eval_rfi_ranges(w["freq_list"]) if w["freq_list"] else []
+        cfg = srtb_b200.BlockConfig()
+        cfg.baseband_input_count = self.n
+        cfg.baseband_input_bits = w["bits"]
+        cfg.baseband_format = self.fmt
+        cfg.window = 0
+        cfg.baseband_reserve_sample = 0
+        cfg.baseband_freq_low, cfg.baseband_bandwidth = w["f_low"], w["bw"]
+        cfg.baseband_sample_rate, cfg.dm = w["fs"], w["dm"]
+        cfg.mitigate_rfi_average_method_threshold = w["avg_thr"]
+        cfg.mitigate_rfi_spectral_kurtosis_threshold = w["sk_thr"]
+        cfg.spectrum_channel_count = w["channels"]
+        cfg.signal_detect_signal_noise_threshold = w["snr"]
+        cfg.signal_detect_channel_threshold = w["chan_thr"]
+        cfg.signal_detect_max_boxcar_length = w["maxbox"]
+        flat = [v for p_ in self.pairs for v in p_]
+        self._arr = (C.c_float * max(1, len(flat)))(*flat)
+        cfg.rfi_freq_pairs = C.cast(self._arr, C.POINTER(C.c_float))
+        cfg.n_rfi_freq_pairs = len(self.pairs)
+        self.cfg = cfg
+        # synthetic blocks: distinct per rank and per ring slot; every second one carries a dispersed pulse
+        self.host_blocks, self.pulse_blocks = [], 0
+        for i in range(self.ring):
+            if inject_pulse and abs(w["bits"]) == 8 and i % 2 == 0:
+                b = synth_block_with_pulse(self.n, self.streams, seed=rank * 1000 + i, w=w)
+                self.pulse_blocks += 1
+            else:
+                b = synth_block(self.n, self.streams, seed=rank * 1000 + i, bits=w["bits"])
+            self.host_blocks.append(torch.from_numpy(b.view(np.uint8)).pin_memory())
+        self.dev_blocks = [hb.cuda(non_blocking=True) for hb in self.host_blocks]
+        torch.cuda.synchronize()
+        self.detections = 0
+        self.blocks_with_detection = 0
+        self._tickets = []
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+
+    @property
+    def launch_count(self):
+        return sum(c.launch_count for c in self.ctxs)
+
+    def _collect(self):
+        c, t = self._tickets.pop(0)
+        res = c.collect_block(t)
+        found = sum(int(r.signal_count[b]) for r in res for b in range(r.n_boxcars))
+        self.detections += found
+        self.blocks_with_detection += 1 if found else 0
+
+    def step_device(self, i):
+        c = self.ctxs[i % len(self.ctxs)]
+        self._tickets.append((c, c.submit_block_device(self.cfg, self.dev_blocks[i % self.ring], self.block_bytes)))
+        if len(self._tickets) >= 2 * len(self.ctxs):
+            self._collect()
+
+    def step_e2e(self, i):
+        c = self.ctxs[i % len(self.ctxs)]
+        self._tickets.append((c, c.submit_block(self.cfg, self.host_blocks[i % self.ring], self.block_bytes)))
+        if len(self._tickets) >= 2 * len(self.ctxs):
+            self._collect()
+
+    def drain(self):
+        while self._tickets:
+            self._collect()
+
+    def timed(self, fn, steps, dist):
+        """K steps between two CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks"""
+        torch = self.torch
+
+        def barrier():
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for st in self.extra_streams:
+            st.wait_stream(self.stream)
+        for i in range(steps):
+            fn(i)
+        self.drain()
+        for st in self.extra_streams:
+            self.stream.wait_stream(st)
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        barrier()
+        return ms
+
+    def warm(self, fn, warmup):
+        # at least W steps, and enough that EVERY context has seen every ring slot once (first use allocates scratch,
+        # builds twiddle tables and sets kernel attributes: cudaMalloc would stall the timed region)
+        warm = max(warmup, (SRTB_RING_SLOTS + 1) * len(self.ctxs))
+        for i in range(warm):
+            fn(i)
+        self.drain()
+        return warm
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--workload", default=os.environ.get("SRTB_BENCH_WORKLOAD", "config2"))
+    ap.add_argument("--workload", default=os.environ.get("SRTB_BENCH_WORKLOAD", "config3"))
+    ap.add_argument("--secondary", default=os.environ.get("SRTB_BENCH_SECONDARY", "config2"),
+                    help="second workload measured briefly (value + e2e) in the same line; 'none' skips it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pulse", action="store_true", help="noise-only blocks (no injected dispersed pulse)")
     ap.add_argument("--stage-iters", type=int, default=5)
     ap.add_argument("--contexts", type=int, default=int(os.environ.get("SRTB_BENCH_CONTEXTS", "0")),
                     help="contexts (CUDA streams) per GPU that blocks alternate over (0 = 6 up to 2^24-sample blocks, 4 up "
-                         "to 2^27, 2 above: long sweeps are pure HBM streams with little left to overlap)")
+                         "to 2^27, 2 above)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     wname = args.workload
@@ -354,175 +579,49 @@ def main():
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
-    n = 1 << w["log2n"]
-    if args.contexts <= 0:
-        args.contexts = 6 if w["log2n"] <= 24 else (4 if w["log2n"] < 28 else 2)
-    fmt = srtb_b200.FORMAT_BY_NAME[w["fmt"]]
-    streams = srtb_b200.FORMAT_STREAMS[fmt]
-    block_bytes = n * streams * abs(w["bits"]) // 8
-    ring = max(2, min(16, (288 << 20) // block_bytes))      # > L2 (126 MB) of distinct input
-    stream = torch.cuda.current_stream()
-    ctx = srtb_b200.Context(local_rank, stream.cuda_stream)
-    # optional extra contexts on their own streams: consecutive blocks alternate over them so the small
-    # detector-tail kernels of one block overlap the FFT sweeps of the next
-    extra_streams = [torch.cuda.Stream() for _ in range(max(0, args.contexts - 1))]
-    ctxs = [ctx] + [srtb_b200.Context(local_rank, st.cuda_stream) for st in extra_streams]
-
-    pairs = srtb_b200.eval_rfi_ranges(w["freq_list"]) if w["freq_list"] else []
-    cfg = srtb_b200.BlockConfig()
-    cfg.baseband_input_count = n
-    cfg.baseband_input_bits = w["bits"]
-    cfg.baseband_format = fmt
-    cfg.window = 0
-    cfg.baseband_reserve_sample = 0
-    cfg.baseband_freq_low, cfg.baseband_bandwidth = w["f_low"], w["bw"]
-    cfg.baseband_sample_rate, cfg.dm = w["fs"], w["dm"]
-    cfg.mitigate_rfi_average_method_threshold = w["avg_thr"]
-    cfg.mitigate_rfi_spectral_kurtosis_threshold = w["sk_thr"]
-    cfg.spectrum_channel_count = w["channels"]
-    cfg.signal_detect_signal_noise_threshold = w["snr"]
-    cfg.signal_detect_channel_threshold = w["chan_thr"]
-    cfg.signal_detect_max_boxcar_length = w["maxbox"]
-    flat = [v for p in pairs for v in p]
-    arr = (C.c_float * max(1, len(flat)))(*flat)
-    cfg.rfi_freq_pairs = C.cast(arr, C.POINTER(C.c_float))
-    cfg.n_rfi_freq_pairs = len(pairs)
-
-    # synthetic blocks: distinct per rank and per ring slot
-    host_blocks = []
-    for i in range(ring):
-        b = synth_block(n, streams, seed=rank * 1000 + i, bits=w["bits"])
-        host_blocks.append(torch.from_numpy(b.view(np.uint8)).pin_memory())
-    dev_blocks = [hb.cuda(non_blocking=True) for hb in host_blocks]
-    torch.cuda.synchronize()
-
-    def barrier():
-        torch.cuda.synchronize()
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, finish=None, body=None):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for st in extra_streams:
-            st.wait_stream(stream)
-        if body:
-            body(steps)
-        else:
-            for i in range(steps):
-                fn(i)
-        if finish:
-            finish()
-        for st in extra_streams:
-            stream.wait_stream(st)
-        e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if dist:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        barrier()
-        return ms
-
-    detections = [0]
-
-    # device-resident blocks go through the same ring API as the e2e path (two blocks in flight, so the
-    # host enqueues block i+1 while block i runs); every block's detector result is still read back
-    dtickets = []
-
-    def _dcollect():
-        c, t = dtickets.pop(0)
-        res = c.collect_block(t)
-        detections[0] += sum(int(r.signal_count[b]) for r in res for b in range(r.n_boxcars))
-
-    def step_device(i):
-        c = ctxs[i % len(ctxs)]
-        dtickets.append((c, c.submit_block_device(cfg, dev_blocks[i % ring], block_bytes)))
-        if len(dtickets) >= 2 * len(ctxs):
-            _dcollect()
-
-    def drain_device():
-        while dtickets:
-            _dcollect()
-
-    def device_body(steps):
-        """one host thread per context (ctypes releases the GIL inside the C calls): the ~10 launches per block are
-        enqueued in parallel, so a slow host core does not cap the device-resident figure. Context c takes blocks
-        c, c + n, c + 2n, ... and keeps two in flight."""
-        found = [0] * len(ctxs)
-
-        def worker(ci):
-            c, mine, det = ctxs[ci], [], 0
-            for i in range(ci, steps, len(ctxs)):
-                mine.append(c.submit_block_device(cfg, dev_blocks[i % ring], block_bytes))
-                if len(mine) >= 2:
-                    det += sum(int(r.signal_count[b]) for r in c.collect_block(mine.pop(0)) for b in range(r.n_boxcars))
-            while mine:
-                det += sum(int(r.signal_count[b]) for r in c.collect_block(mine.pop(0)) for b in range(r.n_boxcars))
-            found[ci] = det
-
-        workers = [threading.Thread(target=worker, args=(ci,)) for ci in range(len(ctxs))]
-        for t_ in workers:
-            t_.start()
-        for t_ in workers:
-            t_.join()
-        detections[0] += sum(found)
-
-    # e2e goes through the pipelined ingest API (pinned-host ring): block i's H2D runs on the copy stream
-    # while block i-1 computes; every block's detector result is read back on the host
-    tickets = []
-
-    def _collect():
-        c, t = tickets.pop(0)
-        res = c.collect_block(t)
-        detections[0] += sum(int(r.signal_count[b]) for r in res for b in range(r.n_boxcars))
-
-    def step_e2e(i):
-        c = ctxs[i % len(ctxs)]
-        tickets.append((c, c.submit_block(cfg, host_blocks[i % ring], block_bytes)))
-        if len(tickets) >= 2 * len(ctxs):
-            _collect()
-
-    def drain_e2e():
-        while tickets:
-            _collect()
+    n_ctx = args.contexts if args.contexts > 0 else default_contexts(w)
+    H = Harness(torch, srtb_b200, wname, w, n_ctx, rank, local_rank, inject_pulse=not args.no_pulse)
+    n, streams, block_bytes, ring = H.n, H.streams, H.block_bytes, H.ring
+    ctx, stream = H.ctxs[0], H.stream
+    samples_per_step = n * streams * world
 
     # ---- device-resident throughput (`value`)
-    # untimed warm-up: at least W steps, and enough that EVERY context has seen every ring slot once (first use
-    # allocates scratch, builds twiddle tables and sets kernel attributes: cudaMalloc would stall the timed region)
-    warm = max(args.warmup, (SRTB_RING_SLOTS + 1) * len(ctxs))
-    for i in range(warm):
-        step_device(i)
-    drain_device()
+    warm = H.warm(H.step_device, args.warmup)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = sum(c.launch_count for c in ctxs)
-    # one host thread per context was measured slower and erratic under the GIL (100..136 vs a steady 139): opt-in only
-    threaded = len(ctxs) > 1 and os.environ.get("SRTB_BENCH_THREADS", "0") == "1"
-    ms_total = timed(step_device, args.steps, drain_device, body=device_body if threaded else None)
-    launches = sum(c.launch_count for c in ctxs) - l0
+    l0 = H.launch_count
+    H.detections = H.blocks_with_detection = 0
+    ms_total = H.timed(H.step_device, args.steps, dist)
+    launches = H.launch_count - l0
+    detections, det_blocks = H.detections, H.blocks_with_detection
     if rank == 0 and not sampler.rows:
         sampler.snapshot()          # short run: take one sample while the GPU is still under load
     ms_per_step = ms_total / args.steps
-    samples_per_step = n * streams * world
     value = samples_per_step / (ms_per_step * 1e-3) / 1e9
 
     # ---- end to end from pinned host memory (`e2e`)
-    for i in range(warm):
-        step_e2e(i)
-    drain_e2e()
-    e2e_runs = [timed(step_e2e, args.steps, drain_e2e) / args.steps for _ in range(3)]
+    H.warm(H.step_e2e, args.warmup)
+    e2e_runs = [H.timed(H.step_e2e, args.steps, dist) / args.steps for _ in range(3)]
     ms_e2e = float(np.median(e2e_runs))           # host-side jitter (PCIe, the feeding thread): median of three
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = samples_per_step / (ms_e2e * 1e-3) / 1e9
-    d2h = C.sizeof(srtb_b200.DetectResult) * streams
+    series_bytes = 0                               # positive series written by the detector kernel: rare, small
+    d2h = C.sizeof(srtb_b200.DetectResult) * streams + series_bytes
+
+    # ---- the same through ONE context (one CUDA stream per GPU, as the reference drives its device)
+    single = None
+    if len(H.ctxs) > 1:
+        extra, H.ctxs, H.extra_streams = (H.ctxs[1:], H.extra_streams), H.ctxs[:1], []
+        H.warm(H.step_device, args.warmup)
+        ms1 = H.timed(H.step_device, max(10, args.steps // 2), dist) / max(10, args.steps // 2)
+        single = {"value": samples_per_step / (ms1 * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms1, "contexts_per_gpu": 1}
+        H.ctxs, H.extra_streams = H.ctxs + extra[0], extra[1]
+    else:
+        single = {"value": value, "unit": UNIT, "ms_per_step": ms_per_step, "contexts_per_gpu": 1}
 
     # ---- per-stage CUDA-event timing (rank 0): each stage called through the C ABI on one stream's data
-    stages = {}
+    stages, fused = {}, {}
     roofline = None
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -530,12 +629,14 @@ def main():
         nc = n // 2
         batch = min(w["channels"], nc)
         L = nc // batch
+        pairs = H.pairs
         coef = srtb_b200.norm_coefficient(nc, w["channels"])
         bins = [r for r in (srtb_b200.rfi_range_to_bins(a, b, w["f_low"], w["bw"], nc) for a, b in pairs) if r]
         f_min, bw = np.float32(w["f_low"]), np.float32(w["bw"])
         f_c, df = float(f_min + bw), float(bw / np.float32(nc))
         outs = [torch.empty(n + 2, dtype=torch.float32, device="cuda") for _ in range(streams)]
         buf = outs[0]
+        fmt, dev_blocks = H.fmt, H.dev_blocks
         calls = {
             "unpack": lambda i: ctx.unpack(dev_blocks[i % ring], block_bytes, w["bits"], fmt, 0, outs, n),
             "fft_r2c": lambda i: ctx.fft_r2c_inplace(buf, n),
@@ -563,8 +664,31 @@ def main():
             per_call_streams = streams if name == "unpack" else 1
             gbs = bytes_per[name] * per_call_streams / (ms * 1e-3) / 1e9
             stages[name] = {"ms": ms, "bytes": bytes_per[name] * per_call_streams, "gbs": gbs, "frac": gbs / peak}
-        chain_bytes = sum(bytes_per.values()) * streams
-        dom = max((s for s in STAGES), key=lambda s: stages[s]["ms"])
+        # ---- the kernel groups the block path really launches (last stream of a block), L2 flushed before each block,
+        # timed by CUDA events inside the library on the launching stream, against the bytes each group must move
+        ctx.stage_stats_enable(True)
+        acc = {k: [] for k in ("r2c", "waterfall", "detect_tail")}
+        grp_bytes = {}
+        for it in range(args.stage_iters + 1):
+            flush.fill_(it & 0xFF)
+            t_ = ctx.submit_block_device(H.cfg, dev_blocks[it % ring], block_bytes)
+            ctx.collect_block(t_)
+            if it == 0:
+                continue
+            for key, sid in (("r2c", 7), ("waterfall", 8), ("detect_tail", 9)):
+                try:
+                    ms_, b_ = ctx.stage_stats(sid)
+                    acc[key].append(ms_)
+                    grp_bytes[key] = b_
+                except Exception:
+                    pass
+        ctx.stage_stats_enable(False)
+        for key, v_ in acc.items():
+            if v_:
+                ms_ = float(np.mean(v_))
+                gbs = grp_bytes[key] / (ms_ * 1e-3) / 1e9
+                fused[key] = {"ms": ms_, "compulsory_bytes": grp_bytes[key], "gbs": gbs, "frac": gbs / peak}
+        dom = max((s_ for s_ in STAGES), key=lambda s_: stages[s_]["ms"])
         traffic, traffic_tag = stage_traffic() if wname == "config2" else ({}, None)
         for k_, v_ in traffic.items():
             if k_ in stages:
@@ -572,14 +696,54 @@ def main():
                 if _NCU_US.get(k_):   # offline: kernel time under ncu (cold cache), for comparison with the live `ms`
                     stages[k_]["ncu_kernel_us"] = _NCU_US[k_]
                     stages[k_]["ncu_frac"] = stages[k_]["bytes"] / (_NCU_US[k_] * 1e-6) / 1e9 / peak
+        # chain: three byte counts, each with its own fraction of the copy peak at the measured block time
+        per_sample_s = ms_per_step * 1e-3 / (n * streams)
+        unfused_bps = sum(bytes_per.values()) / n
+        sweep_bps = sweep_bytes_per_sample(w)
+        dram_bps = measured_dram_bytes_per_sample(wname)
+        chain = {
+            "algorithmic_unfused": {"bytes_per_sample": unfused_bps, "gbs": unfused_bps / per_sample_s / 1e9,
+                                    "frac": unfused_bps / per_sample_s / 1e9 / peak,
+                                    "note": "SURVEY 8d per-pipe bytes: what the chain would move pipe by pipe; a fused chain "
+                                            "can exceed 1.0 of this, it is not a roofline fraction"},
+            "sweep_bytes": {"bytes_per_sample": sweep_bps, "gbs": sweep_bps / per_sample_s / 1e9,
+                            "frac": sweep_bps / per_sample_s / 1e9 / peak,
+                            "note": "what the launched kernels must read + write (each sweep once)"},
+            "dram_measured": None if dram_bps is None else {
+                "bytes_per_sample": dram_bps, "gbs": dram_bps / per_sample_s / 1e9,
+                "frac": dram_bps / per_sample_s / 1e9 / peak,
+                "note": "ncu dram__bytes_read + write of one process_block at this workload (profiles/)"},
+        }
         roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak,
                     "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic.get(dom),
                     "traffic_source": (f"ncu --set full capture profiles/{traffic_tag}_summary.md (dram read+write of the "
                                        "stage's kernels, one launch each, L2 flushed)") if traffic_tag else None,
-                    "peak_source": peak_src,
-                    "chain": {"bytes_per_sample": chain_bytes / (n * streams),
-                              "achieved": chain_bytes / (ms_per_step * 1e-3) / 1e9,
-                              "frac": chain_bytes / (ms_per_step * 1e-3) / 1e9 / peak}}
+                    "peak_source": peak_src, "fused": fused, "chain": chain}
+
+    # ---- secondary workload (BASELINE configs[1]) in brief: value + e2e
+    secondary = None
+    if args.secondary not in ("none", "", wname) and args.secondary in WORKLOADS:
+        H.close()
+        del H
+        torch.cuda.empty_cache()
+        w2 = WORKLOADS[args.secondary]
+        H2 = Harness(torch, srtb_b200, args.secondary, w2, default_contexts(w2), rank, local_rank, inject_pulse=False)
+        steps2 = max(args.steps, 200)
+        H2.warm(H2.step_device, args.warmup)
+        ms2 = H2.timed(H2.step_device, steps2, dist) / steps2
+        H2.warm(H2.step_e2e, args.warmup)
+        ms2e = float(np.median([H2.timed(H2.step_e2e, steps2, dist) / steps2 for _ in range(3)]))
+        sps2 = H2.n * H2.streams * world
+        secondary = {"workload": workload_string(args.secondary, w2), "value": sps2 / (ms2 * 1e-3) / 1e9, "unit": UNIT,
+                     "ms_per_step": ms2, "steps": steps2, "contexts_per_gpu": len(H2.ctxs),
+                     "e2e": {"value": sps2 / (ms2e * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms2e,
+                             "h2d_bytes_per_step": H2.block_bytes * world},
+                     "sweep_bytes_per_sample": sweep_bytes_per_sample(w2)}
+        H2.close()
+        n_ctx_used = n_ctx
+    else:
+        n_ctx_used = n_ctx
+        H.close()
 
     # ---- CPU baseline (oracle port) on a bounded sample of the same workload
     cpu_baseline = None
@@ -588,28 +752,7 @@ def main():
             sample_n = min(n, 1 << 24)
             cpu_chain_seconds(w, 1 << 18, 1, 1)        # warm the OpenMP pool
             dt, threads, stage = cpu_chain_seconds(w, sample_n, 2, streams)
-            fast = None
-            try:  # the same chain with a fast CPU FFT (pocketfft) in place of the naive radix-2 for the two FFT stages
-                import scipy.fft as sfft
-                xs = synth_block(sample_n, 1, 1, w["bits"]).astype(np.float32) if abs(w["bits"]) == 8 else \
-                    np.random.default_rng(1).standard_normal(sample_n).astype(np.float32)
-                nc_ = sample_n // 2
-                cols = min(w["channels"], nc_)
-                sfft.rfft(xs[:1 << 16], workers=threads)
-                t0 = time.perf_counter()
-                spec = sfft.rfft(xs, workers=threads)[:nc_].astype(np.complex64)
-                t_r2c = time.perf_counter() - t0
-                t0 = time.perf_counter()
-                sfft.ifft(spec.reshape(cols, nc_ // cols), axis=1, workers=threads, norm="forward")
-                t_wat = time.perf_counter() - t0
-                per_block = dt / (2 * streams) - stage[1] / streams - stage[4] / streams + t_r2c + t_wat
-                fast = {"value": sample_n / per_block / 1e9, "unit": UNIT,
-                        "fft": f"scipy.fft (pocketfft, workers={threads}) for fft_r2c and watfft, other stages as above",
-                        "fft_r2c_s": t_r2c, "watfft_s": t_wat}
-            except Exception as e:
-                fast = {"value": None, "fft": f"failed: {e}"}
             cpu_baseline = {"value": sample_n * streams * 2 / dt / 1e9, "unit": UNIT, "cores": threads,
-                            "fast_fft": fast,
                             "kind": "port",
                             "sample": f"2 blocks of 2^{int(np.log2(sample_n))} samples x{streams} stream(s) of "
                                       "this workload; restated reference operators with the in-tree naive "
@@ -623,17 +766,19 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (fp64 chirp phase)", "data": "synthetic",
-            "config": {"workload": f"{wname}: 2^{w['log2n']}-sample blocks x{streams} stream(s) per GPU, "
-                                   f"{abs(w['bits'])}-bit {w['fmt']}, C=2^11, DM={w['dm']}, full RFI + detect",
+            "config": {"workload": workload_string(wname, w),
                        "parallelism": f"block-sharded x{world} (no collective)",
                        "l2": f"inputs larger than L2: ring of {ring} distinct blocks ({ring * block_bytes >> 20} MiB)",
-                       "contexts_per_gpu": len(ctxs), "submit_threads_per_gpu": len(ctxs) if threaded else 1, "warmup_steps_run": warm,
-                       "detections": detections[0]},
+                       "contexts_per_gpu": n_ctx_used, "warmup_steps_run": warm,
+                       "injected_pulse": "every second block of the ring carries a dispersed pulse (S/N ~ 25)" if not args.no_pulse else "none",
+                       "detections": detections, "blocks_with_detection": det_blocks},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e,
                     "runs_ms_per_step": e2e_runs, "note": "median of three runs of K steps each",
                     "h2d_bytes_per_step": block_bytes * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": launches,
+            "single_context": single,
+            "secondary": secondary,
             "roofline": roofline,
             "stages": stages,
             "cpu_baseline": cpu_baseline,
@@ -642,8 +787,6 @@ def main():
     if dist:
         dist.barrier()
         dist.destroy_process_group()
-    for c in ctxs:
-        c.close()
     return 0
 
 

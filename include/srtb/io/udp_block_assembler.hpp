@@ -13,10 +13,12 @@
 #include <climits>
 #include <cstddef>
 #include <cstdint>
+#include <cerrno>
 #include <cstring>
 #include <optional>
 #include <span>
 #include <stdexcept>
+#include <stop_token>
 #include <string>
 #include <string_view>
 #include <vector>
@@ -25,6 +27,7 @@
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <sys/socket.h>
+#include <sys/time.h>
 #include <unistd.h>
 #define SRTB_HAS_SOCKETS 1
 #endif
@@ -88,7 +91,7 @@ class block_assembler {
 
   /** fill one block; returns the counter of its first packet, or nullopt when the provider is exhausted
    *  before any packet of this block arrived */
-  std::optional<uint64_t> receive(std::span<std::byte> block) {
+  std::optional<uint64_t> receive(std::span<std::byte> block, std::stop_token st = {}) {
     const size_t count = block.size() / packet_data_size;
     if (count * packet_data_size != block.size())
       throw std::invalid_argument{"Packet of size " + std::to_string(packet_data_size) +
@@ -108,8 +111,10 @@ class block_assembler {
       carry_.reset();
     }
     while (!closed) {
-      std::span<const std::byte> pkt = provider.receive();
-      if (pkt.empty()) break;  // provider exhausted (synthetic streams / closed socket)
+      std::span<const std::byte> pkt;
+      if constexpr (requires { provider.receive(st); }) pkt = provider.receive(st);  // live socket: stoppable wait
+      else pkt = provider.receive();
+      if (pkt.empty()) break;  // provider exhausted (synthetic streams / closed socket / stop requested)
       if (pkt.size() - Backend::packet_header_size != packet_data_size) continue;  // unexpected size: skip
       const uint64_t c = Backend::parse_counter(pkt);
       if (!begin_counter.has_value()) begin_counter = c;
@@ -177,16 +182,40 @@ class recvfrom_packet_provider {
     if (::inet_pton(AF_INET, address.c_str(), &addr.sin_addr) != 1) throw std::runtime_error("[udp] bad address " + address);
     int rcvbuf = 64 << 20;
     ::setsockopt(fd_, SOL_SOCKET, SO_RCVBUF, &rcvbuf, sizeof(rcvbuf));
-    if (::bind(fd_, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) != 0) throw std::runtime_error("[udp] bind failed");
+    // bounded blocking: an idle socket must not keep the receiver thread from seeing its stop request
+    timeval tv{};
+    tv.tv_usec = 100 * 1000;
+    ::setsockopt(fd_, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    if (::bind(fd_, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) != 0) {
+      ::close(fd_);
+      fd_ = -1;
+      throw std::runtime_error("[udp] bind failed on " + address + ":" + std::to_string(port));
+    }
   }
+  recvfrom_packet_provider(const recvfrom_packet_provider&) = delete;
+  recvfrom_packet_provider& operator=(const recvfrom_packet_provider&) = delete;
   recvfrom_packet_provider(recvfrom_packet_provider&& o) noexcept : fd_{o.fd_}, buf_{std::move(o.buf_)} { o.fd_ = -1; }
   ~recvfrom_packet_provider() {
     if (fd_ >= 0) ::close(fd_);
   }
-  std::span<const std::byte> receive() {
-    const ssize_t n = ::recvfrom(fd_, buf_.data(), buf_.size(), 0, nullptr, nullptr);
-    if (n <= 0) return {};
-    return std::span<const std::byte>(buf_.data(), static_cast<size_t>(n));
+  /** next datagram; an empty span means "stop requested" (or a socket error), never a mere timeout */
+  std::span<const std::byte> receive(std::stop_token st = {}) {
+    for (;;) {
+      const ssize_t n = ::recvfrom(fd_, buf_.data(), buf_.size(), 0, nullptr, nullptr);
+      if (n > 0) return std::span<const std::byte>(buf_.data(), static_cast<size_t>(n));
+      if (n < 0 && (errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR)) {
+        if (st.stop_requested()) return {};
+        continue;  // idle link: keep listening
+      }
+      return {};
+    }
+  }
+  /** local port actually bound (port 0 = let the kernel choose; used by the loop-back test) */
+  unsigned short bound_port() const {
+    sockaddr_in a{};
+    socklen_t len = sizeof(a);
+    if (::getsockname(fd_, reinterpret_cast<sockaddr*>(&a), &len) != 0) return 0;
+    return ntohs(a.sin_port);
   }
 };
 #endif

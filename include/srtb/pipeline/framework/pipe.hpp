@@ -79,9 +79,11 @@ class pipe {
 template <typename PipeFunctor, typename InFunctor, typename OutFunctor, typename... Args>
 static std::jthread start_pipe(InFunctor in_functor, OutFunctor out_functor, Args... args) {
   auto ready = std::make_shared<std::atomic<int>>(0);  // 0 = constructing, 1 = ok, -1 = failed
+  // the arguments are moved into the thread and from there into the functor, which is constructed ON the pipe's own
+  // thread (pipe.hpp:148-161 of the reference): move-only arguments (a socket-owning packet provider) work
   std::jthread thread{[ready, in_functor, out_functor](std::stop_token st, Args... a) mutable {
                         try {
-                          pipe<PipeFunctor, InFunctor, OutFunctor> p{PipeFunctor{a...}, in_functor, out_functor};
+                          pipe<PipeFunctor, InFunctor, OutFunctor> p{PipeFunctor{std::move(a)...}, in_functor, out_functor};
                           ready->store(1);
                           p.run(st);
                         } catch (const std::exception& e) {
@@ -90,7 +92,7 @@ static std::jthread start_pipe(InFunctor in_functor, OutFunctor out_functor, Arg
                           throw;  // uncaught in a pipe thread terminates, as in the reference
                         }
                       },
-                      args...};
+                      std::move(args)...};
 #if __has_include(<pthread.h>)
   pthread_setname_np(thread.native_handle(), generate_thread_name<PipeFunctor>().c_str());
 #endif

@@ -26,12 +26,12 @@ class udp_receiver_pipe {
  public:
   explicit udp_receiver_pipe(PacketProvider provider, size_t id = 0) : assembler_{std::move(provider)}, id_{id} {}
 
-  std::optional<srtb::work::copy_to_device_work> operator()(std::stop_token, srtb::work::dummy_work) {
+  std::optional<srtb::work::copy_to_device_work> operator()(std::stop_token stop_token, srtb::work::dummy_work) {
     const size_t bytes = srtb::config.baseband_input_count *
                          static_cast<size_t>(std::abs(srtb::config.baseband_input_bits)) / srtb::BITS_PER_BYTE *
                          Backend::data_stream_count;
     auto h_in = srtb::host_allocator.allocate_shared<std::byte>(bytes);
-    const auto first = assembler_.receive(std::span<std::byte>(h_in.get(), bytes));
+    const auto first = assembler_.receive(std::span<std::byte>(h_in.get(), bytes), stop_token);
     if (!first.has_value()) return std::nullopt;
     SRTB_LOGD << " [udp receiver pipe] " << "id = " << id_ << ": block from packet " << *first << ", lost so far "
               << assembler_.total_lost_packet_count;

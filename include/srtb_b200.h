@@ -94,7 +94,12 @@ typedef enum {
   SRTB_B200_STAGE_WATFFT = 4,
   SRTB_B200_STAGE_RFI_S2 = 5,
   SRTB_B200_STAGE_SIGNAL_DETECT = 6,
-  SRTB_B200_STAGE_COUNT = 7
+  /* groups of the fused block path (srtb_b200_process_block / submit_block), per stream, with the bytes each
+   * group MUST move (compulsory traffic of the fused form): */
+  SRTB_B200_STAGE_FUSED_R2C = 7,        /* unpack + R2C + split + power mean: N*b/8 read, 4N written           */
+  SRTB_B200_STAGE_FUSED_WATERFALL = 8,  /* manual zap, s1, chirp, waterfall FFT, SK, column sums: 4N + 4N        */
+  SRTB_B200_STAGE_FUSED_DETECT_TAIL = 9,/* column-sum reduction, scan, boxcars (reads the partial sums only)   */
+  SRTB_B200_STAGE_COUNT = 10
 } srtb_b200_stage;
 int srtb_b200_stage_stats_enable(srtb_b200_ctx* ctx, int on);
 int srtb_b200_stage_stats(srtb_b200_ctx* ctx, int stage, double* ms, double* bytes);

@@ -18,8 +18,9 @@
 //     produced by the copy engine) signalled on an mbarrier;
 //   * twiddles: stage 0 from W_L^j by repeated multiplication, stages 1 and 2 from small shared-memory tables;
 //   * the chirp phase is evaluated in fp64 like the reference; 1/f comes from one correctly rounded reciprocal per
-//     thread and Newton steps from the neighbouring bin (relative error (B1*df/f)^(2^steps); the host picks the
-//     step count that keeps the phase error below 1e-9 cycles, or the exact reciprocal per bin), the fractional
+//     thread and Newton steps from the neighbouring bin: one step when (B1*df/f)^2 <= 2^-52 (the reciprocal is then
+//     good to an ulp, the accuracy of the reference's own fp64 division chain), two when the fourth power keeps the
+//     phase error below 1e-9 cycles, otherwise the exact reciprocal of every bin; the fractional
 //     part by the round-to-nearest trick (e^{-2 pi i k} only needs k mod 1), sin/cos from the SFU on [-pi, pi].
 #pragma once
 #include "fft_engine.cuh"
@@ -41,7 +42,7 @@ struct bigrow {
   static constexpr size_t off_colacc = (size_t)BUF * sizeof(float2);
   __host__ __device__ static constexpr size_t off_tab(bool sk) { return off_colacc + (sk ? (size_t)BUF * sizeof(float) : 0); }
   __host__ __device__ static constexpr size_t off_mbar(bool sk) { return off_tab(sk) + (size_t)TABN * sizeof(float2); }
-  __host__ __device__ static constexpr size_t off_red(bool sk) { return off_mbar(sk) + 64; }
+  __host__ __device__ static constexpr size_t off_red(bool sk) { return off_mbar(sk) + 128; }  // 16 mbarriers
   __host__ __device__ static constexpr size_t bytes(bool sk) { return off_red(sk) + 4 * 32 * sizeof(float); }
 };
 
@@ -112,7 +113,8 @@ __device__ __forceinline__ float2 bigrow_chirp_point(float2 v, double f, double 
   return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
 }
 
-template <int LOGL, bool FWD, bool SK, bool CHIRP>
+// CHIRP: 0 = plain transform; s1 + chirp on load with 1 = one-step Newton reciprocals, 3 = two steps, 2 = exact reciprocals
+template <int LOGL, bool FWD, bool SK, int CHIRP>
 __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
     fft_bigrow_kernel(const float2* __restrict__ in, float2* __restrict__ out, unsigned nrows,
                       const float2* __restrict__ tabs, row_sk_params skp, row_chirp_params cp) {
@@ -131,21 +133,21 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
   for (int i = tid; i < C::TABN; i += NT) T0[i] = __ldg(&tabs[i]);
   if constexpr (SK)
     for (int i = tid; i < C::BUF; i += NT) colacc[i] = 0.f;
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    fence_mbar_init();
-  }
+  if (tid < 16) mbar_init(&mbar[tid], 1);
+  if (tid == 0) fence_mbar_init();
   __syncthreads();
 
-  // warp 0: fetch one row into the padded layout, one bulk copy per B2-element segment
+  // warp 0: fetch one row into the padded layout, one bulk copy per B2-element segment. The row is sixteen chunks of
+  // B1 elements (d0 = 0..15), each signalled on its own mbarrier, fetched in order: stage 0 consumes chunk i (its
+  // butterfly input i) while the later chunks are still in flight, so most of the load hides behind the chirp.
   auto issue = [&](unsigned row) {
     fence_proxy_async();
-    if (lane == 0) mbar_expect_tx(mbar, (uint32_t)(L * sizeof(float2)));
+    if (lane < 16) mbar_expect_tx(&mbar[lane], (uint32_t)(B1 * sizeof(float2)));
     __syncwarp();
     const float2* src = in + (size_t)row * L;
 #pragma unroll
-    for (int seg = lane; seg < 256; seg += 32)
-      bulk_g2s(buf + (seg >> 4) * S1 + (seg & 15) * S2, src + seg * B2, (uint32_t)(B2 * sizeof(float2)), mbar);
+    for (int seg = lane; seg < 256; seg += 32)  // seg >> 4 = chunk: two chunks per round, in chunk order
+      bulk_g2s(buf + (seg >> 4) * S1 + (seg & 15) * S2, src + seg * B2, (uint32_t)(B2 * sizeof(float2)), &mbar[seg >> 4]);
   };
 
   float limit = 0.f;
@@ -154,30 +156,36 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
   unsigned row = blockIdx.x;
   if (row < nrows && wid == 0) issue(row);
   for (unsigned it = 0; row < nrows; row += gridDim.x, it++) {
-    mbar_wait(mbar, it & 1);
     // ---- stage 0: butterflies over d0 (stride S1), pair j = 2 tid, 2 tid + 1 of [0, B1)
     {
       const int j = 2 * tid;
       float2* const p = buf + (j / B2) * S2 + (j % B2);
       float2 a[16], b[16];
+      if constexpr (!CHIRP) {
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const float4 q = *reinterpret_cast<const float4*>(p + i * S1);
-        a[i] = make_float2(q.x, q.y);
-        b[i] = make_float2(q.z, q.w);
+        for (int i = 0; i < 16; i++) {
+          mbar_wait(&mbar[i], it & 1);
+          const float4 q = *reinterpret_cast<const float4*>(p + i * S1);
+          a[i] = make_float2(q.x, q.y);
+          b[i] = make_float2(q.z, q.w);
+        }
       }
       if constexpr (CHIRP) {
         // bin index of a[i] is row*L + j + i*B1 (b[i]: + 1); f = f_min + df * index in fp64
         double idx = (double)((size_t)row * L + j);
         double fa = fma(cp.df, idx, cp.f_min);
         double ra = __drcp_rn(fa);
-        // 1/f of the next bin: cp.newton Newton steps from the neighbour's reciprocal (each squares the relative
-        // error, which starts at (bin distance * df / f)); cp.newton == 0: a correctly rounded reciprocal per bin
+        // 1/f of the next bin: Newton steps from the neighbour's reciprocal (each squares the relative error, which
+        // starts at bin distance * df / f), or a correctly rounded reciprocal per bin (CHIRP == 2)
         auto refine = [&](double r, double f) {
-          if (cp.newton == 0) return __drcp_rn(f);
-          r = fma(r, fma(-f, r, 1.0), r);
-          for (int st = 1; st < cp.newton; st++) r = fma(r, fma(-f, r, 1.0), r);
-          return r;
+          if constexpr (CHIRP == 1) {
+            return fma(r, fma(-f, r, 1.0), r);  // one Newton step (the host checked that it is good to 1 ulp)
+          } else if constexpr (CHIRP == 3) {
+            r = fma(r, fma(-f, r, 1.0), r);     // two steps
+            return fma(r, fma(-f, r, 1.0), r);
+          } else {
+            return __drcp_rn(f);                // widely spaced bins (short test blocks): exact reciprocal
+          }
         };
 #pragma unroll
         for (int i = 0; i < 16; i++) {
@@ -185,6 +193,12 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
             idx += (double)B1;
             fa = fma(cp.df, idx, cp.f_min);
             ra = refine(ra, fa);
+          }
+          mbar_wait(&mbar[i], it & 1);  // chunk i has landed (later chunks still arriving)
+          {
+            const float4 q = *reinterpret_cast<const float4*>(p + i * S1);
+            a[i] = make_float2(q.x, q.y);
+            b[i] = make_float2(q.z, q.w);
           }
           a[i] = bigrow_chirp_point(a[i], fa, ra, cp, limit);
           const double fb = fma(cp.df, idx + 1.0, cp.f_min);

@@ -762,16 +762,24 @@ __global__ void __launch_bounds__(256) sk_colsum_kernel(float2* __restrict__ x, 
   }
 }
 
-// K17 stage 2 + K16: ts[j] = sum over chunks (fixed order), zero_count.
-// CTA = 32 columns x 32 chunk groups: coalesced along time, fixed-order tree over the groups.
-__global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restrict__ partial,
-                                                            size_t ts_count, size_t chunks,
-                                                            float* __restrict__ ts,
-                                                            const float2* __restrict__ x,
-                                                            size_t time_count, size_t chan_count,
-                                                            detect_dev_result* __restrict__ res) {
+// K17 stage 2 + K16 + K18 + K20 in one launch: ts[j] = sum over chunks (fixed order) and zero_count by every CTA
+// (CTA = 32 columns x 32 chunk groups: coalesced along time, fixed-order tree over the groups); the LAST CTA to
+// finish (ticket) then removes the mean, forms the inclusive scan (fp64 carries) and fills the result header —
+// what used to be a separate single-CTA kernel between two launches.
+__global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __restrict__ partial,
+                                                                 size_t ts_count, size_t chunks,
+                                                                 float* __restrict__ ts, float* __restrict__ acc,
+                                                                 const float2* __restrict__ x,
+                                                                 size_t time_count, size_t chan_count,
+                                                                 float chan_thr, size_t max_boxcar,
+                                                                 unsigned* __restrict__ ticket,
+                                                                 detect_dev_result* __restrict__ res) {
   __shared__ float sm[32][33];
-  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  __shared__ double smd[32];
+  __shared__ double warp_tot[32];
+  __shared__ float s_mean;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
   const size_t j = (size_t)blockIdx.x * 32 + lx;
   float a = 0.f;
   if (j < ts_count) {
@@ -789,76 +797,70 @@ __global__ void __launch_bounds__(1024) colsum_final_kernel(const float* __restr
   }
   // K16: channels whose first sample is zero; every CTA takes a slice, integer atomics (exact)
   {
-    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t c = (size_t)blockIdx.x * blockDim.x + tid;
     int z = 0;
     if (c < chan_count) {
       const float2 v = x[c * time_count];
       z = (v.x * v.x + v.y * v.y == 0.f) ? 1 : 0;
     }
     const unsigned m = __ballot_sync(0xffffffffu, z);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&res->zero_count, (unsigned long long)__popc(m));
-    // channels beyond gridDim.x * blockDim.x (more channels than columns/32*256): strided tail
+    if (lx == 0 && m) atomicAdd(&res->zero_count, (unsigned long long)__popc(m));
     for (size_t cc = c + (size_t)gridDim.x * blockDim.x; cc < chan_count; cc += (size_t)gridDim.x * blockDim.x) {
       const float2 v = x[cc * time_count];
       if (v.x * v.x + v.y * v.y == 0.f) atomicAdd(&res->zero_count, 1ull);
     }
   }
-}
-
-// K18 + K20 in one CTA: mean removal, inclusive scan (fp64 chunk offsets), result header.
-__global__ void __launch_bounds__(1024) detect_scan_kernel(float* __restrict__ ts, float* __restrict__ acc,
-                                                           size_t ts_count, size_t chan_count,
-                                                           float chan_thr, size_t max_boxcar,
-                                                           detect_dev_result* __restrict__ res) {
-  __shared__ double smd[32];
-  __shared__ double chunk_off[1024];
-  __shared__ float s_mean;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  // each thread owns a contiguous chunk: one pass for the mean, one for the scan
-  const size_t per = (ts_count + nt - 1) / nt;
-  const size_t lo = min((size_t)tid * per, ts_count), hi = min(lo + per, ts_count);
+  // ---- last CTA: mean removal, inclusive scan, header
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nt = blockDim.x;
   double local = 0.0;
-  for (size_t i = lo; i < hi; i++) local += (double)ts[i];
+  for (size_t i = tid; i < ts_count; i += nt) local += (double)__ldcg(&ts[i]);
   const double total = block_sum<double>(local, smd);
   if (tid == 0) s_mean = (float)total / (float)ts_count;   // map_average: sum / float(count)
   __syncthreads();
   const float mean = s_mean;
-  // chunk sums of the mean-removed series
-  double lsum = 0.0;
-  for (size_t i = lo; i < hi; i++) {
-    const float v = ts[i] - mean;
-    ts[i] = v;
-    lsum += (double)v;
-  }
-  chunk_off[tid] = lsum;
-  __syncthreads();
-  // exclusive scan of the 1024 chunk sums by warp 0 (32 values per lane, then a shuffle scan)
-  if (tid < 32) {
-    double run = 0.0;
-    const int per_lane = nt / 32;
-    for (int i = 0; i < per_lane; i++) run += chunk_off[tid * per_lane + i];
-    double incl = run;
+  double carry = 0.0;  // running sum of everything before this tile of blockDim.x elements
+  for (size_t base = 0; base < ts_count; base += nt) {
+    const size_t i = base + tid;
+    float v = 0.f;
+    if (i < ts_count) {
+      v = __ldcg(&ts[i]) - mean;
+      ts[i] = v;
+    }
+    double incl = (double)v;  // inclusive scan of the tile in fp64: warp shuffles, then the 32 warp totals
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (tid >= o) incl += t;
+      if (lx >= o) incl += t;
     }
-    double base = incl - run;
-    for (int i = 0; i < per_lane; i++) {
-      const double t = chunk_off[tid * per_lane + i];
-      chunk_off[tid * per_lane + i] = base;
-      base += t;
+    if (lx == 31) warp_tot[ly] = incl;
+    __syncthreads();
+    if (ly == 0) {
+      const double w = warp_tot[lx];
+      double wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lx >= o) wi += t;
+      }
+      warp_tot[lx] = wi - w;                 // exclusive offset of warp lx
+      if (lx == 31) smd[0] = wi;             // tile total
     }
-  }
-  __syncthreads();
-  double run = chunk_off[tid];
-  for (size_t i = lo; i < hi; i++) {
-    run += (double)ts[i];
-    acc[i] = (float)run;
+    __syncthreads();
+    const double run = carry + warp_tot[ly] + incl;
+    if (i < ts_count) acc[i] = (float)run;
+    carry += smd[0];
+    __syncthreads();
   }
   if (tid == 0) {
     res->time_series_count = ts_count;
-    const int enabled = ((float)res->zero_count < chan_thr * (float)chan_count) ? 1 : 0;
+    const unsigned long long zc = *reinterpret_cast<volatile unsigned long long*>(&res->zero_count);  // all CTAs' atomics
+    const int enabled = ((float)zc < chan_thr * (float)chan_count) ? 1 : 0;
     res->detect_enabled = enabled;
     int nb = 0;
     if (enabled) {
@@ -866,6 +868,7 @@ __global__ void __launch_bounds__(1024) detect_scan_kernel(float* __restrict__ t
       for (size_t b = 2; b <= max_boxcar && b < ts_count && nb < 32; b *= 2) nb++;
     }
     res->n_boxcars = nb;
+    *ticket = 0;
   }
 }
 

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <set>
 #include <string>
 #include <vector>
@@ -41,6 +42,7 @@ struct srtb_b200_ctx {
   // s1
   double* partial = nullptr;
   unsigned* ticket = nullptr;
+  unsigned* detect_ticket = nullptr;  // last-CTA ticket of the detector's column-sum kernel
   float* mean = nullptr;
   // detect (slots = streams in flight)
   float* colsum_partial = nullptr;
@@ -175,6 +177,8 @@ int srtb_b200_ctx_create(int device, void* cuda_stream, srtb_b200_ctx** out) {
   if (e == cudaSuccess) e = cudaMalloc(&ctx->partial, sizeof(double) * 4096);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->ticket, sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemset(ctx->ticket, 0, sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->detect_ticket, sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemset(ctx->detect_ticket, 0, sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->mean, sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_res, sizeof(detect_dev_result) * 4);
   if (e == cudaSuccess) e = cudaMemset(ctx->d_res, 0, sizeof(detect_dev_result) * 4);
@@ -200,6 +204,7 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   cudaFree(ctx->fft_scratch);
   cudaFree(ctx->partial);
   cudaFree(ctx->ticket);
+  cudaFree(ctx->detect_ticket);
   cudaFree(ctx->mean);
   cudaFree(ctx->colsum_partial);
   for (auto& p : ctx->series) cudaFree(p);
@@ -564,8 +569,17 @@ static bool plan_last_long() {
   }();
   return on;
 }
+// SRTB_B200_PLAN_FIRST_SHORT=1: give the FIRST sweep the short factor (2^25 = 2^8 * 2^9 * 2^8 instead of 2^9 * 2^8 * 2^8):
+// the raw-byte first sweep then runs 256-point columns of 16 neighbours (64-byte raw segments for two streams)
+static bool plan_first_short() {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_PLAN_FIRST_SHORT");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 static void plan3(int q, int* l1, int* l2, int* l3) {
-  *l1 = (q + 2) / 3;
+  *l1 = plan_first_short() ? q / 3 : (q + 2) / 3;
   const int big = (q - *l1 + 1) / 2, small = q - *l1 - big;
   // the fused R2C last sweep exists up to L = 256: keep the last factor <= 8 when one of the two is
   const bool last_big = plan_last_long() && big <= 8;
@@ -898,11 +912,13 @@ static int launch_bigrow(srtb_b200_ctx* ctx, const float2* in, float2* out, size
     return 0;
   };
   if constexpr (!FWD) {
-    if (sk && chirp) return go(fft_bigrow_kernel<LOGL, false, true, true>, true);
-    if (sk) return go(fft_bigrow_kernel<LOGL, false, true, false>, true);
+    if (sk && chirp && chirp->newton == 1) return go(fft_bigrow_kernel<LOGL, false, true, 1>, true);
+    if (sk && chirp && chirp->newton == 2) return go(fft_bigrow_kernel<LOGL, false, true, 3>, true);
+    if (sk && chirp) return go(fft_bigrow_kernel<LOGL, false, true, 2>, true);
+    if (sk) return go(fft_bigrow_kernel<LOGL, false, true, 0>, true);
   }
   if (sk || chirp) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "fft: fused epilogue exists for the backward transform only");
-  return go(fft_bigrow_kernel<LOGL, FWD, false, false>, false);
+  return go(fft_bigrow_kernel<LOGL, FWD, false, 0>, false);
 }
 
 // L = 2 or 4: one thread per row
@@ -1388,12 +1404,10 @@ static int detect_prepare(srtb_b200_ctx* ctx, int slot, size_t time_count, size_
 static int detect_tail(srtb_b200_ctx* ctx, int slot, const float2* x, size_t time_count, size_t chan_count,
                        size_t ts_count, size_t chunks, float snr, float chan_thr, size_t max_boxcar) {
   float* const host_series = ctx->host_series_dst ? ctx->host_series_dst + (size_t)slot * SRTB_B200_MAX_BOXCARS * time_count : nullptr;
-  colsum_final_kernel<<<(unsigned)((ts_count + 31) / 32), 1024, 0, ctx->stream>>>(
-      ctx->colsum_partial, ts_count, chunks, ctx->series[slot], x, time_count, chan_count, ctx->d_res + slot);
-  ctx->launches++;
-  CK(cudaGetLastError());
-  detect_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->series[slot], ctx->acc, ts_count, chan_count, chan_thr,
-                                                  max_boxcar, ctx->d_res + slot);
+  stage_scope stats_(ctx, SRTB_B200_STAGE_FUSED_DETECT_TAIL, 4.0 * (double)chunks * (double)ts_count);
+  colsum_final_scan_kernel<<<(unsigned)((ts_count + 31) / 32), 1024, 0, ctx->stream>>>(
+      ctx->colsum_partial, ts_count, chunks, ctx->series[slot], ctx->acc, x, time_count, chan_count, chan_thr,
+      max_boxcar, ctx->detect_ticket, ctx->d_res + slot);
   ctx->launches++;
   CK(cudaGetLastError());
   // one CTA per possible boxcar; CTAs beyond n_boxcars (known only on the device) exit at once
@@ -1505,32 +1519,28 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
   const float lo_ = lo * ((M_ - 1) / (M_ + 1)) + 1, hi_ = hi * ((M_ - 1) / (M_ + 1)) + 1;
   size_t chunks = 0;
   int rc = 0;
+  std::unique_ptr<stage_scope> stats_(new stage_scope(ctx, SRTB_B200_STAGE_FUSED_WATERFALL, 16.0 * (double)time_count * (double)chan_count));
   if (time_count == 8192 || time_count == 16384) {
     row_sk_params p{lo_, hi_, nullptr, (unsigned)ts_count};
     row_chirp_params cpv{};
     if (chirp) {
       cpv = *chirp;
-      // 1/f of a bin comes from Newton steps off the reciprocal of the bin B1 = L/16 below: n steps leave a relative
-      // error of (B1 df / f)^(2^n), i.e. |k| times that in cycles of phase. Keep it below 1e-9 cycles (fp32 resolves
-      // 6e-8); widely spaced bins (short test blocks) take more steps or the exact reciprocal of every bin.
+      // 1/f of a bin comes from Newton steps off the reciprocal of the bin B1 = L/16 below; n steps leave a relative
+      // error of (B1 df / f)^(2^n). One step when that is within an ulp of fp64 (2^-52: as good as the division the
+      // reference performs; the J1644 shape has 1.5e-16), two when the fourth power keeps |k| * error below 1e-9
+      // cycles of phase, else the exact reciprocal of every bin (widely spaced bins of short test blocks).
       const double fa = std::min(std::fabs(cpv.f_min), std::fabs(cpv.f_c));
       const double delta = (double)(time_count / 16) * std::fabs(cpv.df) / fa;
       const double q = (cpv.f_c - cpv.f_min) * cpv.inv_fc;
       const double kmax = std::max(1.0, std::fabs(cpv.ddm) / fa * q * q);
-      cpv.newton = 0;
-      double err = delta;
-      for (int n = 1; n <= 3; n++) {
-        err *= err;
-        if (err * kmax < 1e-9) {
-          cpv.newton = n;
-          break;
-        }
-      }
+      const double d2 = delta * delta;
+      cpv.newton = (d2 <= 0x1p-52) ? 1 : ((d2 * d2 * kmax < 1e-9) ? 2 : 0);
     }
     const float2* s_ = src ? src : x;
     rc = (time_count == 8192) ? launch_bigrow<13, false>(ctx, s_, x, chan_count, &p, chirp ? &cpv : nullptr, &chunks)
                               : launch_bigrow<14, false>(ctx, s_, x, chan_count, &p, chirp ? &cpv : nullptr, &chunks);
     if (rc) return rc;
+    stats_.reset();
     return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
   }
   switch (ilog2(time_count)) {
@@ -1540,6 +1550,7 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
     default: rc = watfft_sk_launch<12>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp, src); break;
   }
   if (rc) return rc;
+  stats_.reset();
   return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
 }
 
@@ -1720,6 +1731,8 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
   for (int s = 0; s < streams; s++) {
     float* buf = bufs[s];
     {
+      stage_scope stats_(ctx, SRTB_B200_STAGE_FUSED_R2C,
+                         (double)N * (fuse_unpack ? (double)std::abs(cfg->baseband_input_bits) / 8.0 : 4.0) + 4.0 * (double)N);
       int rc = SRTB_B200_E_UNSUPPORTED;
       if (fuse_unpack && !unpacked) rc = fft_r2c_with_power_mean(ctx, buf, N, &raw[s], nullptr);
       if (rc == SRTB_B200_E_UNSUPPORTED) {

@@ -5,6 +5,7 @@
 #include <array>
 #include <atomic>
 #include <cassert>
+#include <chrono>
 #include <cstdio>
 #include <memory>
 #include <numeric>
@@ -13,6 +14,7 @@
 #include "srtb/pipeline/framework/composite_pipe.hpp"
 #include "srtb/pipeline/framework/dummy_pipe.hpp"
 #include "srtb/pipeline/framework/pipe.hpp"
+#include "srtb/io/udp_block_assembler.hpp"
 #include "srtb/pipeline/framework/pipe_io.hpp"
 #include "srtb/work.hpp"
 
@@ -185,6 +187,67 @@ int main() {
     idle.request_stop();
     idle.join();
   }
+#ifdef SRTB_HAS_SOCKETS
+  {
+    // live-socket source: a move-only, socket-owning packet provider goes through start_pipe into a
+    // pipe functor built on the pipe's thread; datagrams sent over the loop-back interface come out as assembled
+    // blocks; an idle socket does not keep the thread from stopping (bounded recvfrom + stop_token)
+    namespace io = srtb::io;
+    using B = io::backend_registry::fastmb_roach2;
+    constexpr size_t d = B::packet_payload_size - B::packet_header_size;
+    struct block_work {
+      std::vector<std::byte> bytes;
+      uint64_t first = 0;
+    };
+    struct socket_source_pipe {
+      io::udp::block_assembler<io::udp::recvfrom_packet_provider, B> assembler;
+      explicit socket_source_pipe(io::udp::recvfrom_packet_provider p) : assembler{std::move(p)} {}
+      std::optional<block_work> operator()(std::stop_token st, srtb::work::dummy_work) {
+        block_work w;
+        w.bytes.resize(4 * d);
+        const auto first = assembler.receive(w.bytes, st);
+        if (!first) return std::nullopt;
+        w.first = *first;
+        return w;
+      }
+    };
+    io::udp::recvfrom_packet_provider provider{"127.0.0.1", 0};
+    const unsigned short port = provider.bound_port();
+    CHECK(port != 0);
+    auto blocks = std::make_shared<srtb::work_queue<block_work, false>>();
+    std::jthread src = start_pipe<socket_source_pipe>(dummy_in_functor<>{}, queue_out_functor{blocks}, std::move(provider));
+    const int tx = ::socket(AF_INET, SOCK_DGRAM, 0);
+    sockaddr_in to{};
+    to.sin_family = AF_INET;
+    to.sin_port = htons(port);
+    ::inet_pton(AF_INET, "127.0.0.1", &to.sin_addr);
+    std::vector<std::byte> stream(8 * d);
+    for (size_t i = 0; i < stream.size(); i++) stream[i] = static_cast<std::byte>((i * 7 + i / d) & 0xff);
+    auto packets = io::udp::frame_stream<B>(stream, 500);
+    for (size_t i = 0; i < packets.size(); i++) {
+      if (i == 2) continue;  // one datagram lost on the way
+      CHECK(::sendto(tx, packets[i].data(), packets[i].size(), 0, reinterpret_cast<sockaddr*>(&to), sizeof(to)) ==
+            (ssize_t)packets[i].size());
+      std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    }
+    block_work b0, b1;
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::seconds(5);
+    while (!blocks->pop(b0)) CHECK(std::chrono::steady_clock::now() < deadline);
+    while (!blocks->pop(b1)) CHECK(std::chrono::steady_clock::now() < deadline);
+    CHECK(b0.first == 500 && b1.first == 504);
+    for (size_t pkt = 0; pkt < 4; pkt++)
+      for (size_t j = 0; j < d; j += 97) {
+        CHECK(b0.bytes[pkt * d + j] == (pkt == 2 ? std::byte{0} : stream[pkt * d + j]));  // the lost packet is zero-filled
+        CHECK(b1.bytes[pkt * d + j] == stream[(4 + pkt) * d + j]);
+      }
+    // the socket is idle now: the receiver must still stop promptly
+    const auto t_stop = std::chrono::steady_clock::now();
+    src.request_stop();
+    src.join();
+    CHECK(std::chrono::steady_clock::now() - t_stop < std::chrono::seconds(2));
+    ::close(tx);
+  }
+#endif
   CHECK(class_name<add_pipe>() == "add_pipe");
   CHECK(class_name<composite_pipe<add_pipe, double_pipe>>() == "composite_pipe");
   CHECK(generate_thread_name<composite_pipe<add_pipe, double_pipe>>().size() <= 15);

@@ -32,3 +32,24 @@ def test_gpu_arm_fails_loudly_without_a_device():
                        text=True, timeout=600)
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CUDA device" in r.stderr or "no CPU fallback" in r.stderr
+
+
+def test_both_arms_name_the_same_workload_and_default_is_the_j1644_shape():
+    """the driver compares config.workload of the two arms; the default is BASELINE configs[2] (north star)"""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-1500:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    assert d["config"]["workload"] == bench.workload_string("config3", bench.WORKLOADS["config3"])
+    assert "2^26-sample blocks x2 stream(s)" in d["config"]["workload"] and "DM=562.05" in d["config"]["workload"]
+
+
+def test_sweep_byte_model():
+    """bytes the launched kernels must move per sample (bench.py roofline.chain.sweep_bytes)"""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config2"]) == 1 + 4 + 8 + 8 + 8          # 3-sweep R2C, fused waterfall
+    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config3"]) == 29
+    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config1"]) == 0.25 + 4 + 8 + 24 + 32      # unpack + 4 sweeps + unfused tail

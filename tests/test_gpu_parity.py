@@ -844,6 +844,132 @@ def test_j1644_config_shape_full_size(ctx):
     assert sum(res[0].signal_count[b] for b in range(9)) <= 2                  # noise at 8 sigma
 
 
+def _row_rel_l2(g, e, rows_per_chunk=64):
+    """per-row rel-L2 of two [C][L] complex64 arrays, in float64, chunked so that 2^29-point spectra fit in host memory"""
+    C_ = g.shape[0]
+    err = np.zeros(C_)
+    for c0 in range(0, C_, rows_per_chunk):
+        a = g[c0:c0 + rows_per_chunk].astype(np.complex128)
+        b = e[c0:c0 + rows_per_chunk].astype(np.complex128)
+        den = np.sqrt((np.abs(b) ** 2).sum(axis=1))
+        err[c0:c0 + rows_per_chunk] = np.sqrt((np.abs(a - b) ** 2).sum(axis=1)) / np.maximum(den, 1e-300)
+    return err
+
+
+def _compare_full_size(gspec, espec, res, eres, h_series, eseries, sk_thr, snr, max_flip_rows):
+    """full-size comparison against the oracle, channel by channel. With 2^25..2^29 bins and the J1644 threshold
+    (zap above 1.5 x mean: 22 % of the noise bins) a handful of bins lie so close to the s1 threshold that the order in
+    which the mean was summed decides them (the reference's own order is device dependent). Such a flip
+    shows up as ONE frequency bin of ONE channel: the policy is checked literally — a channel may differ only if the
+    difference, taken back to the frequency domain, is concentrated in at most three bins; every other channel must
+    agree to 5e-5, SK decisions may differ only on window-edge channels, and the detector is compared on the time
+    series recomputed over the agreeing channels (directly when every channel agrees)."""
+    C_, L = gspec.shape
+    ezap = np.array([not espec[c].any() for c in range(C_)])
+    gzap = np.array([not gspec[c].any() for c in range(C_)])
+    differ = np.nonzero(gzap != ezap)[0]
+    lo, hi = _sk_window(sk_thr, L)
+    for c in differ:
+        row = (gspec[c] if ezap[c] else espec[c]).astype(np.complex128)
+        pw = np.abs(row) ** 2
+        sk = L * (pw ** 2).sum() / pw.sum() ** 2
+        edge = min(abs(sk - lo) / lo, abs(sk - hi) / hi)
+        assert edge < 50 * BORDER, f"channel {c}: SK {sk:.6f} is {edge:.2e} from the window yet decided differently"
+    both = ~gzap & ~ezap
+    err = np.zeros(C_)
+    idx = np.nonzero(both)[0]
+    err[idx] = _row_rel_l2(gspec[idx], espec[idx])
+    flipped = np.nonzero(err > 5 * REL_L2)[0]
+    assert len(flipped) <= max_flip_rows, f"{len(flipped)} channels differ (worst {err.max():.2e})"
+    for c in flipped:
+        d = np.fft.fft(gspec[c].astype(np.complex128) - espec[c].astype(np.complex128))
+        p = np.sort(np.abs(d) ** 2)[::-1]
+        assert p[:3].sum() > 0.999 * p.sum(), f"channel {c}: difference is not a handful of threshold-border bins"
+    good = both & (err <= 5 * REL_L2)
+    gi = np.nonzero(good)[0]
+    num = den = 0.0
+    for c0 in range(0, len(gi), 64):
+        a = gspec[gi[c0:c0 + 64]].astype(np.complex128)
+        b = espec[gi[c0:c0 + 64]].astype(np.complex128)
+        num += (np.abs(a - b) ** 2).sum()
+        den += (np.abs(b) ** 2).sum()
+    total = float(np.sqrt(num / den))
+    assert total < 5 * REL_L2
+    report = dict(channels=C_, sk_edge_channels=len(differ), s1_border_channels=len(flipped), rel_l2=total)
+    if len(differ) == 0 and len(flipped) == 0:
+        _compare_detect(res, eres, h_series, eseries, snr)
+        return report
+    gts = np.zeros(L)
+    ets = np.zeros(L)
+    for c0 in range(0, len(gi), 64):
+        gts += (np.abs(gspec[gi[c0:c0 + 64]].astype(np.complex128)) ** 2).sum(axis=0)
+        ets += (np.abs(espec[gi[c0:c0 + 64]].astype(np.complex128)) ** 2).sum(axis=0)
+    gts -= gts.mean()
+    ets -= ets.mean()
+    assert np.abs(gts - ets).max() < 2e-4 * np.sqrt(np.mean(ets ** 2))
+    assert abs(int(res.zero_count) - int(eres.zero_count)) <= len(differ)
+    assert res.n_boxcars == eres.n_boxcars and res.detect_enabled == eres.detect_enabled
+    for b in range(res.n_boxcars):        # counts: a flipped bin moves every time sample by ~1e-3 sigma at most
+        ev = eseries[b, :int(eres.series_length[b])].astype(np.float64)
+        near = int((np.abs(ev - eres.threshold[b]) < 2e-3 * eres.threshold[b]).sum())
+        assert abs(int(res.signal_count[b]) - int(eres.signal_count[b])) <= near
+    return report
+
+
+def test_config3_full_size_vs_oracle(ctx, oracle):
+    """BASELINE config #3 — the J1644-4559 shape of the north star — at FULL size against the CPU oracle:
+    dual polarisation (naocpsr_snap1), 2^26 samples per stream, 400 MHz, DM 562.05, C = 2^11 (rows of 2^14 through the
+    whole-row kernel), zap list, SK, boxcars to 256, with a dispersed pulse injected in both streams."""
+    import sys
+    from pathlib import Path
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+    w = bench.WORKLOADS["config3"]
+    n, C_ = 1 << w["log2n"], w["channels"]
+    L = n // 2 // C_
+    raw = bench.synth_block_with_pulse(n, 2, seed=3, w=w)
+    pairs = srtb_b200.eval_rfi_ranges(w["freq_list"])
+    cfg = make_block_config(n, -8, srtb_b200.FORMAT_NAOCPSR_SNAP1, C_, w["dm"], f_low=w["f_low"], bw=w["bw"], fs=w["fs"],
+                            avg_thr=w["avg_thr"], sk_thr=w["sk_thr"], snr=w["snr"], maxbox=w["maxbox"], pairs=pairs)
+    h_series = np.zeros((2, srtb_b200.MAX_BOXCARS, L), np.float32)
+    res = ctx.process_block(cfg, torch.from_numpy(raw.view(np.uint8)).pin_memory(), 2 * n, h_series, copy_all=True)
+    torch.cuda.synchronize()
+    assert len(res) == 2
+    t0_bin = int(n * 0.37) // (2 * C_)
+    for s_ in range(2):
+        stream = np.ascontiguousarray(raw.reshape(-1, 4)[:, 2 * s_:2 * s_ + 2]).reshape(-1)
+        cfg1 = make_block_config(n, -8, srtb_b200.FORMAT_SIMPLE, C_, w["dm"], f_low=w["f_low"], bw=w["bw"], fs=w["fs"],
+                                 avg_thr=w["avg_thr"], sk_thr=w["sk_thr"], snr=w["snr"], maxbox=w["maxbox"], pairs=pairs)
+        work, eres, eseries, _ = oracle.chain(stream.view(np.uint8), oracle_chain_config(cfg1))
+        espec = work[:n].view(np.complex64).reshape(C_, L)
+        gspec = _from_device_ptr(ctx.block_spectrum_ptr(s_), n // 2).reshape(C_, L)
+        rep = _compare_full_size(gspec, espec, res[s_], eres, h_series[s_], eseries, w["sk_thr"], w["snr"], max_flip_rows=8)
+        print(f"config 3 full size, stream {s_}: {rep}")
+        assert res[s_].signal_count[0] > 0 and int(np.argmax(h_series[s_][0, :L])) == t0_bin   # the injected pulse
+        del work, espec, gspec
+
+
+def test_config1_full_size_vs_oracle(ctx, oracle):
+    """BASELINE config #1 — the shipped srtb_config_1644-4559.cfg: 2^30 two-bit samples per block, inverted 64 MHz band,
+    DM -478.80, manual zap 1418-1422 MHz, C = 2^11 (rows of 2^18: four-sweep R2C, chirp sweep, two-sweep waterfall,
+    SK + column sums) — at FULL size against the CPU oracle (about a minute of host time and 20 GB of host memory)."""
+    n, C_ = 1 << 30, 1 << 11
+    L = n // 2 // C_
+    rng = np.random.default_rng(1644)
+    raw = rng.integers(0, 256, n // 4, dtype=np.uint8)
+    cfg = make_block_config(n, 2, srtb_b200.FORMAT_SIMPLE, C_, -478.80, f_low=1405.0 + 64 / 2, bw=-64.0, fs=128e6,
+                            avg_thr=1.5, sk_thr=1.05, snr=8.0, maxbox=256, pairs=[(1418.0, 1422.0)])
+    work, eres, eseries, _ = oracle.chain(raw, oracle_chain_config(cfg))
+    espec = work[:n].view(np.complex64).reshape(C_, L)
+    h_series = np.zeros((srtb_b200.MAX_BOXCARS, L), np.float32)
+    res = ctx.process_block(cfg, torch.from_numpy(raw).pin_memory(), n // 4, h_series, copy_all=True)
+    torch.cuda.synchronize()
+    gspec = _from_device_ptr(ctx.block_spectrum_ptr(0), n // 2).reshape(C_, L)
+    rep = _compare_full_size(gspec, espec, res[0], eres, h_series, eseries, 1.05, 8.0, max_flip_rows=64)
+    print(f"config 1 full size: {rep}")
+    assert res[0].n_boxcars == 9
+
+
 def test_dispersed_pulse_full_size_config2(ctx):
     """BASELINE config #2 at full size with a V3 injection: a 64-sample burst dispersed in
     float64 with the inverse chirp of DM 56.778 (cyclic within the block, spread over all 2^24 samples: 0.2 counts
