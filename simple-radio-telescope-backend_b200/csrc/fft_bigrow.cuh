@@ -14,8 +14,13 @@
 //     accesses (one LDS.128 / STS.128 per two points, addresses base + i * stride: no per-access integer work);
 //   * the row is padded so that every access pattern is bank-conflict free: position p = d0*B1 + d1*B2 + r
 //     (B1 = L/16, B2 = L/256) lives at d0*S1 + d1*S2 + r with S2 = B2 + R3, S1 = 16*S2 + 2;
-//   * the next row arrives by TMA bulk copies (cp.async.bulk, one per B2-element segment so that the padding is
-//     produced by the copy engine) signalled on an mbarrier;
+//   * rows arrive by TMA bulk copies (cp.async.bulk, one per B2-element segment so that the padding is produced by
+//     the copy engine), one mbarrier per chunk of B1 elements. Shared memory holds THREE half-row buffers that
+//     rotate: while row r is transformed in two of them, the first half of row r + 1 lands in the third, and its
+//     second half follows into the buffer row r frees first — stage 0 consumes chunk i while chunks i + 1.. arrive;
+//   * the detector's column sums (one accumulator per time sample, 64 KiB for 2^14) live in TENSOR MEMORY, not in
+//     shared memory: every thread owns 32 cells of its warp's TMEM lane quadrant (tcgen05.ld / tcgen05.st,
+//     SASS LDTM / STTM) — the tensor cores have no work on this path, their 256 KiB accumulator file does;
 //   * twiddles: stage 0 from W_L^j by repeated multiplication, stages 1 and 2 from small shared-memory tables;
 //   * the chirp phase is evaluated in fp64 like the reference; 1/f comes from one correctly rounded reciprocal per
 //     thread and Newton steps from the neighbouring bin: one step when (B1*df/f)^2 <= 2^-52 (the reciprocal is then
@@ -34,17 +39,50 @@ struct bigrow {
   static constexpr int R3 = L / 4096;
   static constexpr int B1 = L / 16, B2 = L / 256;
   static constexpr int S2 = B2 + R3, S1 = 16 * S2 + 2;
-  static constexpr int BUF = 16 * S1;       // padded row, elements
+  static constexpr int HALF = 8 * S1;       // half a padded row (chunks d0 = 0..7 or 8..15), elements
   static constexpr int NT = L / 32;         // threads: 32 points each
   static constexpr int NW = NT / 32;
   static constexpr int CTAS = (LOGL == 13) ? 2 : 1;
+  static constexpr int TMEM_COLS = NW * 8;  // 32 accumulator cells per thread: (NW / 4) column blocks of 32 per lane quadrant
   static constexpr int TABN = B1 + 15 * B2 + 15 * R3;  // W_L^j | W_B1^{i j} [15][B2] | W_B2^{i j} [15][R3]
-  static constexpr size_t off_colacc = (size_t)BUF * sizeof(float2);
-  __host__ __device__ static constexpr size_t off_tab(bool sk) { return off_colacc + (sk ? (size_t)BUF * sizeof(float) : 0); }
-  __host__ __device__ static constexpr size_t off_mbar(bool sk) { return off_tab(sk) + (size_t)TABN * sizeof(float2); }
-  __host__ __device__ static constexpr size_t off_red(bool sk) { return off_mbar(sk) + 128; }  // 16 mbarriers
-  __host__ __device__ static constexpr size_t bytes(bool sk) { return off_red(sk) + 4 * 32 * sizeof(float); }
+  static constexpr size_t off_tab = 3 * (size_t)HALF * sizeof(float2);
+  static constexpr size_t off_mbar = off_tab + (size_t)TABN * sizeof(float2);
+  static constexpr size_t off_red = off_mbar + 24 * 8 + 64;   // 3 buffers x 8 chunk barriers, TMEM base address
+  static constexpr size_t bytes = off_red + 4 * 32 * sizeof(float);
 };
+
+// ---- tensor memory as an accumulator file: 32 consecutive columns of the calling thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+      "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+      "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+      "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // a[i] *= w^i, i = 1..15 (powers at most four multiplications deep)
 __device__ __forceinline__ void bigrow_twiddle_powers(float2 (&a)[16], const float2 w1) {
@@ -113,97 +151,132 @@ __device__ __forceinline__ float2 bigrow_chirp_point(float2 v, double f, double 
   return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
 }
 
-// CHIRP: 0 = plain transform; s1 + chirp on load with 1 = one-step Newton reciprocals, 3 = two steps, 2 = exact reciprocals
+// CHIRP: 0 = plain transform; otherwise s1 + chirp on load, 1/f of successive bins by Newton steps from the neighbour:
+//   1 = one step along a butterfly's inputs (B1 bins apart) and one to the adjacent bin, 3 = two and one,
+//   4 = two and two, 2 = a correctly rounded reciprocal for every bin (widely spaced bins of short test blocks)
 template <int LOGL, bool FWD, bool SK, int CHIRP>
 __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
     fft_bigrow_kernel(const float2* __restrict__ in, float2* __restrict__ out, unsigned nrows,
                       const float2* __restrict__ tabs, row_sk_params skp, row_chirp_params cp) {
   using C = bigrow<LOGL>;
   constexpr int L = C::L, R3 = C::R3, B1 = C::B1, B2 = C::B2, S1 = C::S1, S2 = C::S2, NT = C::NT, NW = C::NW;
+  constexpr int HALF = C::HALF;
   extern __shared__ __align__(128) unsigned char smraw[];
-  float2* const buf = reinterpret_cast<float2*>(smraw);
-  float* const colacc = reinterpret_cast<float*>(smraw + C::off_colacc);  // padded like buf (SK only)
-  float2* const T0 = reinterpret_cast<float2*>(smraw + C::off_tab(SK));
+  float2* const hbuf = reinterpret_cast<float2*>(smraw);  // three half-row buffers
+  float2* const T0 = reinterpret_cast<float2*>(smraw + C::off_tab);
   float2* const T1 = T0 + B1;
   float2* const T2 = T1 + 15 * B2;
-  uint64_t* const mbar = reinterpret_cast<uint64_t*>(smraw + C::off_mbar(SK));
-  float* const red = reinterpret_cast<float*>(smraw + C::off_red(SK));  // [2 slots][s2 | s4][32]
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(smraw + C::off_mbar);  // [3 buffers][8 chunks]
+  uint32_t* const tmem_base_s = reinterpret_cast<uint32_t*>(smraw + C::off_mbar + 24 * 8);
+  float* const red = reinterpret_cast<float*>(smraw + C::off_red);  // [2 slots][s2 | s4][32]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
   for (int i = tid; i < C::TABN; i += NT) T0[i] = __ldg(&tabs[i]);
-  if constexpr (SK)
-    for (int i = tid; i < C::BUF; i += NT) colacc[i] = 0.f;
-  if (tid < 16) mbar_init(&mbar[tid], 1);
+  if (tid < 24) mbar_init(&mbar[tid], 1);
   if (tid == 0) fence_mbar_init();
+  uint32_t my_tmem = 0;
+  if constexpr (SK) {
+    if (wid == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
+                   "n"(C::TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+  }
   __syncthreads();
-
-  // warp 0: fetch one row into the padded layout, one bulk copy per B2-element segment. The row is sixteen chunks of
-  // B1 elements (d0 = 0..15), each signalled on its own mbarrier, fetched in order: stage 0 consumes chunk i (its
-  // butterfly input i) while the later chunks are still in flight, so most of the load hides behind the chirp.
-  auto issue = [&](unsigned row) {
-    fence_proxy_async();
-    if (lane < 16) mbar_expect_tx(&mbar[lane], (uint32_t)(B1 * sizeof(float2)));
-    __syncwarp();
-    const float2* src = in + (size_t)row * L;
+  if constexpr (SK) {
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // this thread's 32 column-sum cells: lane `lane` of quadrant wid & 3, columns 32 (wid >> 2) .. + 31
+    my_tmem = *tmem_base_s + ((uint32_t)(32 * (wid & 3)) << 16) + (uint32_t)((wid >> 2) * 32);
+    float z[32];
 #pragma unroll
-    for (int seg = lane; seg < 256; seg += 32)  // seg >> 4 = chunk: two chunks per round, in chunk order
-      bulk_g2s(buf + (seg >> 4) * S1 + (seg & 15) * S2, src + seg * B2, (uint32_t)(B2 * sizeof(float2)), &mbar[seg >> 4]);
+    for (int i = 0; i < 32; i++) z[i] = 0.f;
+    tmem_st32(my_tmem, z);
+  }
+
+  // warp 0: fetch half a row (chunks d0 = 8 which .. 8 which + 7) into half buffer hb, one bulk copy per B2-element
+  // segment (the copy engine produces the padding), each chunk of B1 elements signalled on its own mbarrier
+  auto issue_half = [&](unsigned row, int which, int hb) {
+    fence_proxy_async();
+    if (lane < 8) mbar_expect_tx(&mbar[hb * 8 + lane], (uint32_t)(B1 * sizeof(float2)));
+    __syncwarp();
+    const float2* src = in + (size_t)row * L + (size_t)which * 8 * B1;
+    float2* dst = hbuf + hb * HALF;
+#pragma unroll
+    for (int seg = lane; seg < 128; seg += 32)  // seg >> 4 = chunk within the half: two chunks per round, in order
+      bulk_g2s(dst + (seg >> 4) * S1 + (seg & 15) * S2, src + seg * B2, (uint32_t)(B2 * sizeof(float2)),
+               &mbar[hb * 8 + (seg >> 4)]);
   };
 
   float limit = 0.f;
   if constexpr (CHIRP) limit = cp.threshold * __ldg(cp.mean);
 
+  // Rotation of the three half buffers: row `it` of this CTA has chunks 0..7 in A = (2 it) % 3 and chunks 8..15 in
+  // B = (2 it + 1) % 3; the third buffer receives chunks 0..7 of the next row meanwhile. Buffer A has been filled
+  // floor(2 it / 3) times before, B floor((2 it + 1) / 3) times: the mbarrier phase parities.
   unsigned row = blockIdx.x;
-  if (row < nrows && wid == 0) issue(row);
+  if (wid == 0) {
+    if (row < nrows) {
+      issue_half(row, 0, 0);
+      issue_half(row, 1, 1);
+    }
+    if (row + gridDim.x < nrows) issue_half(row + gridDim.x, 0, 2);
+  }
   for (unsigned it = 0; row < nrows; row += gridDim.x, it++) {
+    const int hA = (2 * it) % 3, hB = (2 * it + 1) % 3;
+    const unsigned parA = ((2 * it) / 3) & 1, parB = ((2 * it + 1) / 3) & 1;
+    float2* const bufA = hbuf + hA * HALF;
+    float2* const bufB = hbuf + hB * HALF;
+    auto half_of = [&](int d0) { return (d0 < 8 ? bufA : bufB) + (d0 & 7) * S1; };  // first element of chunk d0
     // ---- stage 0: butterflies over d0 (stride S1), pair j = 2 tid, 2 tid + 1 of [0, B1)
     {
       const int j = 2 * tid;
-      float2* const p = buf + (j / B2) * S2 + (j % B2);
+      const int off = (j / B2) * S2 + (j % B2);
+      float2* const pa = bufA + off;
+      float2* const pb = bufB + off;
       float2 a[16], b[16];
-      if constexpr (!CHIRP) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          mbar_wait(&mbar[i], it & 1);
-          const float4 q = *reinterpret_cast<const float4*>(p + i * S1);
-          a[i] = make_float2(q.x, q.y);
-          b[i] = make_float2(q.z, q.w);
-        }
-      }
-      if constexpr (CHIRP) {
-        // bin index of a[i] is row*L + j + i*B1 (b[i]: + 1); f = f_min + df * index in fp64
+      if constexpr (CHIRP != 0) {
+        // s1 + chirp as a pass of its own over the thread's sixteen pairs, written back in place: no butterfly
+        // registers are live yet, so several bins' fp64 phase chains are in flight at once (the thread re-reads only
+        // what it wrote itself: no barrier). Chunk i is consumed as soon as it has landed.
         double idx = (double)((size_t)row * L + j);
         double fa = fma(cp.df, idx, cp.f_min);
         double ra = __drcp_rn(fa);
-        // 1/f of the next bin: Newton steps from the neighbour's reciprocal (each squares the relative error, which
-        // starts at bin distance * df / f), or a correctly rounded reciprocal per bin (CHIRP == 2)
-        auto refine = [&](double r, double f) {
-          if constexpr (CHIRP == 1) {
-            return fma(r, fma(-f, r, 1.0), r);  // one Newton step (the host checked that it is good to 1 ulp)
-          } else if constexpr (CHIRP == 3) {
-            r = fma(r, fma(-f, r, 1.0), r);     // two steps
-            return fma(r, fma(-f, r, 1.0), r);
-          } else {
-            return __drcp_rn(f);                // widely spaced bins (short test blocks): exact reciprocal
-          }
+        auto newton = [](double r, double f) { return fma(r, fma(-f, r, 1.0), r); };
+        auto refine_far = [&](double r, double f) {   // bin B1 further on
+          if constexpr (CHIRP == 2) return __drcp_rn(f);
+          r = newton(r, f);
+          if constexpr (CHIRP >= 3) r = newton(r, f);
+          return r;
         };
-#pragma unroll
+        auto refine_near = [&](double r, double f) {  // adjacent bin
+          if constexpr (CHIRP == 2) return __drcp_rn(f);
+          r = newton(r, f);
+          if constexpr (CHIRP == 4) r = newton(r, f);
+          return r;
+        };
+#pragma unroll 4
         for (int i = 0; i < 16; i++) {
           if (i > 0) {
             idx += (double)B1;
             fa = fma(cp.df, idx, cp.f_min);
-            ra = refine(ra, fa);
+            ra = refine_far(ra, fa);
           }
-          mbar_wait(&mbar[i], it & 1);  // chunk i has landed (later chunks still arriving)
-          {
-            const float4 q = *reinterpret_cast<const float4*>(p + i * S1);
-            a[i] = make_float2(q.x, q.y);
-            b[i] = make_float2(q.z, q.w);
-          }
-          a[i] = bigrow_chirp_point(a[i], fa, ra, cp, limit);
+          float2* const p = (i < 8 ? pa : pb) + (i & 7) * S1;
+          mbar_wait(&mbar[(i < 8 ? hA : hB) * 8 + (i & 7)], i < 8 ? parA : parB);
+          const float4 q = *reinterpret_cast<const float4*>(p);
+          const float2 ya = bigrow_chirp_point(make_float2(q.x, q.y), fa, ra, cp, limit);
           const double fb = fma(cp.df, idx + 1.0, cp.f_min);
-          b[i] = bigrow_chirp_point(b[i], fb, refine(ra, fb), cp, limit);
+          const float2 yb = bigrow_chirp_point(make_float2(q.z, q.w), fb, refine_near(ra, fb), cp, limit);
+          *reinterpret_cast<float4*>(p) = make_float4(ya.x, ya.y, yb.x, yb.y);
         }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        if constexpr (CHIRP == 0) mbar_wait(&mbar[(i < 8 ? hA : hB) * 8 + (i & 7)], i < 8 ? parA : parB);
+        const float4 q = *reinterpret_cast<const float4*>((i < 8 ? pa : pb) + (i & 7) * S1);
+        a[i] = make_float2(q.x, q.y);
+        b[i] = make_float2(q.z, q.w);
       }
       dft16<FWD>(a);
       dft16<FWD>(b);
@@ -212,19 +285,19 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
       bigrow_twiddle_powers(b, make_float2(w.z, w.w));
 #pragma unroll
       for (int i = 0; i < 16; i++)
-        *reinterpret_cast<float4*>(p + i * S1) = make_float4(a[i].x, a[i].y, b[i].x, b[i].y);
+        *reinterpret_cast<float4*>((i < 8 ? pa : pb) + (i & 7) * S1) = make_float4(a[i].x, a[i].y, b[i].x, b[i].y);
     }
     __syncthreads();
     // ---- stage 1: block d0, butterflies over d1 (stride S2), pair of [0, B2)
     {
       const int d0 = tid / (B2 / 2), jp = tid % (B2 / 2);
-      bigrow_stage_table<FWD, S2, B2>(buf + d0 * S1 + 2 * jp, T1 + 2 * jp);
+      bigrow_stage_table<FWD, S2, B2>(half_of(d0) + 2 * jp, T1 + 2 * jp);
     }
     __syncthreads();
     // ---- stage 2: block (d0, d1), butterflies over d2 (stride R3), pair of [0, R3)
     {
       const int blk = tid / (R3 / 2), jp = tid % (R3 / 2);
-      bigrow_stage_table<FWD, R3, R3>(buf + (blk >> 4) * S1 + (blk & 15) * S2 + 2 * jp, T2 + 2 * jp);
+      bigrow_stage_table<FWD, R3, R3>(half_of(blk >> 4) + (blk & 15) * S2 + 2 * jp, T2 + 2 * jp);
     }
     __syncthreads();
     // ---- last stage, pass 1: radix R3 on R3 contiguous elements, in place; row statistics for SK
@@ -235,7 +308,7 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
         // lanes vary (d0 bit 0, d2 bits 0-1): the eight 16-byte chunks of a quarter warp are distinct mod 8
         const int u = (tid >> 3) + (NT / 8) * g;
         const int d0 = (lane & 1) | ((u & 7) << 1), d2 = ((lane >> 1) & 3) | ((u >> 7) << 2), d1 = (u >> 3) & 15;
-        float2* const p = buf + d0 * S1 + d1 * S2 + d2 * 4;
+        float2* const p = half_of(d0) + d1 * S2 + d2 * 4;
         const float4 q0 = *reinterpret_cast<const float4*>(p), q1 = *reinterpret_cast<const float4*>(p + 2);
         float2 x0 = make_float2(q0.x, q0.y), x1 = make_float2(q0.z, q0.w);
         float2 x2 = make_float2(q1.x, q1.y), x3 = make_float2(q1.z, q1.w);
@@ -253,7 +326,7 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
 #pragma unroll
       for (int g = 0; g < 16; g++) {
         const int G = tid + NT * g;  // pair index: d2 = G & 15, d1 = (G >> 4) & 15, d0 = G >> 8
-        float2* const p = buf + (G >> 8) * S1 + ((G >> 4) & 15) * S2 + (G & 15) * 2;
+        float2* const p = half_of(G >> 8) + ((G >> 4) & 15) * S2 + (G & 15) * 2;
         const float4 q = *reinterpret_cast<const float4*>(p);
         const float2 y0 = make_float2(q.x + q.z, q.y + q.w), y1 = make_float2(q.x - q.z, q.y - q.w);
         *reinterpret_cast<float4*>(p) = make_float4(y0.x, y0.y, y1.x, y1.y);
@@ -295,7 +368,7 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
     // ---- pass 2: natural-order store. lane -> (d0, d1 bit 0): 32 consecutive output indices per instruction
     {
       const int pd0 = lane & 15, pd1 = ((wid & 7) << 1) | (lane >> 4), sel = wid >> 3;
-      const int base = pd0 * S1 + pd1 * S2 + 2 * sel;
+      const float2* const base = half_of(pd0) + pd1 * S2 + 2 * sel;
       float2* const o = out + (size_t)row * L + (pd0 + 16 * pd1 + 4096 * (2 * sel));
       if (zap) {
 #pragma unroll
@@ -304,32 +377,43 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
           o[256 * i2 + 4096] = make_float2(0.f, 0.f);
         }
       } else {
+        float acc[SK ? 32 : 1];
+        if constexpr (SK) tmem_ld32(my_tmem, acc);
 #pragma unroll
         for (int i2 = 0; i2 < 16; i2++) {
-          const float4 q = *reinterpret_cast<const float4*>(buf + base + i2 * R3);
+          const float4 q = *reinterpret_cast<const float4*>(base + i2 * R3);
           o[256 * i2] = make_float2(q.x, q.y);          // k = d0 + 16 d1 + 256 d2 + 4096 d3, d3 = 2 sel
           o[256 * i2 + 4096] = make_float2(q.z, q.w);   // d3 = 2 sel + 1
           if constexpr (SK) {
-            float2* const ca = reinterpret_cast<float2*>(colacc + base + i2 * R3);
-            float2 acc = *ca;
-            acc.x += q.x * q.x + q.y * q.y;
-            acc.y += q.z * q.z + q.w * q.w;
-            *ca = acc;
+            acc[2 * i2] += q.x * q.x + q.y * q.y;
+            acc[2 * i2 + 1] += q.z * q.z + q.w * q.w;
           }
         }
+        if constexpr (SK) tmem_st32(my_tmem, acc);
       }
     }
-    __syncthreads();  // the row buffer is free: fetch the next row
-    const unsigned nxt = row + gridDim.x;
-    if (nxt < nrows && wid == 0) issue(nxt);
+    __syncthreads();  // the row's buffers are free: second half of the next row, first half of the one after
+    if (wid == 0) {
+      const unsigned nxt = row + gridDim.x, nxt2 = row + 2 * gridDim.x;
+      if (nxt < nrows) issue_half(nxt, 1, hA);     // B of row it + 1 is A of row it
+      if (nxt2 < nrows) issue_half(nxt2, 0, hB);   // A of row it + 2 is B of row it
+    }
   }
   if constexpr (SK) {
     // column sums of the surviving rows this CTA transformed: one partial row per CTA, natural order
-    __syncthreads();
-    for (unsigned k = tid; k < (unsigned)L; k += NT) {
-      const int idx = (k & 15) * S1 + ((k >> 4) & 15) * S2 + ((k >> 8) & 15) * R3 + (k >> 12);
-      if (k < skp.ts_count) skp.partial[(size_t)blockIdx.x * skp.ts_count + k] = colacc[idx];
+    float acc[32];
+    tmem_ld32(my_tmem, acc);
+    const int pd0 = lane & 15, pd1 = ((wid & 7) << 1) | (lane >> 4), sel = wid >> 3;
+    float* const dst = skp.partial + (size_t)blockIdx.x * skp.ts_count;
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      const unsigned k = (unsigned)(pd0 + 16 * pd1 + 256 * (c >> 1) + 4096 * (2 * sel + (c & 1)));
+      if (k < skp.ts_count) dst[k] = acc[c];
     }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (wid == 0)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_base_s), "n"(C::TMEM_COLS));
   }
 }
 

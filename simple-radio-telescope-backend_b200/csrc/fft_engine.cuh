@@ -683,7 +683,7 @@ struct row_chirp_params {
   double f_min, df, inv_fc, f_c, ddm;
   const float* mean;      // mean |X|^2 of the block (s1 statistic), finalised by the preceding kernel
   float threshold, coef;  // s1: zap above threshold * mean, scale the rest by coef
-  int newton;             // whole-row kernel: Newton steps per reciprocal (1 or 2), 0 = exact reciprocal per bin
+  int newton;             // whole-row kernel: reciprocal mode = the kernel's CHIRP template value (1, 3, 4; 2 = exact)
 };
 
 // ---------------------------------------------------------------------------------

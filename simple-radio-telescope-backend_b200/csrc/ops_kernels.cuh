@@ -824,19 +824,27 @@ __global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __
   if (tid == 0) s_mean = (float)total / (float)ts_count;   // map_average: sum / float(count)
   __syncthreads();
   const float mean = s_mean;
-  double carry = 0.0;  // running sum of everything before this tile of blockDim.x elements
-  for (size_t base = 0; base < ts_count; base += nt) {
-    const size_t i = base + tid;
-    float v = 0.f;
-    if (i < ts_count) {
-      v = __ldcg(&ts[i]) - mean;
-      ts[i] = v;
+  // inclusive scan: super-tiles of 16 * blockDim.x elements; a thread owns 16 CONTIGUOUS elements (all its loads are
+  // issued up front), scans them in fp64, and one block-wide exclusive scan of the thread totals supplies the offsets
+  double carry = 0.0;
+  const size_t tile = (size_t)16 * nt;
+  for (size_t base = 0; base < ts_count; base += tile) {
+    const size_t i0 = base + (size_t)16 * tid;
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = (i0 + e < ts_count) ? __ldcg(&ts[i0 + e]) - mean : 0.f;
+    double run[16];
+    double t = 0.0;
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      t += (double)v[e];
+      run[e] = t;
     }
-    double incl = (double)v;  // inclusive scan of the tile in fp64: warp shuffles, then the 32 warp totals
+    double incl = t;  // inclusive scan of the thread totals across the warp, then across the 32 warps
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const double t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lx >= o) incl += t;
+      const double u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lx >= o) incl += u;
     }
     if (lx == 31) warp_tot[ly] = incl;
     __syncthreads();
@@ -845,15 +853,20 @@ __global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __
       double wi = w;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (lx >= o) wi += t;
+        const double u = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lx >= o) wi += u;
       }
       warp_tot[lx] = wi - w;                 // exclusive offset of warp lx
       if (lx == 31) smd[0] = wi;             // tile total
     }
     __syncthreads();
-    const double run = carry + warp_tot[ly] + incl;
-    if (i < ts_count) acc[i] = (float)run;
+    const double off = carry + warp_tot[ly] + (incl - t);
+#pragma unroll
+    for (int e = 0; e < 16; e++)
+      if (i0 + e < ts_count) {
+        ts[i0 + e] = v[e];
+        acc[i0 + e] = (float)(off + run[e]);
+      }
     carry += smd[0];
     __syncthreads();
   }

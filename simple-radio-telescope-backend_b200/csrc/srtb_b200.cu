@@ -894,7 +894,7 @@ static int launch_bigrow(srtb_b200_ctx* ctx, const float2* in, float2* out, size
   if (int rc = get_bigrow_tables<LOGL>(ctx, FWD, &tabs)) return rc;
   unsigned grid = 1;
   auto go = [&](auto kern, bool with_sk) -> int {
-    const size_t smem = C::bytes(with_sk);
+    const size_t smem = C::bytes;
     if (int rc = persistent_grid(ctx, kern, C::NT, smem, smem, nrows, &grid)) return rc;
     row_sk_params p{};
     if (with_sk) {
@@ -913,7 +913,8 @@ static int launch_bigrow(srtb_b200_ctx* ctx, const float2* in, float2* out, size
   };
   if constexpr (!FWD) {
     if (sk && chirp && chirp->newton == 1) return go(fft_bigrow_kernel<LOGL, false, true, 1>, true);
-    if (sk && chirp && chirp->newton == 2) return go(fft_bigrow_kernel<LOGL, false, true, 3>, true);
+    if (sk && chirp && chirp->newton == 3) return go(fft_bigrow_kernel<LOGL, false, true, 3>, true);
+    if (sk && chirp && chirp->newton == 4) return go(fft_bigrow_kernel<LOGL, false, true, 4>, true);
     if (sk && chirp) return go(fft_bigrow_kernel<LOGL, false, true, 2>, true);
     if (sk) return go(fft_bigrow_kernel<LOGL, false, true, 0>, true);
   }
@@ -1533,8 +1534,14 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
       const double delta = (double)(time_count / 16) * std::fabs(cpv.df) / fa;
       const double q = (cpv.f_c - cpv.f_min) * cpv.inv_fc;
       const double kmax = std::max(1.0, std::fabs(cpv.ddm) / fa * q * q);
+      // two distances: B1 bins (along a butterfly's inputs) and 1 bin (the pair's second column)
       const double d2 = delta * delta;
-      cpv.newton = (d2 <= 0x1p-52) ? 1 : ((d2 * d2 * kmax < 1e-9) ? 2 : 0);
+      const double dn = std::fabs(cpv.df) / fa, dn2 = dn * dn;
+      const int far_steps = (d2 <= 0x1p-52) ? 1 : ((d2 * d2 * kmax < 1e-9) ? 2 : 0);
+      const int near_steps = (dn2 <= 0x1p-52) ? 1 : ((dn2 * dn2 * kmax < 1e-9) ? 2 : 0);
+      // kernel variants: 1 = (1, 1), 3 = (2, 1), 4 = (2, 2), 2 = exact
+      cpv.newton = (far_steps == 0 || near_steps == 0) ? 2
+                   : (far_steps == 1 ? 1 : (near_steps == 1 ? 3 : 4));
     }
     const float2* s_ = src ? src : x;
     rc = (time_count == 8192) ? launch_bigrow<13, false>(ctx, s_, x, chan_count, &p, chirp ? &cpv : nullptr, &chunks)

@@ -856,7 +856,8 @@ def _row_rel_l2(g, e, rows_per_chunk=64):
     return err
 
 
-def _compare_full_size(gspec, espec, res, eres, h_series, eseries, sk_thr, snr, max_flip_rows):
+def _compare_full_size(gspec, espec, res, eres, h_series, eseries, sk_thr, snr, max_flip_rows, s1_power=None,
+                       s1_limit=None):
     """full-size comparison against the oracle, channel by channel. With 2^25..2^29 bins and the J1644 threshold
     (zap above 1.5 x mean: 22 % of the noise bins) a handful of bins lie so close to the s1 threshold that the order in
     which the mean was summed decides them (the reference's own order is device dependent). Such a flip
@@ -882,9 +883,13 @@ def _compare_full_size(gspec, espec, res, eres, h_series, eseries, sk_thr, snr, 
     flipped = np.nonzero(err > 5 * REL_L2)[0]
     assert len(flipped) <= max_flip_rows, f"{len(flipped)} channels differ (worst {err.max():.2e})"
     for c in flipped:
-        d = np.fft.fft(gspec[c].astype(np.complex128) - espec[c].astype(np.complex128))
-        p = np.sort(np.abs(d) ** 2)[::-1]
-        assert p[:3].sum() > 0.999 * p.sum(), f"channel {c}: difference is not a handful of threshold-border bins"
+        d = np.abs(np.fft.fft(gspec[c].astype(np.complex128) - espec[c].astype(np.complex128))) ** 2
+        top = np.argsort(d)[::-1][:3]
+        assert d[top].sum() > 0.999 * d.sum(), f"channel {c}: difference is not a handful of threshold-border bins"
+        if s1_power is not None:   # the bins that flipped really sit on the s1 threshold (float64 |X|^2 of the block)
+            for j in top[d[top] > 1e-3 * d.sum()]:
+                edge = abs(s1_power[c * L + j] / s1_limit - 1)
+                assert edge < BORDER, f"channel {c} bin {j}: |X|^2 is {edge:.2e} from the s1 threshold yet decided differently"
     good = both & (err <= 5 * REL_L2)
     gi = np.nonzero(good)[0]
     num = den = 0.0
@@ -943,7 +948,10 @@ def test_config3_full_size_vs_oracle(ctx, oracle):
         work, eres, eseries, _ = oracle.chain(stream.view(np.uint8), oracle_chain_config(cfg1))
         espec = work[:n].view(np.complex64).reshape(C_, L)
         gspec = _from_device_ptr(ctx.block_spectrum_ptr(s_), n // 2).reshape(C_, L)
-        rep = _compare_full_size(gspec, espec, res[s_], eres, h_series[s_], eseries, w["sk_thr"], w["snr"], max_flip_rows=8)
+        pw = np.abs(np.fft.rfft(stream.astype(np.float64))[:n // 2]) ** 2     # float64 truth of the s1 statistic
+        rep = _compare_full_size(gspec, espec, res[s_], eres, h_series[s_], eseries, w["sk_thr"], w["snr"],
+                                 max_flip_rows=64, s1_power=pw, s1_limit=np.float64(np.float32(w["avg_thr"])) * pw.mean())
+        del pw
         print(f"config 3 full size, stream {s_}: {rep}")
         assert res[s_].signal_count[0] > 0 and int(np.argmax(h_series[s_][0, :L])) == t0_bin   # the injected pulse
         del work, espec, gspec
