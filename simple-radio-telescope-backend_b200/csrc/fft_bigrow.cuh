@@ -12,10 +12,11 @@
 //     digit-reversed order in shared memory, natural order restored by the final store;
 //   * a thread owns TWO adjacent butterflies per stage (32 points) and moves them with 16-byte shared-memory
 //     accesses (one LDS.128 / STS.128 per two points, addresses base + i * stride: no per-access integer work);
-//   * the row is padded so that every access pattern is bank-conflict free: position p = d0*B1 + d1*B2 + r
-//     (B1 = L/16, B2 = L/256) lives at d0*S1 + d1*S2 + r with S2 = B2 + R3, S1 = 16*S2 + 2;
-//   * rows arrive by TMA bulk copies (cp.async.bulk, one per B2-element segment so that the padding is produced by
-//     the copy engine), one mbarrier per chunk of B1 elements. Shared memory holds THREE half-row buffers that
+//   * the sixteen chunks of a row (d0 = 0..15, B1 = L/16 elements each) are stored S1 = B1 + 2 elements apart: the
+//     chunk stride is odd in 16-byte units, so lanes that differ in d0 never meet in a bank group, and every other
+//     access pattern runs over contiguous pairs — all conflict free, while each chunk stays ONE contiguous TMA copy;
+//   * rows arrive by TMA bulk copies (cp.async.bulk, one per chunk: sixteen 8 KiB copies per 2^14-point row), each
+//     signalled on its own mbarrier. Shared memory holds THREE half-row buffers that
 //     rotate: while row r is transformed in two of them, the first half of row r + 1 lands in the third, and its
 //     second half follows into the buffer row r frees first — stage 0 consumes chunk i while chunks i + 1.. arrive;
 //   * the detector's column sums (one accumulator per time sample, 64 KiB for 2^14) live in TENSOR MEMORY, not in
@@ -38,7 +39,7 @@ struct bigrow {
   static constexpr int L = 1 << LOGL;
   static constexpr int R3 = L / 4096;
   static constexpr int B1 = L / 16, B2 = L / 256;
-  static constexpr int S2 = B2 + R3, S1 = 16 * S2 + 2;
+  static constexpr int S2 = B2, S1 = B1 + 2;  // chunks of B1 elements, contiguous inside, two elements apart
   static constexpr int HALF = 8 * S1;       // half a padded row (chunks d0 = 0..7 or 8..15), elements
   static constexpr int NT = L / 32;         // threads: 32 points each
   static constexpr int NW = NT / 32;
@@ -194,18 +195,15 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
     tmem_st32(my_tmem, z);
   }
 
-  // warp 0: fetch half a row (chunks d0 = 8 which .. 8 which + 7) into half buffer hb, one bulk copy per B2-element
-  // segment (the copy engine produces the padding), each chunk of B1 elements signalled on its own mbarrier
+  // warp 0, lanes 0..7: fetch half a row (chunks d0 = 8 which .. 8 which + 7) into half buffer hb, one bulk copy per
+  // chunk, each signalled on its own mbarrier
   auto issue_half = [&](unsigned row, int which, int hb) {
     fence_proxy_async();
-    if (lane < 8) mbar_expect_tx(&mbar[hb * 8 + lane], (uint32_t)(B1 * sizeof(float2)));
-    __syncwarp();
-    const float2* src = in + (size_t)row * L + (size_t)which * 8 * B1;
-    float2* dst = hbuf + hb * HALF;
-#pragma unroll
-    for (int seg = lane; seg < 128; seg += 32)  // seg >> 4 = chunk within the half: two chunks per round, in order
-      bulk_g2s(dst + (seg >> 4) * S1 + (seg & 15) * S2, src + seg * B2, (uint32_t)(B2 * sizeof(float2)),
-               &mbar[hb * 8 + (seg >> 4)]);
+    if (lane < 8) {
+      mbar_expect_tx(&mbar[hb * 8 + lane], (uint32_t)(B1 * sizeof(float2)));
+      bulk_g2s(hbuf + hb * HALF + lane * S1, in + (size_t)row * L + (size_t)(which * 8 + lane) * B1,
+               (uint32_t)(B1 * sizeof(float2)), &mbar[hb * 8 + lane]);
+    }
   };
 
   float limit = 0.f;
@@ -231,9 +229,8 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
     // ---- stage 0: butterflies over d0 (stride S1), pair j = 2 tid, 2 tid + 1 of [0, B1)
     {
       const int j = 2 * tid;
-      const int off = (j / B2) * S2 + (j % B2);
-      float2* const pa = bufA + off;
-      float2* const pb = bufB + off;
+      float2* const pa = bufA + j;
+      float2* const pb = bufB + j;
       float2 a[16], b[16];
       if constexpr (CHIRP != 0) {
         // s1 + chirp as a pass of its own over the thread's sixteen pairs, written back in place: no butterfly
@@ -294,10 +291,10 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
       bigrow_stage_table<FWD, S2, B2>(half_of(d0) + 2 * jp, T1 + 2 * jp);
     }
     __syncthreads();
-    // ---- stage 2: block (d0, d1), butterflies over d2 (stride R3), pair of [0, R3)
+    // ---- stage 2: block (d0, d1), butterflies over d2 (stride R3), pair of [0, R3); lanes vary d0
     {
-      const int blk = tid / (R3 / 2), jp = tid % (R3 / 2);
-      bigrow_stage_table<FWD, R3, R3>(half_of(blk >> 4) + (blk & 15) * S2 + 2 * jp, T2 + 2 * jp);
+      const int d0 = tid & 15, rest = tid >> 4, jp = rest % (R3 / 2), d1 = rest / (R3 / 2);
+      bigrow_stage_table<FWD, R3, R3>(half_of(d0) + d1 * S2 + 2 * jp, T2 + 2 * jp);
     }
     __syncthreads();
     // ---- last stage, pass 1: radix R3 on R3 contiguous elements, in place; row statistics for SK
@@ -305,10 +302,8 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
     if constexpr (R3 == 4) {
 #pragma unroll
       for (int g = 0; g < 8; g++) {
-        // lanes vary (d0 bit 0, d2 bits 0-1): the eight 16-byte chunks of a quarter warp are distinct mod 8
-        const int u = (tid >> 3) + (NT / 8) * g;
-        const int d0 = (lane & 1) | ((u & 7) << 1), d2 = ((lane >> 1) & 3) | ((u >> 7) << 2), d1 = (u >> 3) & 15;
-        float2* const p = half_of(d0) + d1 * S2 + d2 * 4;
+        const int rest = (tid >> 4) + (NT / 16) * g;  // lanes vary d0; (d1, d2) = rest
+        float2* const p = half_of(tid & 15) + (rest >> 4) * S2 + (rest & 15) * 4;
         const float4 q0 = *reinterpret_cast<const float4*>(p), q1 = *reinterpret_cast<const float4*>(p + 2);
         float2 x0 = make_float2(q0.x, q0.y), x1 = make_float2(q0.z, q0.w);
         float2 x2 = make_float2(q1.x, q1.y), x3 = make_float2(q1.z, q1.w);
@@ -325,8 +320,8 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
     } else {
 #pragma unroll
       for (int g = 0; g < 16; g++) {
-        const int G = tid + NT * g;  // pair index: d2 = G & 15, d1 = (G >> 4) & 15, d0 = G >> 8
-        float2* const p = half_of(G >> 8) + ((G >> 4) & 15) * S2 + (G & 15) * 2;
+        const int rest = (tid >> 4) + (NT / 16) * g;  // lanes vary d0; (d1, d2) = rest
+        float2* const p = half_of(tid & 15) + (rest >> 4) * S2 + (rest & 15) * 2;
         const float4 q = *reinterpret_cast<const float4*>(p);
         const float2 y0 = make_float2(q.x + q.z, q.y + q.w), y1 = make_float2(q.x - q.z, q.y - q.w);
         *reinterpret_cast<float4*>(p) = make_float4(y0.x, y0.y, y1.x, y1.y);

@@ -833,13 +833,9 @@ __global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __
     float v[16];
 #pragma unroll
     for (int e = 0; e < 16; e++) v[e] = (i0 + e < ts_count) ? __ldcg(&ts[i0 + e]) - mean : 0.f;
-    double run[16];
-    double t = 0.0;
+    double t = 0.0;  // thread total first; the running sums are formed again when the offset is known (registers)
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-      t += (double)v[e];
-      run[e] = t;
-    }
+    for (int e = 0; e < 16; e++) t += (double)v[e];
     double incl = t;  // inclusive scan of the thread totals across the warp, then across the 32 warps
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -860,13 +856,15 @@ __global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __
       if (lx == 31) smd[0] = wi;             // tile total
     }
     __syncthreads();
-    const double off = carry + warp_tot[ly] + (incl - t);
+    double run = carry + warp_tot[ly] + (incl - t);
 #pragma unroll
-    for (int e = 0; e < 16; e++)
+    for (int e = 0; e < 16; e++) {
+      run += (double)v[e];
       if (i0 + e < ts_count) {
         ts[i0 + e] = v[e];
-        acc[i0 + e] = (float)(off + run[e]);
+        acc[i0 + e] = (float)run;
       }
+    }
     carry += smd[0];
     __syncthreads();
   }

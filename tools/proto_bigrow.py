@@ -11,8 +11,8 @@ LOGL = int(sys.argv[1]) if len(sys.argv) > 1 else 14
 L = 1 << LOGL
 R3 = L // 4096
 B1, B2 = L // 16, L // 256
-S2 = B2 + R3   # chunk stride of a 16*R3-element block == R3/2 (mod 8): the R3/2 pairs of a block interleave
-S1 = 16 * S2 + 2
+S2 = B2           # no padding inside a chunk: each chunk of B1 elements is ONE contiguous bulk copy
+S1 = B1 + 2       # chunk stride in 16-byte units is odd: lanes that differ in d0 never share a bank group
 NT = L // 32
 SIGN = +1.0  # backward transform (waterfall)
 
@@ -72,9 +72,11 @@ for th in range(NT):
         for i in range(16):
             buf[off1[th] + bfly + i * S2] = y[i]
 # stage 2: t -> blk = t // (R3/2) = (d0, d1), jp = t % (R3/2); stride R3; twiddle W_B2^(i j)
-blk = t // (R3 // 2)
-jp2 = t % (R3 // 2)
-off2 = (blk // 16) * S1 + (blk % 16) * S2 + 2 * jp2
+sd0 = t & 15
+rest = t >> 4
+jp2 = rest % (R3 // 2)
+sd1 = rest // (R3 // 2)
+off2 = sd0 * S1 + sd1 * S2 + 2 * jp2
 conf["s2"] = all(check16(off2 + i * R3, "s2") for i in range(16))
 for th in range(NT):
     for bfly in range(2):
@@ -88,17 +90,11 @@ for th in range(NT):
 ng = 32 // R3
 ok = True
 for g in range(ng):
-    if R3 == 4:
-        # lanes vary (d0 bit 0, d2 bits 0-1): chunk index d0*545 + d1*34 + 2*d2 takes 8 distinct values mod 8
-        l = t & 31
-        u = (t >> 3) + (NT // 8) * g
-        gd0 = (l & 1) | ((u & 7) << 1)
-        gd2 = ((l >> 1) & 3) | ((u >> 7) << 2)
-        gd1 = (u >> 3) & 15
-        base = gd0 * S1 + gd1 * S2 + gd2 * R3
-    else:
-        G = t + NT * g
-        base = (G // 256) * S1 + ((G // 16) % 16) * S2 + (G % 16) * R3
+    # lanes vary d0 (chunk stride odd in 16-byte units): conflict free for both radices
+    gd0 = t & 15
+    rest = (t >> 4) + (NT // 16) * g
+    gd1, gd2 = rest >> 4, rest & 15
+    base = gd0 * S1 + gd1 * S2 + gd2 * R3
     for c in range(R3 // 2):
         ok &= check16(base + 2 * c, "last")
     for th in range(NT):
