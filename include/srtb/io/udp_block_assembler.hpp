@@ -10,6 +10,7 @@
 // Packet providers: any type with `std::span<const std::byte> receive()`; an in-memory one (synthetic
 // "UDP-shaped" streams, BASELINE config #5) and a plain recvfrom() socket one are provided.
 #pragma once
+#include <chrono>
 #include <climits>
 #include <cstddef>
 #include <cstdint>
@@ -164,6 +165,76 @@ inline std::vector<std::vector<std::byte>> frame_stream(std::span<const std::byt
   }
   return out;
 }
+
+/** synthetic LIVE stream (BASELINE config #5): the packets of a few pre-framed blocks are replayed for ever with a
+ *  running counter, released at a target payload rate like a NIC would deliver them. A consumer that falls behind by
+ *  more than `backlog_bytes` (the socket buffer of a real receiver) loses packets: the counter jumps ahead and the
+ *  block assembler zero-fills the gap, exactly as on a real link. rate <= 0: as fast as the consumer takes them. */
+template <typename Backend>
+class paced_packet_provider {
+  static constexpr size_t data_size = Backend::packet_payload_size - Backend::packet_header_size;
+  std::vector<std::byte> store_;  // n_ packets of packet_payload_size bytes
+  size_t n_ = 0, next_ = 0;
+  uint64_t counter_ = 0;
+  double bytes_per_s_ = 0;
+  size_t backlog_packets_ = 0;
+  std::chrono::steady_clock::time_point origin_{};
+  bool started_ = false;
+  uint64_t released_ = 0;  // packets the "link" has delivered or dropped so far
+  uint64_t dropped_ = 0;
+  std::chrono::steady_clock::time_point deadline_{};
+  double run_seconds_ = 0;  // > 0: stop this long after the first packet was asked for
+
+ public:
+  paced_packet_provider(std::span<const std::byte> payload, double payload_bytes_per_s, uint64_t first_counter = 0,
+                        size_t backlog_bytes = size_t{64} << 20)
+      : counter_{first_counter}, bytes_per_s_{payload_bytes_per_s}, backlog_packets_{backlog_bytes / data_size} {
+    n_ = payload.size() / data_size;
+    if (n_ == 0) throw std::invalid_argument("[paced_packet_provider] payload smaller than one packet");
+    store_.resize(n_ * Backend::packet_payload_size);
+    for (size_t i = 0; i < n_; i++)
+      std::memcpy(store_.data() + i * Backend::packet_payload_size + Backend::packet_header_size,
+                  payload.data() + i * data_size, data_size);
+  }
+  /** stop handing out packets after `seconds` of stream time (the receiver pipe then ends like a closed socket) */
+  void run_for(double seconds) { run_seconds_ = seconds; }
+  uint64_t dropped_packets() const { return dropped_; }
+
+  std::span<const std::byte> receive(std::stop_token st = {}) {
+    using clock = std::chrono::steady_clock;
+    if (!started_) {
+      origin_ = clock::now();
+      started_ = true;
+      deadline_ = origin_ + std::chrono::duration_cast<clock::duration>(std::chrono::duration<double>(run_seconds_));
+    }
+    const bool has_deadline_ = run_seconds_ > 0;
+    if (bytes_per_s_ > 0) {
+      for (;;) {
+        const auto now = clock::now();
+        if (st.stop_requested() || (has_deadline_ && now >= deadline_)) return {};
+        const double elapsed = std::chrono::duration<double>(now - origin_).count();
+        const uint64_t due = static_cast<uint64_t>(elapsed * bytes_per_s_ / (double)data_size);  // packets sent by now
+        if (due > released_ + backlog_packets_) {  // consumer too slow: the oldest packets are gone
+          const uint64_t lost = due - released_ - backlog_packets_;
+          released_ += lost;
+          counter_ += lost;
+          next_ = (next_ + lost) % n_;
+          dropped_ += lost;
+        }
+        if (due > released_) break;  // a packet is waiting
+        // idle link: nothing has arrived yet
+      }
+    } else if (st.stop_requested() || (has_deadline_ && clock::now() >= deadline_)) {
+      return {};
+    }
+    std::byte* pkt = store_.data() + next_ * Backend::packet_payload_size;
+    Backend::write_header(std::span<std::byte>(pkt, Backend::packet_header_size), counter_);
+    next_ = (next_ + 1) % n_;
+    counter_++;
+    released_++;
+    return std::span<const std::byte>(pkt, Backend::packet_payload_size);
+  }
+};
 
 #ifdef SRTB_HAS_SOCKETS
 /** blocking recvfrom() provider (reference: io/udp/recvfrom_packet_provider.hpp) */

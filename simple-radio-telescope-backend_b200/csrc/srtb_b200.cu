@@ -1649,6 +1649,29 @@ static int format_streams(int format) {
 
 // enqueue every stage of one block on ctx->stream (no host sync); results land in
 // ctx->h_res[res_base .. res_base + streams) once the stream reaches the final D2H copy
+// unpack fused into the first FFT sweep: possible when the samples are 8-bit, the window is the rectangle and every
+// complex point of a stream is one fixed-size byte group (simple, "1 1 2 2", "1 2 1 2"); fills raw[stream]
+static bool raw_sources_for(const srtb_b200_block_config* cfg, const void* d_baseband, size_t baseband_bytes, int streams,
+                            raw_source (&raw)[4]) {
+  const int bits = cfg->baseband_input_bits;
+  const int fmt = cfg->baseband_format;
+  const size_t N = cfg->baseband_input_count;
+  if (!((bits == 8 || bits == -8) && cfg->window == SRTB_B200_WINDOW_RECTANGLE && N >= ((size_t)1 << 14) &&
+        (fmt == SRTB_B200_FORMAT_SIMPLE || (fmt == SRTB_B200_FORMAT_NAOCPSR_SNAP1 && bits == -8) ||
+         fmt == SRTB_B200_FORMAT_INTERLEAVED_2) &&
+        baseband_bytes >= N * (size_t)streams && get_encode_tiled() && !std::getenv("SRTB_B200_NO_FUSED_UNPACK")))
+    return false;
+  for (int s = 0; s < streams; s++) {
+    raw[s].base = d_baseband;
+    raw[s].is_signed = (bits < 0);
+    raw[s].G = 2 * streams;
+    if (fmt == SRTB_B200_FORMAT_SIMPLE) { raw[s].o0 = 0; raw[s].o1 = 1; }
+    else if (fmt == SRTB_B200_FORMAT_NAOCPSR_SNAP1) { raw[s].o0 = 2 * s; raw[s].o1 = 2 * s + 1; }
+    else { raw[s].o0 = s; raw[s].o1 = s + 2; }
+  }
+  return true;
+}
+
 // (re)allocate one set of per-stream working buffers of N + 2 floats (the in-place buffer of the reference's works,
 // unpack_pipe.hpp:65-67) owned by the ctx
 static int ensure_stream_bufs(srtb_b200_ctx* ctx, float* (&bufs)[4], size_t* elems, size_t N, int streams) {
@@ -1686,25 +1709,7 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
   // unpack: fused into the first FFT pass when the samples are 8-bit and every complex point of a
   // stream is one fixed-size byte group (simple, "1 1 2 2", "1 2 1 2"); otherwise the unpack kernel
   raw_source raw[4];
-  bool fuse_unpack = false;
-  {
-    const int bits = cfg->baseband_input_bits;
-    const int fmt = cfg->baseband_format;
-    if ((bits == 8 || bits == -8) && cfg->window == SRTB_B200_WINDOW_RECTANGLE && N >= ((size_t)1 << 14) &&
-        (fmt == SRTB_B200_FORMAT_SIMPLE || fmt == SRTB_B200_FORMAT_NAOCPSR_SNAP1 ||
-         fmt == SRTB_B200_FORMAT_INTERLEAVED_2) &&
-        baseband_bytes >= N * (size_t)streams && get_encode_tiled() && !std::getenv("SRTB_B200_NO_FUSED_UNPACK")) {
-      fuse_unpack = true;
-      for (int s = 0; s < streams; s++) {
-        raw[s].base = d_baseband;
-        raw[s].is_signed = (bits < 0);
-        raw[s].G = 2 * streams;
-        if (fmt == SRTB_B200_FORMAT_SIMPLE) { raw[s].o0 = 0; raw[s].o1 = 1; }
-        else if (fmt == SRTB_B200_FORMAT_NAOCPSR_SNAP1 && bits == -8) { raw[s].o0 = 2 * s; raw[s].o1 = 2 * s + 1; }
-        else { raw[s].o0 = s; raw[s].o1 = s + 2; }
-      }
-    }
-  }
+  const bool fuse_unpack = raw_sources_for(cfg, d_baseband, baseband_bytes, streams, raw);
   bool unpacked = false;
   auto ensure_unpacked = [&]() -> int {
     if (unpacked) return 0;
@@ -1861,9 +1866,18 @@ extern "C" int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b
   const size_t L = Nc / batch;
   if (int rc = ensure(ctx, &ctx->sweep_buf, &ctx->sweep_buf_bytes, (Nc + 1) * sizeof(float2))) return rc;
   float2* W = static_cast<float2*>(ctx->sweep_buf);
-  if (int rc = srtb_b200_unpack(ctx, d_baseband, baseband_bytes, cfg->baseband_input_bits, cfg->baseband_format,
-                                cfg->window, ctx->stream_buf, N))
-    return rc;
+  // unpack: fused into the first R2C sweep when the format allows (as in process_block), else the unpack kernel
+  raw_source raw[4];
+  bool fuse_unpack = raw_sources_for(cfg, d_baseband, baseband_bytes, streams, raw);
+  bool unpacked = false;
+  auto ensure_unpacked = [&]() -> int {
+    if (unpacked) return 0;
+    unpacked = true;
+    return srtb_b200_unpack(ctx, d_baseband, baseband_bytes, cfg->baseband_input_bits, cfg->baseband_format,
+                            cfg->window, ctx->stream_buf, N);
+  };
+  if (!fuse_unpack)
+    if (int rc = ensure_unpacked()) return rc;
   std::vector<size_t> bins;
   for (uint64_t r = 0; r < cfg->n_rfi_freq_pairs; r++) {
     size_t lo, hi;
@@ -1882,7 +1896,16 @@ extern "C" int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b
   const bool fuse_chirp = chirp_fusable(L);
   for (int s = 0; s < streams; s++) {
     float* buf = ctx->stream_buf[s];
-    if (int rc = fft_r2c_with_power_mean(ctx, buf, N)) return rc;  // leaves mean(|X|^2) in ctx->mean
+    {
+      int rc = SRTB_B200_E_UNSUPPORTED;
+      if (fuse_unpack && !unpacked) rc = fft_r2c_with_power_mean(ctx, buf, N, &raw[s], nullptr);
+      if (rc == SRTB_B200_E_UNSUPPORTED) {
+        if (fuse_unpack && !unpacked && s > 0) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "dm_sweep: fused unpack refused a later stream");
+        if (int rc2 = ensure_unpacked()) return rc2;
+        rc = fft_r2c_with_power_mean(ctx, buf, N);  // leaves mean(|X|^2) in ctx->mean
+      }
+      if (rc) return rc;
+    }
     const bool fused = fuse_chirp && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0;
     if (fused)  // the manual zap does not depend on the DM: once, on the kept spectrum
       if (int rc = zero_bin_ranges(ctx, reinterpret_cast<float2*>(buf), bins)) return rc;

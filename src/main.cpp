@@ -11,6 +11,10 @@
 // Extra options (not part of srtb::configs; consumed here before the reference-style parser sees argv):
 //   --gpu_devices 0,1,...   GPUs to use (default: all visible)      --chains_per_gpu N   chain pipes per GPU (default 2)
 //   --ring_depth N          blocks in flight per chain pipe (1..3, default 3)
+//   --synthetic_udp_rate R  no socket: a synthetic packet stream (the format's framing, Gaussian 8-bit noise) released at
+//                           R samples/s per receiver like a NIC would (0 = as fast as it is taken); with
+//   --synthetic_duration S  seconds of stream (default 10); prints one JSON line with blocks, rate and lost packets
+//   --discard_output 1      count results instead of writing candidate files
 #include <atomic>
 #include <chrono>
 #include <csignal>
@@ -85,6 +89,57 @@ std::string take_option(std::vector<std::string>& args, const std::string& name,
   return def;
 }
 
+/** results counted, nothing written (throughput runs) */
+struct discard_sink {
+  std::shared_ptr<std::atomic<uint64_t>> done, positives;
+  std::optional<srtb::work::dummy_work> operator()(std::stop_token, srtb::work::write_signal_work w) {
+    if (!w.time_series.empty()) (*positives)++;
+    (*done)++;
+    return srtb::work::dummy_work{};
+  }
+};
+
+struct synthetic_stats {
+  std::shared_ptr<std::atomic<uint64_t>> received = std::make_shared<std::atomic<uint64_t>>(0);
+  std::shared_ptr<std::atomic<uint64_t>> lost = std::make_shared<std::atomic<uint64_t>>(0);
+};
+
+/** udp_receiver_pipe over the paced synthetic provider; publishes its packet statistics when the stream ends */
+template <typename Backend>
+struct synthetic_receiver_pipe {
+  using provider = srtb::io::udp::paced_packet_provider<Backend>;
+  srtb::pipeline::udp_receiver_pipe<provider, Backend> inner;
+  synthetic_stats stats;
+  synthetic_receiver_pipe(provider p, size_t id, synthetic_stats st) : inner{std::move(p), id}, stats{st} {}
+  std::optional<srtb::work::copy_to_device_work> operator()(std::stop_token st, srtb::work::dummy_work d) {
+    auto w = inner(st, d);
+    stats.received->store(inner.received_packets());
+    stats.lost->store(inner.lost_packets());
+    return w;
+  }
+};
+
+template <typename Backend>
+std::jthread start_synthetic_source(size_t id, double samples_per_s, double seconds, round_robin_out_functor out,
+                                    synthetic_stats stats) {
+  using namespace srtb::pipeline;
+  // four distinct blocks of Gaussian-ish 8-bit noise (sum of four uniform bytes, sigma ~ 20 counts), framed and replayed
+  const size_t block_bytes = srtb::config.baseband_input_count * Backend::data_stream_count;
+  std::vector<std::byte> payload(4 * block_bytes);
+  uint64_t x = 0x9E3779B97F4A7C15ull + id;
+  for (size_t i = 0; i < payload.size(); i++) {
+    x ^= x << 13;
+    x ^= x >> 7;
+    x ^= x << 17;
+    const int sum = (int)(x & 0xff) + (int)((x >> 8) & 0xff) + (int)((x >> 16) & 0xff) + (int)((x >> 24) & 0xff) - 510;
+    payload[i] = static_cast<std::byte>(static_cast<int8_t>(sum * 20 / 148));
+  }
+  typename synthetic_receiver_pipe<Backend>::provider prov{payload, samples_per_s * (double)Backend::data_stream_count,
+                                                            (uint64_t)id << 40};
+  prov.run_for(seconds);
+  return start_pipe<synthetic_receiver_pipe<Backend>>(dummy_in_functor<>{}, out, std::move(prov), id, stats);
+}
+
 template <typename Backend>
 std::jthread start_udp_source(size_t id, const std::string& address, unsigned short port, round_robin_out_functor out) {
   using namespace srtb::pipeline;
@@ -100,6 +155,9 @@ int main(int argc, char** argv) {
   const std::string devices_opt = take_option(args, "gpu_devices", "");
   const int chains_per_gpu = std::max(1, std::atoi(take_option(args, "chains_per_gpu", "2").c_str()));
   const int ring_depth = std::max(1, std::atoi(take_option(args, "ring_depth", "3").c_str()));
+  const std::string synth_rate_opt = take_option(args, "synthetic_udp_rate", "");
+  const double synth_seconds = std::atof(take_option(args, "synthetic_duration", "10").c_str());
+  const bool discard = std::atoi(take_option(args, "discard_output", "0").c_str()) != 0;
   std::vector<char*> av{argv[0]};
   for (auto& a : args) av.push_back(a.data());
   auto& cfg = srtb::config;
@@ -141,7 +199,10 @@ int main(int argc, char** argv) {
   }
   // sink (main.cpp:206-216)
   srtb::cuda_queue q0{devices.front()};
-  if (cfg.baseband_write_all) {
+  auto positives = std::make_shared<std::atomic<uint64_t>>(0);
+  if (discard) {
+    threads.push_back(start_pipe<discard_sink>(queue_in_functor{out_q}, dummy_out_functor<>{}, done, positives));
+  } else if (cfg.baseband_write_all) {
     SRTB_LOGW << " [main] " << "Writing all baseband data, take care of disk space!";
     threads.push_back(start_pipe<counting_sink<write_file_pipe>>(
         queue_in_functor{out_q}, dummy_out_functor<>{}, std::make_shared<write_file_pipe>(q0), done));
@@ -155,7 +216,27 @@ int main(int argc, char** argv) {
   round_robin_out_functor rr{gpu_queues, submitted};
   const size_t streams = srtb::io::backend_registry::get_data_stream_count(cfg.baseband_format_type);
   const auto t0 = std::chrono::steady_clock::now();
-  if (!cfg.input_file_path.empty()) {
+  if (!synth_rate_opt.empty()) {
+    // synthetic live stream (BASELINE config #5): one paced receiver, blocks dealt over the GPUs; ends after
+    // synthetic_duration seconds of stream and prints one JSON line
+    const double rate = std::atof(synth_rate_opt.c_str());
+    const std::string fmt{resolve_format_alias(cfg.baseband_format_type)};
+    synthetic_stats st;
+    std::jthread source;
+    if (fmt == "naocpsr_snap1") source = start_synthetic_source<srtb::io::backend_registry::naocpsr_snap1>(0, rate, synth_seconds, rr, st);
+    else source = start_synthetic_source<srtb::io::backend_registry::fastmb_roach2>(0, rate, synth_seconds, rr, st);
+    source.join();
+    while (done->load() < submitted->load() * streams && !g_interrupted) std::this_thread::yield();
+    const double dt_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("{\"blocks\": %llu, \"streams\": %zu, \"samples_per_stream_block\": %zu, \"seconds\": %.6f, "
+                "\"gsamples_per_s\": %.4f, \"target_samples_per_s\": %.3e, \"received_packets\": %llu, "
+                "\"lost_packets\": %llu, \"blocks_with_candidates\": %llu, \"gpus\": %zu}\n",
+                (unsigned long long)submitted->load(), streams, (size_t)cfg.baseband_input_count, dt_,
+                (double)submitted->load() * (double)streams * (double)cfg.baseband_input_count / dt_ / 1e9, rate,
+                (unsigned long long)st.received->load(), (unsigned long long)st.lost->load(),
+                (unsigned long long)positives->load(), devices.size());
+    std::fflush(stdout);
+  } else if (!cfg.input_file_path.empty()) {
     std::jthread source = start_pipe<read_file_pipe>(dummy_in_functor<>{}, rr);
     source.join();  // the pipe thread ends when the file has been read
     while (done->load() < submitted->load() * streams && !g_interrupted) std::this_thread::yield();

@@ -1,11 +1,13 @@
 // CPU-only tests of the SURVEY section 8(f) host pieces: the config loader with its expression grammar
 // (include/srtb/program_options.hpp), the NPY writer, and the file reader's block/overlap arithmetic.
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstdio>
 #include <filesystem>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "srtb/io/npy.hpp"
@@ -89,6 +91,37 @@ int main(int argc, char** argv) {
   CHECK(c.udp_receiver_address.size() == 2 && c.udp_receiver_address[1] == "10.0.1.3");
   CHECK(srtb::log::current_level == srtb::log::levels::DEBUG);
   srtb::log::current_level = srtb::log::levels::WARNING;
+  // the two shipped configuration files, verbatim, when the reference tree is present (argv[2] = its userspace dir):
+  // srtb_config.cfg:2-22 and srtb_config_1644-4559.cfg:2-29 must load into srtb::configs unchanged
+  if (argc > 2) {
+    const std::string ref = argv[2];
+    {
+      std::string b0 = "prog", b1 = "--config_file_name", b2 = ref + "/srtb_config.cfg";
+      char* bv[] = {b0.data(), b1.data(), b2.data()};
+      srtb::configs r;
+      srtb::program_options::apply_changed_configs(srtb::program_options::parse_arguments(3, bv, "none.cfg"), r);
+      CHECK(r.baseband_input_count == (size_t{1} << 30) && r.spectrum_channel_count == 2048);
+      CHECK(r.baseband_format_type == "simple" && r.baseband_input_bits == -8);
+      CHECK(r.baseband_freq_low == 1000.0f && r.baseband_bandwidth == 500.0f && r.baseband_sample_rate == 1e9f);
+      CHECK(r.baseband_reserve_sample == false && r.baseband_output_file_prefix == "/dev/shm/");
+      CHECK(r.udp_receiver_address.size() == 1 && r.udp_receiver_address[0] == "10.0.1.2" && r.udp_receiver_port[0] == 12004);
+      CHECK(r.udp_receiver_cpu_preferred.size() == 1 && r.udp_receiver_cpu_preferred[0] == 29 && r.dm == 0.0f);
+      CHECK(r.mitigate_rfi_average_method_threshold == 5.0f && r.mitigate_rfi_spectral_kurtosis_threshold == 1.05f);
+      CHECK(r.signal_detect_signal_noise_threshold == 8.0f && r.signal_detect_max_boxcar_length == 16);
+    }
+    {
+      std::string b0 = "prog", b1 = "--config_file_name", b2 = ref + "/srtb_config_1644-4559.cfg";
+      char* bv[] = {b0.data(), b1.data(), b2.data()};
+      srtb::configs r;
+      srtb::program_options::apply_changed_configs(srtb::program_options::parse_arguments(3, bv, "none.cfg"), r);
+      CHECK(r.baseband_input_count == (size_t{1} << 30) && r.spectrum_channel_count == 2048 && r.baseband_input_bits == 2);
+      CHECK(r.baseband_freq_low == 1437.0f && r.baseband_bandwidth == -64.0f && r.baseband_sample_rate == 128e6f);
+      CHECK(r.dm == -478.80f && r.baseband_reserve_sample == false && r.mitigate_rfi_freq_list == "1418-1422");
+      CHECK(r.mitigate_rfi_average_method_threshold == 1.5f && r.signal_detect_max_boxcar_length == 256);
+      CHECK(r.input_file_path == "/tmp/buf3.bin" && r.input_file_offset_bytes == 0 && r.gui_enable == true);
+    }
+    srtb::log::current_level = srtb::log::levels::WARNING;
+  }
   // command line beats the file; unknown keys are rejected
   const std::string dir = (argc > 1) ? argv[1] : "/tmp";
   const std::string cfg_path = dir + "/srtb_test.cfg";
@@ -165,6 +198,39 @@ int main(int argc, char** argv) {
     G::write_header(gp, 0x0123456789abcdefull);
     CHECK(G::parse_counter(gp) == 0x0123456789abcdefull && G::packet_payload_size - G::packet_header_size == 8192);
     CHECK(backend_registry::naocpsr_snap1::data_stream_count == 2);
+  }
+  {
+    // synthetic live stream (BASELINE config #5): packets released at a target rate with a running counter; a consumer
+    // that stalls for longer than the backlog loses packets, which the assembler zero-fills and counts
+    using namespace srtb::io;
+    using B = backend_registry::fastmb_roach2;
+    constexpr size_t d = B::packet_payload_size - B::packet_header_size;
+    std::vector<std::byte> payload(16 * d);
+    for (size_t i = 0; i < payload.size(); i++) payload[i] = static_cast<std::byte>(1 + i % 251);
+    const double rate = 40e6;  // bytes/s
+    udp::paced_packet_provider<B> prov{payload, rate, 7000, /*backlog_bytes=*/64 * d};
+    prov.run_for(0.5);
+    udp::block_assembler<udp::paced_packet_provider<B>, B> a{std::move(prov)};
+    std::vector<std::byte> block(32 * d);
+    const auto t0 = std::chrono::steady_clock::now();
+    size_t blocks = 0;
+    uint64_t expect_first = 7000;
+    bool stalled = false;
+    while (auto first = a.receive(block)) {
+      CHECK(*first == expect_first);   // blocks are counter-contiguous even across lost packets
+      expect_first += 32;
+      blocks++;
+      if (blocks == 20 && !stalled) {  // stall for much longer than the 64-packet backlog lasts (6.5 ms at this rate)
+        std::this_thread::sleep_for(std::chrono::milliseconds(60));
+        stalled = true;
+      }
+    }
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    CHECK(dt > 0.45 && dt < 1.0);
+    const double achieved = (double)(a.total_received_packet_count + a.total_lost_packet_count) * d / dt;
+    CHECK(achieved > 0.8 * rate && achieved < 1.2 * rate);
+    CHECK(a.total_lost_packet_count > 300 && a.total_lost_packet_count < 900);  // ~60 ms of a 9766 packet/s stream
+    CHECK(a.provider.dropped_packets() >= a.total_lost_packet_count - 32);
   }
   std::printf("host next ok\n");
   return 0;
