@@ -62,7 +62,7 @@ WORKLOADS = {
     # BASELINE.json configs[3]: Crab giant-pulse injection, 2^27-sample blocks, DM sweep 0..1000 (21 trials), block-sharded
     "config4": dict(log2n=27, bits=-8, fmt="simple", channels=1 << 11, dm=56.78, f_low=1000.0, bw=500.0,
                     fs=1e9, avg_thr=5.0, sk_thr=1.05, snr=8.0, chan_thr=0.9, maxbox=256, freq_list="",
-                    dms=[50.0 * i for i in range(21)]),
+                    dms=[0.0, 56.78] + [50.0 * i for i in range(2, 21)]),      # trial 1 is the Crab's DM itself
     # BASELINE.json configs[4]: continuous UDP-shaped stream (fastmb_roach2 framing), 1 Gsample/s per GPU, pinned ring
     "config5": dict(log2n=26, bits=-8, fmt="simple", channels=1 << 11, dm=56.778, f_low=1000.0, bw=500.0,
                     fs=1e9, avg_thr=5.0, sk_thr=1.05, snr=8.0, chan_thr=0.9, maxbox=256, freq_list="",

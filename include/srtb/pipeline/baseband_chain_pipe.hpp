@@ -35,7 +35,7 @@ struct block_config_holder {
 
   static int format_of(std::string_view name, int bits) {
     name = resolve_format_alias(name);
-    if (name == "simple") return SRTB_B200_FORMAT_SIMPLE;
+    if (name == "simple" || name == "fastmb_roach2") return SRTB_B200_FORMAT_SIMPLE;  // one stream (unpack_pipe.hpp:396)
     if (name == "interleaved_samples_2") return SRTB_B200_FORMAT_INTERLEAVED_2;
     if (name == "naocpsr_snap1") return bits == -8 ? SRTB_B200_FORMAT_NAOCPSR_SNAP1 : SRTB_B200_FORMAT_INTERLEAVED_2;
     if (name == "gznupsr_a1") return SRTB_B200_FORMAT_GZNUPSR_A1_2;

@@ -206,6 +206,8 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
     }
   };
 
+  pdl_launch_dependents();
+  pdl_wait();  // tables, barriers and tensor memory were set up while the preceding kernel drained
   float limit = 0.f;
   if constexpr (CHIRP) limit = cp.threshold * __ldg(cp.mean);
 

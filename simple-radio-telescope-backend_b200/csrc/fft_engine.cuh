@@ -451,6 +451,12 @@ struct trans_io {
 // ---------------------------------------------------------------------------------
 // TMA (cp.async.bulk) + mbarrier helpers
 // ---------------------------------------------------------------------------------
+// programmatic dependent launch (griddepcontrol): a kernel launched with the stream-serialisation attribute may start
+// while its predecessor drains; everything it does before pdl_wait() (shared-memory tables, barrier and TMEM set-up)
+// overlaps the predecessor's tail, everything after sees the predecessor's results. No-ops in a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -792,6 +798,8 @@ __global__ void __launch_bounds__(((1 << LOGL) / 16) * T, CHIRP ? SRTB_ROW16_CHI
     }
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();  // the spectrum and the s1 mean come from the preceding kernels
   auto issue = [&](unsigned tl, int b) {
     const size_t row0 = (size_t)tl * T;
     const size_t rows = (nrows - row0 < (size_t)T) ? nrows - row0 : (size_t)T;
@@ -1122,6 +1130,8 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, col16_threads<L
   for (int i = tid; i < (3 << btw.q); i += blockDim.x) stw[i] = __ldg(&btw.tab[i]);
   for (int i = tid; i < L; i += blockDim.x) ltw[i] = __ldg(&tw[i]);
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();  // the input (and, in place, the output region) belongs to the preceding kernel until here
   auto issue = [&](uint32_t tl, int b) {
     const uint32_t a = tl / btiles, b0 = (tl % btiles) * T;
     fence_proxy_async();
@@ -1563,6 +1573,8 @@ __global__ void __launch_bounds__(2 * T * ((1 << LOGL) / 16), 3)
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t M = (size_t)A << LOGL;
   auto issue = [&](uint32_t tl, int b) {
     const uint32_t tau = tl % tiles_per_rest, rest = tl / tiles_per_rest;
@@ -1652,6 +1664,8 @@ __global__ void __launch_bounds__(256) r2c_col0_fixup_kernel(float2* __restrict_
                                                               float* __restrict__ mean_out) {
   __shared__ double red[8];
   __shared__ bool last;
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t n = M / L1;  // column length; pairs j <-> n - j
   double acc = 0.0;
   for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j <= n / 2; j += (size_t)gridDim.x * blockDim.x) {

@@ -529,6 +529,8 @@ struct bin_ranges {
   unsigned long long lo[16], hi[16];
 };
 __global__ void __launch_bounds__(256) rfi_zero_ranges_kernel(float2* __restrict__ x, bin_ranges r) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t lo = r.lo[blockIdx.y], hi = r.hi[blockIdx.y];
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = lo + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i <= hi; i += stride)
@@ -779,21 +781,35 @@ __global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __
   __shared__ double warp_tot[32];
   __shared__ float s_mean;
   __shared__ bool s_last;
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x, lx = tid & 31, ly = tid >> 5;
-  const size_t j = (size_t)blockIdx.x * 32 + lx;
-  float a = 0.f;
-  if (j < ts_count) {
-    const size_t per = (chunks + 31) / 32;
-    const size_t c0 = (size_t)ly * per, c1 = min(c0 + per, chunks);
-    for (size_t c = c0; c < c1; c++) a += partial[c * ts_count + j];
-  }
-  sm[ly][lx] = a;
-  __syncthreads();
-  if (ly == 0 && j < ts_count) {
-    float t = sm[0][lx];
+  // one wave of CTAs, each walking its share of the 32-column groups: the grid-wide fence + ticket at the end then
+  // costs one round of latency instead of one per wave. The partial rows of a group are loaded eight at a time
+  // (independent loads in flight) and added in index order.
+  const size_t per = (chunks + 31) / 32;
+  const size_t c0 = (size_t)ly * per, c1 = min(c0 + per, chunks);
+  for (size_t grp = blockIdx.x; grp * 32 < ts_count; grp += gridDim.x) {
+    const size_t j = grp * 32 + lx;
+    float a = 0.f;
+    if (j < ts_count) {
+      for (size_t c = c0; c < c1; c += 8) {
+        float v[8];
 #pragma unroll
-    for (int g = 1; g < 32; g++) t += sm[g][lx];
-    ts[j] = t;
+        for (int u = 0; u < 8; u++) v[u] = (c + u < c1) ? partial[(c + u) * ts_count + j] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; u++) a += v[u];
+      }
+    }
+    __syncthreads();  // sm[][] of the previous group has been consumed
+    sm[ly][lx] = a;
+    __syncthreads();
+    if (ly == 0 && j < ts_count) {
+      float t = sm[0][lx];
+#pragma unroll
+      for (int g = 1; g < 32; g++) t += sm[g][lx];
+      ts[j] = t;
+    }
   }
   // K16: channels whose first sample is zero; every CTA takes a slice, integer atomics (exact)
   {
@@ -810,10 +826,13 @@ __global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __
       if (v.x * v.x + v.y * v.y == 0.f) atomicAdd(&res->zero_count, 1ull);
     }
   }
-  // ---- last CTA: mean removal, inclusive scan, header
-  __threadfence();
+  // ---- last CTA: mean removal, inclusive scan, header. One fence per CTA: the barrier orders every thread's stores
+  // before thread 0's fence, which is cumulative (PTX memory model), so they are visible to whoever sees the ticket
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
@@ -894,6 +913,8 @@ __global__ void __launch_bounds__(1024) detect_boxcar_kernel(float* __restrict__
                                                              float* __restrict__ host_out) {
   __shared__ double smd[32];
   __shared__ float s_thr;
+  pdl_launch_dependents();
+  pdl_wait();
   const int nb = blockIdx.x;
   if (nb >= res->n_boxcars) return;
   const int tid = threadIdx.x, nt = blockDim.x;

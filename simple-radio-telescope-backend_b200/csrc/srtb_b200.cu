@@ -83,6 +83,7 @@ struct srtb_b200_ctx {
   bool stat_have[SRTB_B200_STAGE_COUNT] = {};
   // ring path: pinned host destination [streams][MAX_BOXCARS][L] of the current block's positive series (else null)
   float* host_series_dst = nullptr;
+  bool res_zeroed = false;  // block path: the per-stream result headers were zeroed before the first kernel
   // process_block
   void* d_baseband = nullptr;
   size_t d_baseband_bytes = 0;
@@ -473,7 +474,7 @@ static int launch_row(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t 
       if (int rc = persistent_grid(ctx, kern, threads, smem, smem, ntiles, &grid)) return rc;
       const float2* tw = nullptr;
       if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
-      kern<<<grid, threads, smem, ctx->stream>>>(in, out, nrows, tw, row_sk_params{}, row_chirp_params{});
+      CK(launch_pdl(ctx, kern, dim3(grid), dim3(threads), smem, in, out, nrows, tw, row_sk_params{}, row_chirp_params{}));
       ctx->launches++;
       CK(cudaGetLastError());
       return 0;
@@ -541,6 +542,31 @@ static bool make_tensor_map(tensor_map_blob* out, const void* base, int rank, co
   if (r != CUDA_SUCCESS) return false;
   std::memcpy(out->bytes, &m, sizeof(m));
   return true;
+}
+
+// SRTB_B200_PDL=0: plain launches (A/B); default: the kernels of the block path are launched with programmatic
+// stream serialisation, so each one's set-up overlaps its predecessor's tail (they all call pdl_wait() before
+// touching anything a predecessor produces)
+static bool use_pdl() {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(srtb_b200_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 template <class K>
@@ -653,7 +679,7 @@ static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, siz
       auto kern16 = fft_col16_tma_kernel<LOGL, T, FWD>;
       constexpr int threads = col16_threads<LOGL, T>::value;
       if (int rc = persistent_grid(ctx, kern16, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
-      kern16<<<grid, threads, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, raw_params{});
+      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, raw_params{}));
       ctx->launches++;
       CK(cudaGetLastError());
       *done = true;
@@ -701,8 +727,8 @@ static int launch_col_tma_raw(srtb_b200_ctx* ctx, const raw_source& src, float2*
       auto kern16 = fft_col16_tma_kernel<LOGL, T, true, RAW>;
       constexpr int threads = col16_threads<LOGL, T>::value;
       if (int rc = persistent_grid(ctx, kern16, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
-      kern16<<<grid, threads, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
-                                                   raw_params{src.G, src.o0, src.o1});
+      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
+                    raw_params{src.G, src.o0, src.o1}));
       ctx->launches++;
       CK(cudaGetLastError());
       *done = true;
@@ -905,7 +931,7 @@ static int launch_bigrow(srtb_b200_ctx* ctx, const float2* in, float2* out, size
       sk->partial = ctx->colsum_partial;
       p = *sk;
     }
-    kern<<<grid, C::NT, smem, ctx->stream>>>(in, out, (unsigned)nrows, tabs, p, chirp ? *chirp : row_chirp_params{});
+    CK(launch_pdl(ctx, kern, dim3(grid), dim3(C::NT), smem, in, out, (unsigned)nrows, tabs, p, chirp ? *chirp : row_chirp_params{}));
     ctx->launches++;
     CK(cudaGetLastError());
     if (chunks_out) *chunks_out = grid;
@@ -1063,9 +1089,8 @@ static int launch_trans_r2c(srtb_b200_ctx* ctx, const float2* in, float2* out, s
       constexpr int threads = 2 * T * (L / 16);
       if (int rc = persistent_grid(ctx, kern16, threads, smem, smem, ntiles, &grid)) return rc;
       grid = std::min<unsigned>(grid, 2048);
-      kern16<<<grid, threads, smem, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
-                                                  (uint32_t)tiles_per_rest, (uint32_t)ntiles, tw, ctx->partial,
-                                                  (uint32_t)rest_inner);
+      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
+                    (uint32_t)tiles_per_rest, (uint32_t)ntiles, tw, ctx->partial, (uint32_t)rest_inner));
       launched = true;
     }
   }
@@ -1084,7 +1109,8 @@ static int launch_trans_r2c(srtb_b200_ctx* ctx, const float2* in, float2* out, s
     const size_t pairs = ((A << LOGL) / L1) / 2 + 1;
     const unsigned fgrid = (unsigned)std::min<size_t>((pairs + 255) / 256, 2048);
     if (grid + fgrid > 4096) return fail(ctx, SRTB_B200_E_SIZE, "r2c: partial buffer too small");
-    r2c_col0_fixup_kernel<<<fgrid, 256, 0, ctx->stream>>>(out, A << LOGL, L1, ctx->partial, grid, ctx->ticket, ctx->mean);
+    CK(launch_pdl(ctx, r2c_col0_fixup_kernel, dim3(fgrid), dim3(256), 0, out, (size_t)(A << LOGL), (size_t)L1, ctx->partial,
+                  (unsigned)grid, ctx->ticket, ctx->mean));
   }
   ctx->launches++;
   CK(cudaGetLastError());
@@ -1309,7 +1335,7 @@ static int zero_bin_ranges(srtb_b200_ctx* ctx, float2* x, const std::vector<size
       longest = std::max<size_t>(longest, br.hi[r] - br.lo[r] + 1);
     }
     dim3 g(grid_for(ctx, longest, 256), (unsigned)nr);
-    rfi_zero_ranges_kernel<<<g, 256, 0, ctx->stream>>>(x, br);
+    CK(launch_pdl(ctx, rfi_zero_ranges_kernel, g, dim3(256), 0, x, br));
     ctx->launches++;
     CK(cudaGetLastError());
   }
@@ -1406,16 +1432,16 @@ static int detect_tail(srtb_b200_ctx* ctx, int slot, const float2* x, size_t tim
                        size_t ts_count, size_t chunks, float snr, float chan_thr, size_t max_boxcar) {
   float* const host_series = ctx->host_series_dst ? ctx->host_series_dst + (size_t)slot * SRTB_B200_MAX_BOXCARS * time_count : nullptr;
   stage_scope stats_(ctx, SRTB_B200_STAGE_FUSED_DETECT_TAIL, 4.0 * (double)chunks * (double)ts_count);
-  colsum_final_scan_kernel<<<(unsigned)((ts_count + 31) / 32), 1024, 0, ctx->stream>>>(
-      ctx->colsum_partial, ts_count, chunks, ctx->series[slot], ctx->acc, x, time_count, chan_count, chan_thr,
-      max_boxcar, ctx->detect_ticket, ctx->d_res + slot);
+  CK(launch_pdl(ctx, colsum_final_scan_kernel, dim3((unsigned)std::min<size_t>((ts_count + 31) / 32, (size_t)ctx->sm_count)),
+                dim3(1024), 0, (const float*)ctx->colsum_partial, ts_count, chunks, ctx->series[slot], ctx->acc, x, time_count,
+                chan_count, chan_thr, max_boxcar, ctx->detect_ticket, ctx->d_res + slot));
   ctx->launches++;
   CK(cudaGetLastError());
   // one CTA per possible boxcar; CTAs beyond n_boxcars (known only on the device) exit at once
   unsigned max_nb = 1;
   for (size_t b = 2; b <= max_boxcar && b < ts_count && max_nb < SRTB_B200_MAX_BOXCARS; b *= 2) max_nb++;
-  detect_boxcar_kernel<<<max_nb, 1024, 0, ctx->stream>>>(ctx->series[slot], time_count, ctx->acc, ts_count, snr,
-                                                         ctx->d_res + slot, host_series);
+  CK(launch_pdl(ctx, detect_boxcar_kernel, dim3(max_nb), dim3(1024), 0, ctx->series[slot], time_count, (const float*)ctx->acc,
+                ts_count, snr, ctx->d_res + slot, host_series));
   ctx->launches++;
   CK(cudaGetLastError());
   ctx->slot_time_count[slot] = time_count;
@@ -1477,7 +1503,7 @@ static int watfft_sk_launch(srtb_b200_ctx* ctx, float2* x, size_t chan_count, fl
       const float2* tw = nullptr;
       if (int rc = get_stage_twiddles(ctx, LOGL, &tw)) return rc;
       row_sk_params p{lo_, hi_, ctx->colsum_partial, (unsigned)ts_count};
-      kern<<<grid, threads, smem, ctx->stream>>>(src, x, chan_count, tw, p, chirp ? *chirp : row_chirp_params{});
+      CK(launch_pdl(ctx, kern, dim3(grid), dim3(threads), smem, src, x, chan_count, tw, p, chirp ? *chirp : row_chirp_params{}));
       ctx->launches++;
       CK(cudaGetLastError());
       *chunks_out = grid;
@@ -1513,7 +1539,9 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
                                   const float2* src = nullptr) {
   const size_t ts_count = (time_count <= time_reserved_count) ? time_count : time_count - time_reserved_count;
   if (int rc = detect_prepare(ctx, slot, time_count, 1)) return rc;
-  CK(cudaMemsetAsync(ctx->d_res + slot, 0, sizeof(detect_dev_result), ctx->stream));
+  // the result header is zeroed here unless the block path did it for every stream up front (a memset between two
+  // kernels would break their programmatic-dependent-launch chain)
+  if (!ctx->res_zeroed) CK(cudaMemsetAsync(ctx->d_res + slot, 0, sizeof(detect_dev_result), ctx->stream));
   const float M_ = static_cast<float>(time_count);
   float hi = sk_threshold, lo = 2 - sk_threshold;
   if (lo > hi) std::swap(lo, hi);
@@ -1703,9 +1731,14 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
   if (N < 2 || !is_pow2(N)) return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(N));
   struct series_dst_scope {  // detect_tail reads ctx->host_series_dst; it is only meaningful inside this call
     srtb_b200_ctx* c;
-    ~series_dst_scope() { c->host_series_dst = nullptr; }
+    ~series_dst_scope() {
+      c->host_series_dst = nullptr;
+      c->res_zeroed = false;
+    }
   } series_scope_{ctx};
   ctx->host_series_dst = host_series;
+  CK(cudaMemsetAsync(ctx->d_res, 0, sizeof(detect_dev_result) * streams, ctx->stream));
+  ctx->res_zeroed = true;
   // unpack: fused into the first FFT pass when the samples are 8-bit and every complex point of a
   // stream is one fixed-size byte group (simple, "1 1 2 2", "1 2 1 2"); otherwise the unpack kernel
   raw_source raw[4];
