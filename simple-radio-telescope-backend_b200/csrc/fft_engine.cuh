@@ -969,8 +969,14 @@ struct tile_tma_smem {
 // (G = bytes per complex point: 2 for one stream, 4 when two streams share the block) and stage 0
 // converts the two samples at byte offsets o0/o1 of each group to float (K1's integer -> f32 cast,
 // exact) instead of reading complex64 that a separate kernel would have written and this one re-read.
+// RAW == 3: packed sub-byte samples (2 or 4 bits, MSB first, unsigned: unpack.hpp:43-156): a complex point is 2*bits
+// consecutive bits. `delta`: byte offset subtracted for odd points (gznupsr_a1 puts four consecutive samples of one
+// stream into a word, so odd points sit 2 bytes after the even point of the same word, not G bytes: unpack.hpp:338-369)
 struct raw_params {
   int G, o0, o1;
+  int delta;      // RAW 1/2: offset correction of odd points
+  int row_bytes;  // bytes of one tile row in shared memory (T * G, or T * bits / 4 for packed samples)
+  int bits;       // RAW 3: bits per sample
 };
 
 template <int LOGL, int T, bool FWD, int RAW = 0 /* 0 = complex64, 1 = int8 pairs, 2 = uint8 pairs */>
@@ -1143,10 +1149,10 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, col16_threads<L
         tma_load_2d(dst + r * T, &tmap, (int)b0, (int)(a * L + r), &mbar[b]);
     } else {
       unsigned char* dst = b ? raw1 : raw0;
-      mbar_expect_tx(&mbar[b], (uint32_t)(BUF * rp.G));
+      mbar_expect_tx(&mbar[b], (uint32_t)(L * rp.row_bytes));
 #pragma unroll
       for (int r = 0; r < L; r += ROWS_PER_BOX)
-        tma_load_2d(dst + (size_t)r * T * rp.G, &tmap, (int)(b0 * rp.G), (int)(a * L + r), &mbar[b]);
+        tma_load_2d(dst + (size_t)r * rp.row_bytes, &tmap, (int)(b0 / T) * rp.row_bytes, (int)(a * L + r), &mbar[b]);
     }
   };
   uint32_t tile = blockIdx.x;
@@ -1162,11 +1168,21 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, col16_threads<L
     if constexpr (RAW == 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) v[e] = sm[(u + e * U) * T + t];
-    } else {
-      const unsigned char* rawb = (b ? raw1 : raw0) + (size_t)t * rp.G;
+    } else if constexpr (RAW == 3) {
+      // packed samples: point t of a row occupies bits [2 bits t, 2 bits (t + 1)) counted from the row's MSB
+      const int nb = rp.bits, per_byte = 4 / nb, p = t % per_byte;
+      const int sh_re = 8 - nb * (2 * p + 1), sh_im = sh_re - nb, mask = (1 << nb) - 1;
+      const unsigned char* rawb = (b ? raw1 : raw0) + t / per_byte;
 #pragma unroll
       for (int e = 0; e < 16; e++) {
-        const unsigned char* g = rawb + (size_t)(u + e * U) * T * rp.G;
+        const unsigned w = rawb[(size_t)(u + e * U) * rp.row_bytes];
+        v[e] = make_float2((float)((w >> sh_re) & mask), (float)((w >> sh_im) & mask));
+      }
+    } else {
+      const unsigned char* rawb = (b ? raw1 : raw0) + (size_t)t * rp.G - (size_t)((t & 1) * rp.delta);
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const unsigned char* g = rawb + (size_t)(u + e * U) * rp.row_bytes;
         if (RAW == 1) v[e] = make_float2((float)(int)(signed char)g[rp.o0], (float)(int)(signed char)g[rp.o1]);
         else v[e] = make_float2((float)g[rp.o0], (float)g[rp.o1]);
       }
@@ -1693,10 +1709,10 @@ __global__ void __launch_bounds__(256) r2c_col0_fixup_kernel(float2* __restrict_
     partial[nparts + blockIdx.x] = a;
     __threadfence();
     last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (last) __threadfence();  // one acquiring fence (a fence per warp serialises: ~1 us each)
   }
   __syncthreads();
   if (last) {
-    __threadfence();
     double a = 0.0;
     for (unsigned i = threadIdx.x; i < nparts + gridDim.x; i += blockDim.x) a += partial[i];
 #pragma unroll

@@ -436,10 +436,10 @@ __global__ void __launch_bounds__(256) r2c_post_kernel(float2* __restrict__ H, s
       partial[blockIdx.x] = s;
       __threadfence();
       last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+      if (last) __threadfence();  // one acquiring fence (a fence per warp serialises: ~1 us each)
     }
     __syncthreads();
     if (last) {
-      __threadfence();
       double a = 0.0;
       for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) a += partial[i];
       a = block_sum<double>(a, sm);
@@ -487,10 +487,10 @@ __global__ void __launch_bounds__(256) power_sum_kernel(const float2* __restrict
     __threadfence();
     const unsigned t = atomicAdd(ticket, 1u);
     last = (t == gridDim.x - 1);
+    if (last) __threadfence();  // one acquiring fence (a fence per warp serialises: ~1 us each)
   }
   __syncthreads();
   if (last) {
-    __threadfence();
     double a = 0.0;
     for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) a += partial[i];
     a = block_sum<double>(a, sm);
@@ -832,10 +832,10 @@ __global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __
   if (tid == 0) {
     __threadfence();
     s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (s_last) __threadfence();  // acquiring side, once: 32 warps fencing one after the other cost ~30 us here
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
   const int nt = blockDim.x;
   double local = 0.0;
   for (size_t i = tid; i < ts_count; i += nt) local += (double)__ldcg(&ts[i]);
@@ -954,7 +954,8 @@ __global__ void __launch_bounds__(1024) detect_boxcar_kernel(float* __restrict__
     if (s_hit) {
       float* h = host_out + (size_t)nb * row_stride;
       for (size_t i = tid; i < n; i += nt) h[i] = v[i];
-      __threadfence_system();
+      __syncthreads();
+      if (tid == 0) __threadfence_system();
     }
   }
 }

@@ -83,6 +83,7 @@ struct srtb_b200_ctx {
   bool stat_have[SRTB_B200_STAGE_COUNT] = {};
   // ring path: pinned host destination [streams][MAX_BOXCARS][L] of the current block's positive series (else null)
   float* host_series_dst = nullptr;
+  bool pdl_auto = false;    // programmatic dependent launch for the current block (short kernels only)
   bool res_zeroed = false;  // block path: the per-stream result headers were zeroed before the first kernel
   // process_block
   void* d_baseband = nullptr;
@@ -544,15 +545,17 @@ static bool make_tensor_map(tensor_map_blob* out, const void* base, int rank, co
   return true;
 }
 
-// SRTB_B200_PDL=0: plain launches (A/B); default: the kernels of the block path are launched with programmatic
-// stream serialisation, so each one's set-up overlaps its predecessor's tail (they all call pdl_wait() before
-// touching anything a predecessor produces)
-static bool use_pdl() {
-  static const bool on = [] {
+// Programmatic dependent launch along the block path: each kernel's set-up (tables into shared memory, barriers, tensor
+// memory) overlaps its predecessor's tail; every such kernel calls pdl_wait() before touching anything a predecessor
+// produces. Measured (profiles/r02_pdl.md): +4 % on 2^24-sample blocks, whose kernels last 20-60 us, and -1..-4 % on
+// 2^26-sample blocks, where the early-resident CTAs of the next kernel only take shared memory from the running one.
+// Hence: on for blocks up to 2^25 samples, off above; SRTB_B200_PDL=0 / 1 forces it.
+static bool use_pdl(const srtb_b200_ctx* ctx) {
+  static const int forced = [] {
     const char* e = std::getenv("SRTB_B200_PDL");
-    return !(e && e[0] == '0');
+    return e ? (e[0] == '0' ? 0 : 1) : -1;
   }();
-  return on;
+  return forced >= 0 ? forced == 1 : ctx->pdl_auto;
 }
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(srtb_b200_ctx* ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
@@ -565,7 +568,7 @@ static cudaError_t launch_pdl(srtb_b200_ctx* ctx, void (*kern)(KArgs...), dim3 g
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cfg.numAttrs = use_pdl(ctx) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
@@ -699,6 +702,8 @@ static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, siz
 struct raw_source {
   const void* base = nullptr;  // device pointer to the block's bytes
   int G = 0, o0 = 0, o1 = 0;   // bytes per complex point, byte offsets of its two samples
+  int delta = 0;               // subtracted from the offsets of odd points (gznupsr_a1 word layout)
+  int bits = 0;                // 2 or 4: packed unsigned samples (G, o0, o1 unused)
   bool is_signed = true;
 };
 
@@ -710,10 +715,14 @@ static int launch_col_tma_raw(srtb_b200_ctx* ctx, const raw_source& src, float2*
   }
   *done = false;
   if ((reinterpret_cast<uintptr_t>(src.base) & 15u) || B >= ((size_t)1 << 29)) return 0;
+  // one tile row = T complex points: T * G bytes, or T * bits / 4 bytes of packed samples; TMA wants >= 16 bytes
+  const size_t row_bytes = (RAW == 3) ? (size_t)T * src.bits / 4 : (size_t)T * src.G;
+  const size_t line_bytes = (RAW == 3) ? B * src.bits / 4 : B * src.G;
+  if (row_bytes < 16 || (row_bytes & 15) || (line_bytes & 15) || row_bytes > (size_t)T * 4) return 0;
   tensor_map_blob tm;
-  const cuuint64_t dims[2] = {(cuuint64_t)B * src.G, (cuuint64_t)L};
-  const cuuint64_t strides[1] = {(cuuint64_t)B * src.G};
-  const cuuint32_t box[2] = {(cuuint32_t)(T * src.G), (cuuint32_t)std::min(L, 256)};
+  const cuuint64_t dims[2] = {(cuuint64_t)line_bytes, (cuuint64_t)L};
+  const cuuint64_t strides[1] = {(cuuint64_t)line_bytes};
+  const cuuint32_t box[2] = {(cuuint32_t)row_bytes, (cuuint32_t)std::min(L, 256)};
   if (!make_tensor_map(&tm, src.base, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_UINT8)) return 0;
   big_twiddle btw;
   if (int rc = get_big_twiddles(ctx, LOGL + ilog2(B), &btw)) return rc;
@@ -722,31 +731,42 @@ static int launch_col_tma_raw(srtb_b200_ctx* ctx, const raw_source& src, float2*
   const size_t smem = tile_tma_smem<LOGL, T>::bytes(btw.q);
   const size_t ntiles = B / T;
   unsigned grid = 1;
+  const raw_params rp{src.G, src.o0, src.o1, src.delta, (int)row_bytes, src.bits};
   if constexpr (LOGL >= 7 && LOGL <= 9) {
     if (use_col16()) {
       auto kern16 = fft_col16_tma_kernel<LOGL, T, true, RAW>;
       constexpr int threads = col16_threads<LOGL, T>::value;
       if (int rc = persistent_grid(ctx, kern16, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
-      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
-                    raw_params{src.G, src.o0, src.o1}));
+      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, rp));
       ctx->launches++;
       CK(cudaGetLastError());
       *done = true;
       return 0;
     }
   }
-  auto kern = fft_col_tma_kernel<LOGL, T, true, RAW>;
-  if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
-  kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
-                                                                raw_params{src.G, src.o0, src.o1});
-  ctx->launches++;
-  CK(cudaGetLastError());
-  *done = true;
-  return 0;
+  if constexpr (RAW == 3) {
+    return 0;  // packed samples: sixteen-point kernel only
+  } else {
+    if (src.delta) return 0;
+    auto kern = fft_col_tma_kernel<LOGL, T, true, RAW>;
+    if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
+    kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, rp);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    *done = true;
+    return 0;
+  }
 }
 
 static int dispatch_col_raw(srtb_b200_ctx* ctx, int logl, const raw_source& src, float2* out, size_t B, bool* done) {
   *done = false;
+  if (src.bits) {  // packed 2- / 4-bit samples
+    switch (logl) {
+      case 7: return launch_col_tma_raw<7, 3>(ctx, src, out, B, done);
+      case 8: return launch_col_tma_raw<8, 3>(ctx, src, out, B, done);
+      default: return 0;
+    }
+  }
   switch (logl) {
     case 7: return src.is_signed ? launch_col_tma_raw<7, 1>(ctx, src, out, B, done) : launch_col_tma_raw<7, 2>(ctx, src, out, B, done);
     case 8: return src.is_signed ? launch_col_tma_raw<8, 1>(ctx, src, out, B, done) : launch_col_tma_raw<8, 2>(ctx, src, out, B, done);
@@ -1684,10 +1704,19 @@ static bool raw_sources_for(const srtb_b200_block_config* cfg, const void* d_bas
   const int bits = cfg->baseband_input_bits;
   const int fmt = cfg->baseband_format;
   const size_t N = cfg->baseband_input_count;
-  if (!((bits == 8 || bits == -8) && cfg->window == SRTB_B200_WINDOW_RECTANGLE && N >= ((size_t)1 << 14) &&
-        (fmt == SRTB_B200_FORMAT_SIMPLE || (fmt == SRTB_B200_FORMAT_NAOCPSR_SNAP1 && bits == -8) ||
-         fmt == SRTB_B200_FORMAT_INTERLEAVED_2) &&
-        baseband_bytes >= N * (size_t)streams && get_encode_tiled() && !std::getenv("SRTB_B200_NO_FUSED_UNPACK")))
+  if (cfg->window != SRTB_B200_WINDOW_RECTANGLE || N < ((size_t)1 << 14) || !get_encode_tiled() ||
+      std::getenv("SRTB_B200_NO_FUSED_UNPACK"))
+    return false;
+  if ((bits == 2 || bits == 4) && fmt == SRTB_B200_FORMAT_SIMPLE && baseband_bytes * 8 >= N * (size_t)bits) {
+    // packed unsigned samples (the shipped J1644 configuration is 2-bit): decoded in the first sweep's stage 0
+    raw[0].base = d_baseband;
+    raw[0].bits = bits;
+    raw[0].is_signed = false;
+    return true;
+  }
+  if (!((bits == 8 || bits == -8) && baseband_bytes >= N * (size_t)streams)) return false;
+  if (!(fmt == SRTB_B200_FORMAT_SIMPLE || (fmt == SRTB_B200_FORMAT_NAOCPSR_SNAP1 && bits == -8) ||
+        fmt == SRTB_B200_FORMAT_INTERLEAVED_2 || fmt == SRTB_B200_FORMAT_GZNUPSR_A1_2))
     return false;
   for (int s = 0; s < streams; s++) {
     raw[s].base = d_baseband;
@@ -1695,6 +1724,14 @@ static bool raw_sources_for(const srtb_b200_block_config* cfg, const void* d_bas
     raw[s].G = 2 * streams;
     if (fmt == SRTB_B200_FORMAT_SIMPLE) { raw[s].o0 = 0; raw[s].o1 = 1; }
     else if (fmt == SRTB_B200_FORMAT_NAOCPSR_SNAP1) { raw[s].o0 = 2 * s; raw[s].o1 = 2 * s + 1; }
+    else if (fmt == SRTB_B200_FORMAT_GZNUPSR_A1_2) {
+      // words of four int8 samples alternate between the two streams (unpack.hpp:338-369): point m of stream s is at
+      // byte 4 m + 4 s - 2 (m & 1); always read as signed (the reference casts to int8 whatever the sign of `bits`)
+      raw[s].o0 = 4 * s;
+      raw[s].o1 = 4 * s + 1;
+      raw[s].delta = 2;
+      raw[s].is_signed = true;
+    }
     else { raw[s].o0 = s; raw[s].o1 = s + 2; }
   }
   return true;
@@ -1734,9 +1771,11 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
     ~series_dst_scope() {
       c->host_series_dst = nullptr;
       c->res_zeroed = false;
+      c->pdl_auto = false;
     }
   } series_scope_{ctx};
   ctx->host_series_dst = host_series;
+  ctx->pdl_auto = N <= ((size_t)1 << 25);
   CK(cudaMemsetAsync(ctx->d_res, 0, sizeof(detect_dev_result) * streams, ctx->stream));
   ctx->res_zeroed = true;
   // unpack: fused into the first FFT pass when the samples are 8-bit and every complex point of a

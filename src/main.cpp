@@ -51,7 +51,11 @@ using output_queue = srtb::work_queue<srtb::work::write_signal_work, false>;
 struct round_robin_out_functor {
   std::vector<std::shared_ptr<copy_queue>> queues;
   std::shared_ptr<std::atomic<uint64_t>> submitted;
+  std::shared_ptr<std::atomic<int64_t>> first_ns = std::make_shared<std::atomic<int64_t>>(0);  // first block handed over
   void operator()(std::stop_token st, srtb::work::copy_to_device_work w) {
+    if (submitted->load() == 0)
+      first_ns->store(std::chrono::duration_cast<std::chrono::nanoseconds>(
+                          std::chrono::steady_clock::now().time_since_epoch()).count());
     auto& q = queues[submitted->load() % queues.size()];
     while (!q->push(w)) {
       if (st.stop_requested()) return;
@@ -227,12 +231,17 @@ int main(int argc, char** argv) {
     else source = start_synthetic_source<srtb::io::backend_registry::fastmb_roach2>(0, rate, synth_seconds, rr, st);
     source.join();
     while (done->load() < submitted->load() * streams && !g_interrupted) std::this_thread::yield();
-    const double dt_ = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    // steady state: from the moment the first assembled block is handed to a GPU (start-up allocations are over) to
+    // the last result; the blocks after the first are what arrived in that interval
+    const int64_t now_ns = std::chrono::duration_cast<std::chrono::nanoseconds>(
+                               std::chrono::steady_clock::now().time_since_epoch()).count();
+    const double dt_ = (double)(now_ns - rr.first_ns->load()) * 1e-9;
+    const double blocks_in_dt = submitted->load() > 1 ? (double)(submitted->load() - 1) : 0.0;
     std::printf("{\"blocks\": %llu, \"streams\": %zu, \"samples_per_stream_block\": %zu, \"seconds\": %.6f, "
                 "\"gsamples_per_s\": %.4f, \"target_samples_per_s\": %.3e, \"received_packets\": %llu, "
                 "\"lost_packets\": %llu, \"blocks_with_candidates\": %llu, \"gpus\": %zu}\n",
                 (unsigned long long)submitted->load(), streams, (size_t)cfg.baseband_input_count, dt_,
-                (double)submitted->load() * (double)streams * (double)cfg.baseband_input_count / dt_ / 1e9, rate,
+                blocks_in_dt * (double)streams * (double)cfg.baseband_input_count / dt_ / 1e9, rate,
                 (unsigned long long)st.received->load(), (unsigned long long)st.lost->load(),
                 (unsigned long long)positives->load(), devices.size());
     std::fflush(stdout);

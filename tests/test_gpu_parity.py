@@ -1143,3 +1143,47 @@ def test_process_block_equals_per_pipe_composition(ctx, fmt_name, bits, streams)
         assert np.array_equal(gz, rz)
         assert rel_l2(fused[s_][~gz], ref[~rz]) < REL_L2
         _compare_detect(res[s_], r, hs[s_], series, 6.0)
+
+
+@pytest.mark.parametrize("bits", [2, 4])
+def test_packed_samples_fused_first_sweep_vs_oracle(ctx, oracle, bits):
+    """2- and 4-bit packed baseband (the shipped J1644 configuration is 2-bit: srtb_config_1644-4559.cfg:22) through
+    process_block at a size whose first R2C sweep decodes the packed bytes itself (2^28 samples: four-sweep plan, 32
+    columns per tile = 16 / 32 bytes per row), against the oracle chain; and the same block with the fusion switched
+    off must give the same detector result (the unpack kernel is bit-exact, so only the FFT's first sweep differs)."""
+    import os
+    import subprocess
+    import sys
+    n, C_ = 1 << 28, 1 << 11
+    L = n // 2 // C_
+    rng = np.random.default_rng(280 + bits)
+    raw = rng.integers(0, 256, n * bits // 8, dtype=np.uint8)
+    cfg = make_block_config(n, bits, srtb_b200.FORMAT_SIMPLE, C_, -478.80, f_low=1437.0, bw=-64.0, fs=128e6,
+                            avg_thr=1.5, sk_thr=1.05, snr=8.0, maxbox=256, pairs=[(1418.0, 1422.0)])
+    l0 = ctx.launch_count
+    h_series = np.zeros((srtb_b200.MAX_BOXCARS, L), np.float32)
+    res = ctx.process_block(cfg, torch.from_numpy(raw).pin_memory(), raw.size, h_series, copy_all=True)
+    torch.cuda.synchronize()
+    fused_launches = ctx.launch_count - l0
+    gspec = _from_device_ptr(ctx.block_spectrum_ptr(0), n // 2).reshape(C_, L)
+    work, eres, eseries, _ = oracle.chain(raw, oracle_chain_config(cfg))
+    espec = work[:n].view(np.complex64).reshape(C_, L)
+    rep = _compare_full_size(gspec, espec, res[0], eres, h_series, eseries, 1.05, 8.0, max_flip_rows=64)
+    print(f"{bits}-bit packed, 2^28 samples: {rep}, {fused_launches} launches")
+    # the fused route launches no unpack kernel: one launch fewer than with SRTB_B200_NO_FUSED_UNPACK=1 (checked in a
+    # child process because the switch is read when a block is enqueued and would leak into the other tests)
+    code = ("import os, sys, numpy as np, torch; sys.path[:0] = %r; import srtb_b200; from test_gpu_parity import make_block_config;"
+            "os.environ['SRTB_B200_NO_FUSED_UNPACK'] = '1';"
+            "n = 1 << 28; rng = np.random.default_rng(%d); raw = rng.integers(0, 256, n * %d // 8, dtype=np.uint8);"
+            "ctx = srtb_b200.Context(0, torch.cuda.current_stream().cuda_stream);"
+            "cfg = make_block_config(n, %d, srtb_b200.FORMAT_SIMPLE, 1 << 11, -478.80, f_low=1437.0, bw=-64.0, fs=128e6,"
+            " avg_thr=1.5, sk_thr=1.05, snr=8.0, maxbox=256, pairs=[(1418.0, 1422.0)]);"
+            "l0 = ctx.launch_count; r = ctx.process_block(cfg, torch.from_numpy(raw).pin_memory(), raw.size, None)[0];"
+            "print('RESULT', ctx.launch_count - l0, int(r.zero_count), [int(r.signal_count[b]) for b in range(r.n_boxcars)])"
+            ) % ([p for p in sys.path if 'repo' in p], 280 + bits, bits, bits)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                         env={**os.environ, "PYTHONPATH": os.pathsep.join(sys.path)})
+    assert out.returncode == 0, out.stderr[-1500:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][-1].split(None, 3)
+    assert int(line[1]) == fused_launches + 1, (line, fused_launches)
+    assert int(line[2]) == int(res[0].zero_count)
