@@ -134,6 +134,7 @@ using fft_1d_c2c_work = work<complex_ptr>;
 using rfi_mitigation_s1_work = work<complex_ptr>;
 using dedisperse_work = work<complex_ptr>;
 using ifft_1d_c2c_work = work<complex_ptr>;
+using refft_1d_c2c_work = work<complex_ptr>;
 using watfft_1d_c2c_work = work<complex_ptr>;
 using rfi_mitigation_s2_work = work<complex_ptr>;
 using signal_detect_work = work<complex_ptr>;

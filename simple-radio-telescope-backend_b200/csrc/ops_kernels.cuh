@@ -837,25 +837,40 @@ __global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __
   __syncthreads();
   if (!s_last) return;
   const int nt = blockDim.x;
+  // every access below is a 16-byte vector per thread (a warp touches 512 contiguous bytes): a single CTA that
+  // scatters 4-byte accesses over 32 sectors per instruction spends a microsecond per thousand of them
+  const bool vec = ((reinterpret_cast<uintptr_t>(ts) | reinterpret_cast<uintptr_t>(acc)) & 15u) == 0;
+  auto load4 = [&](size_t i0, float (&v)[4]) {
+    if (vec && i0 + 3 < ts_count) {
+      const float4 q = __ldcg(reinterpret_cast<const float4*>(ts + i0));
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++) v[e] = (i0 + e < ts_count) ? __ldcg(&ts[i0 + e]) : 0.f;
+    }
+  };
   double local = 0.0;
-  for (size_t i = tid; i < ts_count; i += nt) local += (double)__ldcg(&ts[i]);
+  for (size_t i0 = (size_t)4 * tid; i0 < ts_count; i0 += (size_t)4 * nt) {
+    float v[4];
+    load4(i0, v);
+    local += ((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3]);
+  }
   const double total = block_sum<double>(local, smd);
   if (tid == 0) s_mean = (float)total / (float)ts_count;   // map_average: sum / float(count)
   __syncthreads();
   const float mean = s_mean;
-  // inclusive scan: super-tiles of 16 * blockDim.x elements; a thread owns 16 CONTIGUOUS elements (all its loads are
-  // issued up front), scans them in fp64, and one block-wide exclusive scan of the thread totals supplies the offsets
+  // inclusive scan in tiles of 4 * blockDim.x elements: a thread scans its four in fp64, one block-wide exclusive
+  // scan of the thread totals (warp shuffles, then the 32 warp totals) supplies the offsets, `carry` links the tiles
   double carry = 0.0;
-  const size_t tile = (size_t)16 * nt;
+  const size_t tile = (size_t)4 * nt;
   for (size_t base = 0; base < ts_count; base += tile) {
-    const size_t i0 = base + (size_t)16 * tid;
-    float v[16];
+    const size_t i0 = base + (size_t)4 * tid;
+    float v[4];
+    load4(i0, v);
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = (i0 + e < ts_count) ? __ldcg(&ts[i0 + e]) - mean : 0.f;
-    double t = 0.0;  // thread total first; the running sums are formed again when the offset is known (registers)
-#pragma unroll
-    for (int e = 0; e < 16; e++) t += (double)v[e];
-    double incl = t;  // inclusive scan of the thread totals across the warp, then across the 32 warps
+    for (int e = 0; e < 4; e++) v[e] = (i0 + e < ts_count) ? v[e] - mean : 0.f;
+    const double t = ((double)v[0] + (double)v[1]) + ((double)v[2] + (double)v[3]);
+    double incl = t;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const double u = __shfl_up_sync(0xffffffffu, incl, o);
@@ -876,13 +891,22 @@ __global__ void __launch_bounds__(1024) colsum_final_scan_kernel(const float* __
     }
     __syncthreads();
     double run = carry + warp_tot[ly] + (incl - t);
+    float a4[4];
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
+    for (int e = 0; e < 4; e++) {
       run += (double)v[e];
-      if (i0 + e < ts_count) {
-        ts[i0 + e] = v[e];
-        acc[i0 + e] = (float)run;
-      }
+      a4[e] = (float)run;
+    }
+    if (vec && i0 + 3 < ts_count) {
+      *reinterpret_cast<float4*>(ts + i0) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(acc + i0) = make_float4(a4[0], a4[1], a4[2], a4[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; e++)
+        if (i0 + e < ts_count) {
+          ts[i0 + e] = v[e];
+          acc[i0 + e] = a4[e];
+        }
     }
     carry += smd[0];
     __syncthreads();
@@ -921,14 +945,20 @@ __global__ void __launch_bounds__(1024) detect_boxcar_kernel(float* __restrict__
   const size_t b = (size_t)1 << nb;
   float* v = series + (size_t)nb * row_stride;
   const size_t n = (nb == 0) ? ts_count : ts_count - b;
+  // eight independent loads in flight per thread and pass (a single CTA per boxcar is latency bound otherwise)
   double sq = 0.0;
-  if (nb == 0) {
-    for (size_t i = tid; i < n; i += nt) sq += (double)v[i] * (double)v[i];
-  } else {
-    for (size_t i = tid; i < n; i += nt) {
-      const float d = acc[i + b] - acc[i];
-      v[i] = d;
-      sq += (double)d * (double)d;
+  for (size_t i = tid; i < n; i += (size_t)8 * nt) {
+    float d[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const size_t j = i + (size_t)e * nt;
+      d[e] = (j < n) ? ((nb == 0) ? v[j] : acc[j + b] - acc[j]) : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const size_t j = i + (size_t)e * nt;
+      if (nb != 0 && j < n) v[j] = d[e];
+      sq += (double)d[e] * (double)d[e];
     }
   }
   sq = block_sum<double>(sq, smd);
@@ -943,8 +973,17 @@ __global__ void __launch_bounds__(1024) detect_boxcar_kernel(float* __restrict__
   __syncthreads();
   const float thr = s_thr;
   double cnt = 0.0;
-  for (size_t i = tid; i < n; i += nt)
-    if (v[i] > thr) cnt += 1.0;
+  for (size_t i = tid; i < n; i += (size_t)8 * nt) {
+    float d[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const size_t j = i + (size_t)e * nt;
+      d[e] = (j < n) ? v[j] : -INFINITY;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+      if (d[e] > thr) cnt += 1.0;
+  }
   cnt = block_sum<double>(cnt, smd);
   if (tid == 0) res->signal_count[nb] = (unsigned long long)cnt;
   if (host_out) {

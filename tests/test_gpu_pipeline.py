@@ -254,3 +254,77 @@ baseband_output_file_prefix = {prefix}
     # blocks without a detection leave no files (file mode keeps only positives)
     quiet = [w for w in works if not w["series"]]
     assert quiet and not Path(f"{prefix}{quiet[0]['block']}.bin").exists()
+
+
+def test_alternate_pipes_ifft_refft():
+    """ifft_1d_c2c_pipe -> refft_1d_c2c_pipe (the reference's alternative back half, fft_pipe.hpp:88-278) against a
+    float64 DFT, including the overlap-save tail cut (tests/cpp/test_alt_pipes.cpp)"""
+    d = BIN.parent
+    subprocess.run(["make", "-C", str(d), "test_alt_pipes"], check=True, capture_output=True)
+    r = subprocess.run([str(d / "test_alt_pipes")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "alt pipes ok" in r.stdout, (r.stdout[-500:], r.stderr[-1500:])
+
+
+def test_product_executable_replays_a_file(tmp_path, oracle):
+    """src/srtb_b200 — the drop-in executable: reference-style config file (expressions), file source, fused chain on
+    every visible GPU, candidate sink. Its .tim / .npy / .bin output for a block with a burst must match what the
+    oracle finds in that block."""
+    exe = ROOT / "src" / "srtb_b200"
+    subprocess.run(["make", "-C", str(ROOT / "src")], check=True, capture_output=True)
+    logn, C_ = 18, 64
+    n = 1 << logn
+    blocks = [_block(n, s) for s in range(61, 65)]
+    inp = tmp_path / "bb.bin"
+    np.concatenate(blocks).tofile(inp)
+    prefix = tmp_path / "cand_"
+    cfg = tmp_path / "replay.cfg"
+    cfg.write_text(f"""# replay
+baseband_input_count = 2 ** {logn}
+baseband_input_bits = -8
+baseband_format_type = simple
+baseband_freq_low = 1000.0
+baseband_bandwidth = 500.0
+baseband_sample_rate = 1000 * 1e6
+baseband_reserve_sample = 0
+dm = 0
+spectrum_channel_count = 2 ** 6
+mitigate_rfi_average_method_threshold = 5
+mitigate_rfi_spectral_kurtosis_threshold = 1.3
+signal_detect_signal_noise_threshold = 6
+signal_detect_max_boxcar_length = 64
+input_file_path = {inp}
+baseband_output_file_prefix = {prefix}
+log_level = 2
+""")
+    r = subprocess.run([str(exe), "--config_file_name", str(cfg), "--chains_per_gpu", "2", "--ring_depth", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "4 block(s) x 1 stream(s)" in r.stderr
+    tims = sorted(tmp_path.glob("cand_*.tim"))
+    npys = sorted(tmp_path.glob("cand_*.npy"))
+    assert tims and npys, list(tmp_path.iterdir())
+    # every block has the burst: one spectrum per block, and the boxcar-1 series of block 0 equals the oracle's
+    assert len(npys) == 4
+    spec = np.load(npys[0])
+    assert spec.shape == (C_, n // 2 // C_) and spec.dtype == np.complex64
+    import oracle_lib
+    oc = oracle_lib.ChainConfig()
+    oc.baseband_input_count, oc.baseband_input_bits, oc.window = n, -8, 0
+    oc.baseband_freq_low, oc.baseband_bandwidth, oc.baseband_sample_rate, oc.dm = 1000.0, 500.0, 1e9, 0.0
+    oc.baseband_reserve_sample = 0
+    oc.rfi_average_threshold, oc.rfi_sk_threshold, oc.spectrum_channel_count = 5.0, 1.3, C_
+    oc.snr_threshold, oc.channel_threshold, oc.max_boxcar_length = 6.0, 0.9, 64
+    oc.n_rfi_pairs = 0
+    work, eres, eseries, _ = oracle.chain(blocks[0].view(np.uint8), oc)
+    espec = work[:n].view(np.complex64).reshape(C_, -1)
+    # file replays carry no packet counter: the candidate files are named after the block's timestamp
+    # (write_signal_pipe.hpp:145-148), so block 0's files are found by content
+    keep = ~np.all(espec == 0, axis=1)
+    match = [p for p in npys if np.linalg.norm(np.load(p)[keep] - espec[keep]) / np.linalg.norm(espec[keep]) < 5e-5]
+    assert len(match) == 1, [p.name for p in npys]
+    stem = match[0].name.split(".")[0]
+    assert (tmp_path / f"{stem}.bin").stat().st_size == n                      # the raw block next to it
+    assert eres.signal_count[0] > 0
+    ts = np.fromfile(tmp_path / f"{stem}.1.tim", np.float32)
+    assert ts.size == int(eres.series_length[0])
+    assert np.abs(ts - eseries[0, :ts.size]).max() < 2e-4 * np.sqrt(np.mean(eseries[0, :ts.size].astype(np.float64) ** 2))
