@@ -128,30 +128,6 @@ __device__ __forceinline__ void bigrow_stage_table(float2* __restrict__ p, const
   }
 }
 
-#ifndef SRTB_BIGROW_FAST_SINCOS
-#define SRTB_BIGROW_FAST_SINCOS 1
-#endif
-
-// s1 + chirp on one spectrum bin: f and 1/f in fp64 (K12: coherent_dedispersion.hpp:133-150)
-__device__ __forceinline__ float2 bigrow_chirp_point(float2 v, double f, double r, const row_chirp_params& cp,
-                                                     float limit) {
-  const double q = (f - cp.f_c) * cp.inv_fc;
-  const double k = (cp.ddm * r) * (q * q);
-  // k mod 1 in [-0.5, 0.5]: e^{-2 pi i k} is unchanged by the integer that is dropped
-  constexpr double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
-  const double kr = __dadd_rn(__dadd_rn(k, MAGIC), -MAGIC);
-  const float frac = (float)(k - kr);
-  float s, c;
-#if SRTB_BIGROW_FAST_SINCOS
-  __sincosf(-6.283185307179586f * frac, &s, &c);  // SFU, argument in [-pi, pi]: abs error <= 2^-21
-#else
-  sincospif(-2.0f * frac, &s, &c);
-#endif
-  const float scale = (v.x * v.x + v.y * v.y > limit) ? 0.f : cp.coef;  // rfi_mitigation_pipe.hpp:66-79
-  const float wr = c * scale, wi = s * scale;
-  return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
-}
-
 // CHIRP: 0 = plain transform; otherwise s1 + chirp on load, 1/f of successive bins by Newton steps from the neighbour:
 //   1 = one step along a butterfly's inputs (B1 bins apart) and one to the adjacent bin, 3 = two and one,
 //   4 = two and two, 2 = a correctly rounded reciprocal for every bin (widely spaced bins of short test blocks)
@@ -264,9 +240,9 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
           float2* const p = (i < 8 ? pa : pb) + (i & 7) * S1;
           mbar_wait(&mbar[(i < 8 ? hA : hB) * 8 + (i & 7)], i < 8 ? parA : parB);
           const float4 q = *reinterpret_cast<const float4*>(p);
-          const float2 ya = bigrow_chirp_point(make_float2(q.x, q.y), fa, ra, cp, limit);
+          const float2 ya = chirp_point(make_float2(q.x, q.y), fa, ra, cp, limit);
           const double fb = fma(cp.df, idx + 1.0, cp.f_min);
-          const float2 yb = bigrow_chirp_point(make_float2(q.z, q.w), fb, refine_near(ra, fb), cp, limit);
+          const float2 yb = chirp_point(make_float2(q.z, q.w), fb, refine_near(ra, fb), cp, limit);
           *reinterpret_cast<float4*>(p) = make_float4(ya.x, ya.y, yb.x, yb.y);
         }
       }

@@ -692,6 +692,30 @@ struct row_chirp_params {
   int newton;             // whole-row kernel: reciprocal mode = the kernel's CHIRP template value (1, 3, 4; 2 = exact)
 };
 
+#ifndef SRTB_FAST_SINCOS
+#define SRTB_FAST_SINCOS 1
+#endif
+
+// s1 + chirp on one spectrum bin: f and 1/f in fp64 (K12: coherent_dedispersion.hpp:133-150)
+__device__ __forceinline__ float2 chirp_point(float2 v, double f, double r, const row_chirp_params& cp,
+                                                     float limit) {
+  const double q = (f - cp.f_c) * cp.inv_fc;
+  const double k = (cp.ddm * r) * (q * q);
+  // k mod 1 in [-0.5, 0.5]: e^{-2 pi i k} is unchanged by the integer that is dropped
+  constexpr double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+  const double kr = __dadd_rn(__dadd_rn(k, MAGIC), -MAGIC);
+  const float frac = (float)(k - kr);
+  float s, c;
+#if SRTB_FAST_SINCOS
+  __sincosf(-6.283185307179586f * frac, &s, &c);  // SFU, argument in [-pi, pi]: abs error <= 2^-21
+#else
+  sincospif(-2.0f * frac, &s, &c);
+#endif
+  const float scale = (v.x * v.x + v.y * v.y > limit) ? 0.f : cp.coef;  // rfi_mitigation_pipe.hpp:66-79
+  const float wr = c * scale, wi = s * scale;
+  return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+}
+
 // ---------------------------------------------------------------------------------
 // Row pass with sixteen points per thread (radix-16 stages: L = 4096 as 16^3, 2048 as 16*16*8,
 // 1024 as 16*16*4, 256 as 16*16): three stages and five CTA barriers per 4096-point row instead of
@@ -1110,11 +1134,15 @@ struct col16_threads {
   static constexpr int min_blocks = (768 / value) < 1 ? 1 : (768 / value);  // aim at 24 resident warps per SM
 };
 
-template <int LOGL, int T, bool FWD, int RAW = 0>
-__global__ void __launch_bounds__(col16_threads<LOGL, T>::value, col16_threads<LOGL, T>::min_blocks)
+// CH (long waterfall rows, process_block only): rfi_mitigation_s1 (zap + normalise) and the dedispersion chirp are
+// applied to the spectrum as the tile's points are taken out of shared memory (the bin of point idx of column b0 + t
+// of row a is a L B + idx B + b0 + t); 1/f by Newton steps from the point U B bins below (cp.newton = 1 or 2 steps,
+// else the exact reciprocal), like the whole-row kernel.
+template <int LOGL, int T, bool FWD, int RAW = 0, bool CH = false>
+__global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_threads<LOGL, T>::min_blocks)
     fft_col16_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, size_t B,
                          uint32_t btiles, uint32_t ntiles, big_twiddle btw, const float2* __restrict__ tw,
-                         raw_params rp) {
+                         raw_params rp, row_chirp_params cp) {
   using SC = sched16<LOGL>;
   constexpr int L = 1 << LOGL, U = L / 16, S = SC::S, BUF = tile_tma_smem<LOGL, T>::BUF;
   constexpr int ROWS_PER_BOX = (L < 256) ? L : 256;
@@ -1168,6 +1196,28 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, col16_threads<L
     if constexpr (RAW == 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) v[e] = sm[(u + e * U) * T + t];
+      if constexpr (CH) {
+        const uint32_t ta = tile / btiles, tb0 = (tile % btiles) * T;
+        const float limit = cp.threshold * __ldg(cp.mean);
+        double idx = (double)(((size_t)ta << LOGL) * B + (size_t)u * B + tb0 + t);
+        const double step = (double)((size_t)U * B);
+        double f = fma(cp.df, idx, cp.f_min);
+        double r = __drcp_rn(f);
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          if (e > 0) {
+            idx += step;
+            f = fma(cp.df, idx, cp.f_min);
+            if (cp.newton == 0) {
+              r = __drcp_rn(f);
+            } else {
+              r = fma(r, fma(-f, r, 1.0), r);
+              if (cp.newton > 1) r = fma(r, fma(-f, r, 1.0), r);
+            }
+          }
+          v[e] = chirp_point(v[e], f, r, cp, limit);
+        }
+      }
     } else if constexpr (RAW == 3) {
       // packed samples: point t of a row occupies bits [2 bits t, 2 bits (t + 1)) counted from the row's MSB
       const int nb = rp.bits, per_byte = 4 / nb, p = t % per_byte;
@@ -1237,11 +1287,11 @@ template <int LOGL, int T, bool FWD>
 __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOGL, T>::min_blocks)
     fft_trans_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, uint32_t A,
                          uint32_t S_, uint32_t L1, uint32_t k1tiles, uint32_t ntiles,
-                         const float2* __restrict__ tw) {
+                         const float2* __restrict__ tw, float2* __restrict__ tile_stats) {
   using SC = sched<LOGL>;
   using LAY = tile_layout<LOGL, T, MODE_TRANS>;
   constexpr int L = 1 << LOGL, U = L / 8, S = SC::S, BUF = tile_tma_smem<LOGL, T>::BUF;
-  static_assert(L <= 256 || true, "");
+  __shared__ float2 stat_sm[2][32];
   extern __shared__ __align__(128) unsigned char smraw[];
   float2* const buf0 = reinterpret_cast<float2*>(smraw);
   float2* const buf1 = buf0 + BUF;
@@ -1318,7 +1368,30 @@ __global__ void __launch_bounds__(pass_threads<LOGL, T>::value, pass_threads<LOG
 #pragma unroll
       for (int e = 0; e < 8; e++) o[(size_t)A * e * U] = v[e];
     }
+    if (tile_stats) {
+      float s2 = 0.f, s4 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const float p = v[e].x * v[e].x + v[e].y * v[e].y;
+        s2 += p;
+        s4 += p * p;
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o2);
+        s4 += __shfl_xor_sync(0xffffffffu, s4, o2);
+      }
+      if ((tid & 31) == 0) stat_sm[it & 1][tid >> 5] = make_float2(s2, s4);
+    }
     __syncthreads();
+    if (tile_stats && tid == 0) {
+      float2 a = stat_sm[it & 1][0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+        a.x += stat_sm[it & 1][w].x;
+        a.y += stat_sm[it & 1][w].y;
+      }
+      tile_stats[tile] = a;
+    }
   }
 }
 
@@ -1337,10 +1410,11 @@ template <int LOGL, int T, bool FWD>
 __global__ void __launch_bounds__(T * ((1 << LOGL) / 16), 768 / (T * ((1 << LOGL) / 16)))
     fft_trans16_tma_kernel(const __grid_constant__ tensor_map_blob tmap, float2* __restrict__ out, uint32_t A,
                            uint32_t S_, uint32_t L1, uint32_t k1tiles, uint32_t ntiles,
-                           const float2* __restrict__ tw, uint32_t rest_inner) {
+                           const float2* __restrict__ tw, uint32_t rest_inner, float2* __restrict__ tile_stats) {
   using SC = sched16<LOGL>;
   static_assert(SC::S == 2 && T == 16 && LOGL <= 8, "two radix stages, sixteen rows per tile");
   constexpr int L = 1 << LOGL, U = L / 16, BUF = tile_tma_smem<LOGL, T>::BUF;
+  __shared__ float2 stat_sm[2][32];
   extern __shared__ __align__(128) unsigned char smraw[];
   float2* const buf0 = reinterpret_cast<float2*>(smraw);
   float2* const buf1 = buf0 + BUF;
@@ -1392,7 +1466,32 @@ __global__ void __launch_bounds__(T * ((1 << LOGL) / 16), 768 / (T * ((1 << LOGL
 #pragma unroll
       for (int e = 0; e < 16; e++) o[(size_t)A * e * U] = v[e];
     }
+    if (tile_stats) {
+      // spectral-kurtosis statistics of this tile (sum |y|^2, sum |y|^4) for the row decision taken after the sweep
+      // (rfi_mitigation.hpp:292-341): warp partials now, folded by thread 0 after the tile's closing barrier
+      float s2 = 0.f, s4 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        const float p = v[e].x * v[e].x + v[e].y * v[e].y;
+        s2 += p;
+        s4 += p * p;
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o2);
+        s4 += __shfl_xor_sync(0xffffffffu, s4, o2);
+      }
+      if ((tid & 31) == 0) stat_sm[it & 1][tid >> 5] = make_float2(s2, s4);
+    }
     __syncthreads();
+    if (tile_stats && tid == 0) {
+      float2 a = stat_sm[it & 1][0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+        a.x += stat_sm[it & 1][w].x;
+        a.y += stat_sm[it & 1][w].y;
+      }
+      tile_stats[tile] = a;
+    }
   }
 }
 

@@ -661,28 +661,61 @@ struct detect_dev_result {
   float threshold[32];
 };
 
+// K14 for long rows (process_block, rows above 2^14): the last waterfall sweep left per-tile (sum |y|^2, sum |y|^4);
+// one thread per channel row folds its tiles in index order and decides (rfi_mitigation.hpp:292-341; NaN -> keep)
+__global__ void __launch_bounds__(256) sk_decide_kernel(const float2* __restrict__ tile_stats, unsigned tiles_per_row,
+                                                        size_t chan_count, float m_count, float thr_lo, float thr_hi,
+                                                        unsigned char* __restrict__ zap) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= chan_count) return;
+  float s2 = 0.f, s4 = 0.f;
+  for (unsigned t = 0; t < tiles_per_row; t++) {
+    const float2 v = tile_stats[c * tiles_per_row + t];
+    s2 += v.x;
+    s4 += v.y;
+  }
+  const float sk = m_count * (s4 / (s2 * s2));
+  zap[c] = (sk > thr_hi || sk < thr_lo) ? 1 : 0;
+}
+
 // K17 stage 1: partial column sums over a chunk of channels. Thread = 2 adjacent time
 // samples (one float4 load), lanes along time (coalesced); blockIdx.y = channel chunk.
-__global__ void __launch_bounds__(256) colsum_partial_kernel(const float2* __restrict__ x,
+// zap (optional): rows flagged by sk_decide_kernel are zeroed here (K15) instead of being added.
+__global__ void __launch_bounds__(256) colsum_partial_kernel(float2* __restrict__ x,
                                                              size_t time_count, size_t chan_count,
                                                              size_t ts_count, size_t rows_per_chunk,
-                                                             float* __restrict__ partial) {
+                                                             float* __restrict__ partial,
+                                                             const unsigned char* __restrict__ zap) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t j2 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (j2 >= ts_count) return;
+  if (j2 >= time_count) return;
   const size_t c0 = (size_t)blockIdx.y * rows_per_chunk;
   const size_t c1 = min(c0 + rows_per_chunk, chan_count);
   float a0 = 0.f, a1 = 0.f;
-  const bool two = (j2 + 1 < ts_count);
+  const bool two = (j2 + 1 < time_count);
   const bool vec = ((time_count & 1) == 0);
   if (vec && two) {
 #pragma unroll 8
     for (size_t c = c0; c < c1; c++) {
-      const float4 v = *reinterpret_cast<const float4*>(x + c * time_count + j2);
+      float4* p = reinterpret_cast<float4*>(x + c * time_count + j2);
+      if (zap && zap[c]) {
+        *p = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      const float4 v = *p;
       a0 += v.x * v.x + v.y * v.y;
       a1 += v.z * v.z + v.w * v.w;
     }
   } else {
     for (size_t c = c0; c < c1; c++) {
+      if (zap && zap[c]) {
+        x[c * time_count + j2] = make_float2(0.f, 0.f);
+        if (two) x[c * time_count + j2 + 1] = make_float2(0.f, 0.f);
+        continue;
+      }
       const float2 v = x[c * time_count + j2];
       a0 += v.x * v.x + v.y * v.y;
       if (two) {
@@ -691,9 +724,11 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float2* __res
       }
     }
   }
-  float* p = partial + (size_t)blockIdx.y * ts_count + j2;
-  p[0] = a0;
-  if (two) p[1] = a1;
+  if (j2 < ts_count) {
+    float* p = partial + (size_t)blockIdx.y * ts_count + j2;
+    p[0] = a0;
+    if (j2 + 1 < ts_count) p[1] = a1;
+  }
 }
 
 // K14 + K15 + K17 stage 1 fused (process_block only): one sweep over the dynamic spectrum computes

@@ -76,6 +76,11 @@ struct srtb_b200_ctx {
   size_t sweep_buf_bytes = 0;
   void* sweep_res = nullptr;
   size_t sweep_res_bytes = 0;
+  // long waterfall rows: per-tile SK statistics of the last sweep, per-row zap flags
+  void* long_stats = nullptr;
+  size_t long_stats_bytes = 0;
+  void* long_zap = nullptr;
+  size_t long_zap_bytes = 0;
   // optional per-stage timing (srtb_b200_stage_stats)
   bool stats_on = false;
   cudaEvent_t stat_ev[SRTB_B200_STAGE_COUNT][2] = {};
@@ -216,6 +221,8 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   cudaFree(ctx->d_baseband);
   cudaFree(ctx->sweep_buf);
   cudaFree(ctx->sweep_res);
+  cudaFree(ctx->long_stats);
+  cudaFree(ctx->long_zap);
   for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) {
     cudaFree(ctx->slot_baseband[i]);
     for (auto& p : ctx->slot_stream_buf[i]) cudaFree(p);
@@ -658,10 +665,11 @@ static bool wide_col(size_t A, size_t L, size_t B) {
 }
 
 template <int LOGL, bool FWD, int TT = col_t<LOGL>::value>
-static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t B, bool* done) {
+static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t A, size_t B, bool* done,
+                          const row_chirp_params* chirp = nullptr) {
   constexpr int T = TT, L = 1 << LOGL;
   if constexpr (LOGL == 7 && TT == col_t<LOGL>::value) {
-    if (use_col16() && wide_col(A, L, B)) return launch_col_tma<LOGL, FWD, 32>(ctx, in, out, A, B, done);
+    if (use_col16() && wide_col(A, L, B) && !chirp) return launch_col_tma<LOGL, FWD, 32>(ctx, in, out, A, B, done);
   }
   *done = false;
   if ((reinterpret_cast<uintptr_t>(in) & 15u) || A * L >= ((size_t)1 << 31) || B >= ((size_t)1 << 31)) return 0;
@@ -682,13 +690,27 @@ static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, siz
       auto kern16 = fft_col16_tma_kernel<LOGL, T, FWD>;
       constexpr int threads = col16_threads<LOGL, T>::value;
       if (int rc = persistent_grid(ctx, kern16, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
-      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, raw_params{}));
+      if constexpr (!FWD) {
+        if (chirp) {  // s1 + chirp applied as the tile is read (long waterfall rows)
+          auto kernc = fft_col16_tma_kernel<LOGL, T, FWD, 0, true>;
+          if (int rc = persistent_grid(ctx, kernc, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
+          CK(launch_pdl(ctx, kernc, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
+                        raw_params{}, *chirp));
+          ctx->launches++;
+          CK(cudaGetLastError());
+          *done = true;
+          return 0;
+        }
+      }
+      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
+                    raw_params{}, row_chirp_params{}));
       ctx->launches++;
       CK(cudaGetLastError());
       *done = true;
       return 0;
     }
   }
+  if (chirp) return 0;  // the chirp-on-load sweep exists for the sixteen-point kernel only
   auto kern = fft_col_tma_kernel<LOGL, T, FWD>;
   if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
   kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, raw_params{});
@@ -737,7 +759,8 @@ static int launch_col_tma_raw(srtb_b200_ctx* ctx, const raw_source& src, float2*
       auto kern16 = fft_col16_tma_kernel<LOGL, T, true, RAW>;
       constexpr int threads = col16_threads<LOGL, T>::value;
       if (int rc = persistent_grid(ctx, kern16, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
-      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, rp));
+      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, rp,
+                    row_chirp_params{}));
       ctx->launches++;
       CK(cudaGetLastError());
       *done = true;
@@ -778,7 +801,7 @@ static int dispatch_col_raw(srtb_b200_ctx* ctx, int logl, const raw_source& src,
 
 template <int LOGL, bool FWD>
 static int launch_trans_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, size_t batch, size_t A, size_t L1,
-                            bool* done, size_t rest_inner = 0) {
+                            bool* done, size_t rest_inner = 0, float2* tile_stats = nullptr) {
   constexpr int T = col_t<LOGL>::value, L = 1 << LOGL;
   *done = false;
   const size_t S = A / L1;
@@ -800,7 +823,8 @@ static int launch_trans_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, s
       unsigned grid16 = 1;
       if (int rc = persistent_grid(ctx, kern16, threads, smem16, smem16, ntiles16, &grid16)) return rc;
       kern16<<<grid16, threads, smem16, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
-                                                     (uint32_t)k1tiles16, (uint32_t)ntiles16, tw, (uint32_t)rest_inner);
+                                                     (uint32_t)k1tiles16, (uint32_t)ntiles16, tw, (uint32_t)rest_inner,
+                                                     tile_stats);
       ctx->launches++;
       CK(cudaGetLastError());
       *done = true;
@@ -814,7 +838,7 @@ static int launch_trans_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, s
   unsigned grid = 1;
   if (int rc = persistent_grid(ctx, kern, pass_threads<LOGL, T>::value, smem, smem, ntiles, &grid)) return rc;
   kern<<<grid, pass_threads<LOGL, T>::value, smem, ctx->stream>>>(tm, out, (uint32_t)A, (uint32_t)S, (uint32_t)L1,
-                                                                  (uint32_t)k1tiles, (uint32_t)ntiles, tw);
+                                                                  (uint32_t)k1tiles, (uint32_t)ntiles, tw, tile_stats);
   ctx->launches++;
   CK(cudaGetLastError());
   *done = true;
@@ -1480,7 +1504,8 @@ static int detect_enqueue(srtb_b200_ctx* ctx, int slot, const float2* x, size_t 
   if (int rc = detect_prepare(ctx, slot, time_count, chunks * ts_count)) return rc;
   CK(cudaMemsetAsync(ctx->d_res + slot, 0, sizeof(detect_dev_result), ctx->stream));
   dim3 g((unsigned)ctas_per_chunk, (unsigned)chunks);
-  colsum_partial_kernel<<<g, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, ctx->colsum_partial);
+  colsum_partial_kernel<<<g, 256, 0, ctx->stream>>>(const_cast<float2*>(x), time_count, chan_count, ts_count, rows_per_chunk,
+                                                    ctx->colsum_partial, nullptr);
   ctx->launches++;
   CK(cudaGetLastError());
   return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
@@ -1605,6 +1630,89 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
     default: rc = watfft_sk_launch<12>(ctx, x, chan_count, lo_, hi_, ts_count, &chunks, chirp, src); break;
   }
   if (rc) return rc;
+  stats_.reset();
+  return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
+}
+
+// Rows longer than one CTA's shared memory (2^15 .. 2^20 time samples; the shipped configurations have 2^18):
+//   sweep A  column FFTs with rfi_mitigation_s1 + the chirp applied as the tile is read  (spectrum -> scratch)
+//   sweep B  transposing last sweep, leaving per-tile (sum |y|^2, sum |y|^4)              (scratch -> spectrum)
+//   decide   one thread per channel folds its tiles and takes the SK decision
+//   sums     the detector's partial column sums, zeroing the flagged rows on the way (one read of the spectrum)
+// i.e. 20 bytes per sample instead of the 32 of dedisperse + two-sweep waterfall + SK + column sums.
+static bool long_fusable(size_t time_count, const float2* x) {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_LONG_FUSED");
+    return !(e && e[0] == '0');
+  }();
+  const int q = ilog2(time_count);
+  return on && use_fused_chirp() && use_col16() && is_pow2(time_count) && q >= 15 && q <= 18 && get_encode_tiled() &&
+         (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+}
+
+static int watfft_long_fused(srtb_b200_ctx* ctx, int slot, float2* x, const float2* src, size_t time_count,
+                             size_t chan_count, size_t time_reserved_count, float sk_threshold, float snr,
+                             float chan_thr, size_t max_boxcar, const row_chirp_params& chirp) {
+  const size_t ts_count = (time_count <= time_reserved_count) ? time_count : time_count - time_reserved_count;
+  const int q = ilog2(time_count);
+  const int l1 = (q + 1) / 2, l2 = q - l1;
+  const size_t L1 = (size_t)1 << l1, L2 = (size_t)1 << l2;
+  if (int rc = ensure(ctx, &ctx->fft_scratch, &ctx->fft_scratch_bytes, chan_count * time_count * sizeof(float2))) return rc;
+  float2* s = static_cast<float2*>(ctx->fft_scratch);
+  const size_t T_last = (l2 <= 8) ? 16 : 8;  // rows per tile of the last sweep (col_t)
+  const size_t tiles_per_row = L1 / T_last;
+  if (int rc = ensure(ctx, &ctx->long_stats, &ctx->long_stats_bytes, chan_count * tiles_per_row * sizeof(float2))) return rc;
+  if (int rc = ensure(ctx, &ctx->long_zap, &ctx->long_zap_bytes, chan_count)) return rc;
+  float2* stats = static_cast<float2*>(ctx->long_stats);
+  unsigned char* zap = static_cast<unsigned char*>(ctx->long_zap);
+  row_chirp_params cp = chirp;
+  {
+    // Newton steps for 1/f between a thread's consecutive points, U * B = (L1 / 16) * L2 bins apart
+    const double fa = std::min(std::fabs(cp.f_min), std::fabs(cp.f_c));
+    const double delta = (double)((L1 / 16) * L2) * std::fabs(cp.df) / fa, d2 = delta * delta;
+    const double qq = (cp.f_c - cp.f_min) * cp.inv_fc;
+    const double kmax = std::max(1.0, std::fabs(cp.ddm) / fa * qq * qq);
+    cp.newton = (d2 <= 0x1p-52) ? 1 : ((d2 * d2 * kmax < 1e-9) ? 2 : 0);
+  }
+  std::unique_ptr<stage_scope> stats_(new stage_scope(ctx, SRTB_B200_STAGE_FUSED_WATERFALL, 40.0 * (double)time_count * (double)chan_count));
+  bool done = false;
+  int rc = 0;
+  switch (l1) {
+    case 8: rc = launch_col_tma<8, false>(ctx, src, s, chan_count, L2, &done, &cp); break;
+    case 9: rc = launch_col_tma<9, false>(ctx, src, s, chan_count, L2, &done, &cp); break;
+    default: break;
+  }
+  if (rc) return rc;
+  if (!done) return SRTB_B200_E_UNSUPPORTED;
+  done = false;
+  switch (l2) {
+    case 7: rc = launch_trans_tma<7, false>(ctx, s, x, chan_count, L1, L1, &done, 0, stats); break;
+    case 8: rc = launch_trans_tma<8, false>(ctx, s, x, chan_count, L1, L1, &done, 0, stats); break;
+    case 9: rc = launch_trans_tma<9, false>(ctx, s, x, chan_count, L1, L1, &done, 0, stats); break;
+    default: break;
+  }
+  if (rc) return rc;
+  if (!done) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "watfft: long fused plan needs the TMA last sweep");
+  const float M_ = static_cast<float>(time_count);
+  float hi = sk_threshold, lo = 2 - sk_threshold;
+  if (lo > hi) std::swap(lo, hi);
+  const float lo_ = lo * ((M_ - 1) / (M_ + 1)) + 1, hi_ = hi * ((M_ - 1) / (M_ + 1)) + 1;
+  sk_decide_kernel<<<(unsigned)((chan_count + 255) / 256), 256, 0, ctx->stream>>>(stats, (unsigned)tiles_per_row, chan_count,
+                                                                             M_, lo_, hi_, zap);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  // partial column sums (all time samples are visited so that flagged rows are zeroed completely)
+  const size_t ctas_per_chunk = (time_count + 511) / 512;
+  size_t chunks = std::max<size_t>(1, (size_t)ctx->sm_count * 8 / ctas_per_chunk);
+  chunks = std::min(chunks, std::min<size_t>(128, chan_count));
+  const size_t rows_per_chunk = (chan_count + chunks - 1) / chunks;
+  chunks = (chan_count + rows_per_chunk - 1) / rows_per_chunk;
+  if (int rc2 = detect_prepare(ctx, slot, time_count, chunks * ts_count)) return rc2;
+  if (!ctx->res_zeroed) CK(cudaMemsetAsync(ctx->d_res + slot, 0, sizeof(detect_dev_result), ctx->stream));
+  dim3 g((unsigned)ctas_per_chunk, (unsigned)chunks);
+  colsum_partial_kernel<<<g, 256, 0, ctx->stream>>>(x, time_count, chan_count, ts_count, rows_per_chunk, ctx->colsum_partial, zap);
+  ctx->launches++;
+  CK(cudaGetLastError());
   stats_.reset();
   return detect_tail(ctx, slot, x, time_count, chan_count, ts_count, chunks, snr, chan_thr, max_boxcar);
 }
@@ -1846,6 +1954,22 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
         return rc;
       continue;
     }
+    if (long_fusable(L, reinterpret_cast<float2*>(buf))) {
+      // long rows: manual zap on the raw spectrum, then chirp-on-load column sweep, last sweep with SK statistics,
+      // decision, column sums (20 bytes per sample)
+      if (int rc = zero_bin_ranges(ctx, reinterpret_cast<float2*>(buf), bins)) return rc;
+      constexpr double D = 4.148808e3;
+      row_chirp_params cp{(double)f_min, (double)df, 1.0 / (double)f_c, (double)f_c, (D * 1e6) * (double)cfg->dm,
+                          ctx->mean, cfg->mitigate_rfi_average_method_threshold, coef, 0};
+      const int rc = watfft_long_fused(ctx, s, reinterpret_cast<float2*>(buf), reinterpret_cast<const float2*>(buf), L, batch,
+                                       reserved, cfg->mitigate_rfi_spectral_kurtosis_threshold,
+                                       cfg->signal_detect_signal_noise_threshold, cfg->signal_detect_channel_threshold,
+                                       cfg->signal_detect_max_boxcar_length, cp);
+      if (rc != SRTB_B200_E_UNSUPPORTED) {
+        if (rc) return rc;
+        continue;
+      }
+    }
     if (int rc = rfi_s1_dedisperse_fused(ctx, reinterpret_cast<float2*>(buf), Nc,
                                          cfg->mitigate_rfi_average_method_threshold, coef, bins, f_min, f_c, df, cfg->dm,
                                          /*mean_ready=*/true))
@@ -1978,14 +2102,24 @@ extern "C" int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b
       }
       if (rc) return rc;
     }
-    const bool fused = fuse_chirp && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0;
+    const bool longf = long_fusable(L, W) && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0;
+    const bool fused = (fuse_chirp || longf) && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0;
     if (fused)  // the manual zap does not depend on the DM: once, on the kept spectrum
       if (int rc = zero_bin_ranges(ctx, reinterpret_cast<float2*>(buf), bins)) return rc;
     for (size_t j = 0; j < n_dm; j++) {
       const size_t reserved = srtb_b200_nsamps_reserved(N, cfg->spectrum_channel_count, cfg->baseband_freq_low,
                                                         cfg->baseband_bandwidth, cfg->baseband_sample_rate, h_dms[j],
                                                         cfg->baseband_reserve_sample) / batch;
-      if (fused) {
+      if (longf) {
+        constexpr double D = 4.148808e3;
+        row_chirp_params cp{(double)f_min, (double)df, 1.0 / (double)f_c, (double)f_c, (D * 1e6) * (double)h_dms[j],
+                            ctx->mean, cfg->mitigate_rfi_average_method_threshold, coef, 0};
+        if (int rc = watfft_long_fused(ctx, 0, W, reinterpret_cast<const float2*>(buf), L, batch, reserved,
+                                       cfg->mitigate_rfi_spectral_kurtosis_threshold,
+                                       cfg->signal_detect_signal_noise_threshold, cfg->signal_detect_channel_threshold,
+                                       cfg->signal_detect_max_boxcar_length, cp))
+          return rc;
+      } else if (fused) {
         constexpr double D = 4.148808e3;
         row_chirp_params cp{(double)f_min, (double)df, 1.0 / (double)f_c, (double)f_c, (D * 1e6) * (double)h_dms[j],
                             ctx->mean, cfg->mitigate_rfi_average_method_threshold, coef};

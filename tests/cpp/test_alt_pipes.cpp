@@ -28,11 +28,11 @@ int main() {
   const size_t Nc = 1 << 12, C = 1 << 4;
   cfg.baseband_input_count = 2 * Nc;
   cfg.spectrum_channel_count = C;
-  cfg.baseband_reserve_sample = true;      // a non-zero tail: dm / band chosen so that nsamps_reserved() = 2 * 512
+  cfg.baseband_reserve_sample = true;      // a non-zero overlap-save tail
   cfg.baseband_freq_low = 1000.0f;
   cfg.baseband_bandwidth = 500.0f;
   cfg.baseband_sample_rate = 1e9f;
-  cfg.dm = 0.1f;
+  cfg.dm = 2e-4f;  // dispersive delay of ~460 samples across the band: nsamps_reserved() = 928 of 8192
   const size_t reserved_complex = srtb::codd::nsamps_reserved() / 2;
   CHECK(reserved_complex > 0 && reserved_complex < Nc);
   srtb::cuda_queue q{0};

@@ -476,8 +476,10 @@ def synth_baseband(n, seed, tone=True, pulse=True):
 
 @pytest.mark.parametrize("logn,C_,dm", [(16, 16, 0.0), (20, 256, 10.0), (18, 128, 0.5), (17, 128, 0.0),
                                         (20, 64, 10.0), (20, 32, 56.778), (22, 128, 562.05), (23, 512, 3.0),
+                                        (22, 64, 56.778), (23, 64, 10.0), (21, 8, 3.0), (22, 8, 30.0),
                                         (24, 2048, 56.778)])     # the last one: BASELINE config #2 at full size
-# (20, 64), (23, 512): rows of 2^13; (20, 32), (22, 128): rows of 2^14 -> the whole-row kernel (fft_bigrow.cuh)
+# (20, 64), (23, 512): rows of 2^13; (20, 32), (22, 128): rows of 2^14 -> the whole-row kernel (fft_bigrow.cuh);
+# (22, 64), (23, 64), (21, 8), (22, 8): rows of 2^15 .. 2^18 -> chirp-on-load column sweep + last sweep with SK statistics
 def test_chain_vs_oracle(ctx, oracle, logn, C_, dm):
     n = 1 << logn
     bb = synth_baseband(n, seed=logn)
