@@ -182,6 +182,12 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
     }
   };
 
+  // CHIRP = 5: one 128-byte line of the row's phases per thread (L * 4 bytes = NT lines), asked into L2 ahead of use
+  auto prefetch_phase = [&](unsigned r) {
+    if constexpr (CHIRP == 5)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(cp.phase + (size_t)r * L) + (size_t)tid * 128));
+  };
+  if (blockIdx.x < nrows) prefetch_phase(blockIdx.x);  // the table is a constant of the run: no dependency to wait for
   pdl_launch_dependents();
   pdl_wait();  // tables, barriers and tensor memory were set up while the preceding kernel drained
   float limit = 0.f;
@@ -210,7 +216,24 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
       float2* const pa = bufA + j;
       float2* const pb = bufB + j;
       float2 a[16], b[16];
-      if constexpr (CHIRP != 0) {
+      if constexpr (CHIRP == 5) {
+        // tabulated phases (two adjacent bins per 8-byte load, prefetched into L2 while the previous row was stored):
+        // s1 + chirp applied as the pairs are taken out of shared memory, no pass of its own and no fp64
+        const float2* const ph = reinterpret_cast<const float2*>(cp.phase + (size_t)row * L + j);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          float2 pq[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) pq[i] = __ldg(ph + (size_t)(8 * h + i) * (B1 / 2));
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            mbar_wait(&mbar[(h ? hB : hA) * 8 + i], h ? parB : parA);
+            const float4 q = *reinterpret_cast<const float4*>((h ? pb : pa) + i * S1);
+            a[8 * h + i] = chirp_point_tab(make_float2(q.x, q.y), pq[i].x, limit, cp.coef);
+            b[8 * h + i] = chirp_point_tab(make_float2(q.z, q.w), pq[i].y, limit, cp.coef);
+          }
+        }
+      } else if constexpr (CHIRP != 0) {
         // s1 + chirp as a pass of its own over the thread's sixteen pairs, written back in place: no butterfly
         // registers are live yet, so several bins' fp64 phase chains are in flight at once (the thread re-reads only
         // what it wrote itself: no barrier). Chunk i is consumed as soon as it has landed.
@@ -246,12 +269,14 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
           *reinterpret_cast<float4*>(p) = make_float4(ya.x, ya.y, yb.x, yb.y);
         }
       }
+      if constexpr (CHIRP != 5) {
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        if constexpr (CHIRP == 0) mbar_wait(&mbar[(i < 8 ? hA : hB) * 8 + (i & 7)], i < 8 ? parA : parB);
-        const float4 q = *reinterpret_cast<const float4*>((i < 8 ? pa : pb) + (i & 7) * S1);
-        a[i] = make_float2(q.x, q.y);
-        b[i] = make_float2(q.z, q.w);
+        for (int i = 0; i < 16; i++) {
+          if constexpr (CHIRP == 0) mbar_wait(&mbar[(i < 8 ? hA : hB) * 8 + (i & 7)], i < 8 ? parA : parB);
+          const float4 q = *reinterpret_cast<const float4*>((i < 8 ? pa : pb) + (i & 7) * S1);
+          a[i] = make_float2(q.x, q.y);
+          b[i] = make_float2(q.z, q.w);
+        }
       }
       dft16<FWD>(a);
       dft16<FWD>(b);
@@ -338,6 +363,7 @@ __global__ void __launch_bounds__(bigrow<LOGL>::NT, bigrow<LOGL>::CTAS)
       const float sk = (float)L * (b / (a * a));
       zap = (sk > skp.thr_hi || sk < skp.thr_lo);  // NaN (all-zero row): untouched (rfi_mitigation.hpp:333-339)
     }
+    if (row + gridDim.x < nrows) prefetch_phase(row + gridDim.x);
     // ---- pass 2: natural-order store. lane -> (d0, d1 bit 0): 32 consecutive output indices per instruction
     {
       const int pd0 = lane & 15, pd1 = ((wid & 7) << 1) | (lane >> 4), sel = wid >> 3;

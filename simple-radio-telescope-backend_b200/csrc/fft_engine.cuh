@@ -216,11 +216,14 @@ struct sched16 {
 
 // stage_compute for sixteen slots: slot e is the point read at u + e*U (U = L/16); radix 16 (one
 // butterfly), 8 (two), 4 (four). Twiddles always come from the table (column-mode mapping).
-template <int LOGL, int LOGR, int LOGNS, bool FWD, int TWSHIFT = LOGL - LOGNS - LOGR>
+// PAD: the output slots are returned for a tile whose rows carry one spare row after every sixteen
+// (row r sits at r + (r >> 4)); with NS = 1 (radix 16 first) or NS a multiple of 16 this stays base + i * constant.
+template <int LOGL, int LOGR, int LOGNS, bool FWD, int TWSHIFT = LOGL - LOGNS - LOGR, bool PAD = false>
 __device__ __forceinline__ void stage_compute16(float2 (&v)[16], int u, const float2* __restrict__ tw,
                                                 int (&oidx)[16]) {
   constexpr int L = 1 << LOGL, U = L / 16, R = 1 << LOGR, NB = 16 / R, NS = 1 << LOGNS;
   static_assert(LOGR >= 2 && LOGR <= 4, "radix 4, 8 or 16");
+  static_assert(!PAD || NS >= 16 || (NS == 1 && LOGR == 4), "padded rows: slot stride must keep the pad linear");
 #pragma unroll
   for (int m = 0; m < NB; m++) {
     const int b = u + m * U;
@@ -238,8 +241,15 @@ __device__ __forceinline__ void stage_compute16(float2 (&v)[16], int u, const fl
       dft4<FWD>(v[m], v[m + 4], v[m + 8], v[m + 12]);
     }
     const int obase = ((b >> LOGNS) << (LOGNS + LOGR)) + k;
+    if constexpr (PAD) {
+      const int pbase = obase + (obase >> 4);
+      constexpr int PSTEP = NS >= 16 ? NS + NS / 16 : NS;
 #pragma unroll
-    for (int i = 0; i < R; i++) oidx[m + i * NB] = obase + i * NS;
+      for (int i = 0; i < R; i++) oidx[m + i * NB] = pbase + i * PSTEP;
+    } else {
+#pragma unroll
+      for (int i = 0; i < R; i++) oidx[m + i * NB] = obase + i * NS;
+    }
   }
 }
 
@@ -363,6 +373,14 @@ __device__ __forceinline__ float2 big_tw_lookup(const float2* s, int q, uint32_t
   const float2 w0 = s[idx & mask];
   const float2 w1 = s[(1u << q) + ((idx >> q) & mask)];
   const float2 w2 = s[(2u << q) + (idx >> (2 * q))];
+  return c_mul(c_mul(w2, w1), w0);
+}
+
+__device__ __forceinline__ float2 big_tw_lookup_ldg(const float2* __restrict__ g, int q, uint32_t idx) {
+  const uint32_t mask = (1u << q) - 1u;
+  const float2 w0 = __ldg(&g[idx & mask]);
+  const float2 w1 = __ldg(&g[(1u << q) + ((idx >> q) & mask)]);
+  const float2 w2 = __ldg(&g[(2u << q) + (idx >> (2 * q))]);
   return c_mul(c_mul(w2, w1), w0);
 }
 
@@ -690,6 +708,9 @@ struct row_chirp_params {
   const float* mean;      // mean |X|^2 of the block (s1 statistic), finalised by the preceding kernel
   float threshold, coef;  // s1: zap above threshold * mean, scale the rest by coef
   int newton;             // whole-row kernel: reciprocal mode = the kernel's CHIRP template value (1, 3, 4; 2 = exact)
+  // optional: -2 pi frac(k) of every bin of the block (chirp_phase_table_kernel); the whole-row kernel then runs as
+  // CHIRP = 5 and evaluates no fp64 at all
+  const float* phase;
 };
 
 #ifndef SRTB_FAST_SINCOS
@@ -714,6 +735,30 @@ __device__ __forceinline__ float2 chirp_point(float2 v, double f, double r, cons
   const float scale = (v.x * v.x + v.y * v.y > limit) ? 0.f : cp.coef;  // rfi_mitigation_pipe.hpp:66-79
   const float wr = c * scale, wi = s * scale;
   return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+}
+
+// the same on a tabulated phase: ang = -2 pi frac(k) in [-pi, pi], rounded to fp32 once
+__device__ __forceinline__ float2 chirp_point_tab(float2 v, float ang, float limit, float coef) {
+  float s, c;
+  __sincosf(ang, &s, &c);
+  const float scale = (v.x * v.x + v.y * v.y > limit) ? 0.f : coef;
+  const float wr = c * scale, wi = s * scale;
+  return make_float2(v.x * wr - v.y * wi, v.x * wi + v.y * wr);
+}
+
+// K12 phase of every bin of a block, once per (block geometry, DM): k exactly as chirp_factor evaluates it (fp64,
+// correctly rounded reciprocal), reduced to [-1/2, 1/2] cycles and stored as the fp32 angle -2 pi frac(k) — the very
+// value chirp_point hands to the SFU, so both routes agree to the last bit of the argument. DM and band are constants
+// of a run, so the table is part of the plan like the twiddles.
+__global__ void __launch_bounds__(256) chirp_phase_table_kernel(float* __restrict__ out, size_t n, double f_min,
+                                                                double df, double inv_fc, double f_c, double ddm) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double f = fma(df, (double)i, f_min);
+    const double q = (f - f_c) * inv_fc;
+    const double k = (ddm * __drcp_rn(f)) * (q * q);
+    const float fr = (float)(k - rint(k));  // the difference is exact, in [-1/2, 1/2]
+    out[i] = -6.283185307179586f * fr;
+  }
 }
 
 // ---------------------------------------------------------------------------------
@@ -984,6 +1029,20 @@ struct tile_tma_smem {
   static constexpr size_t bytes(int q) { return data_bytes + 128 + (size_t)(L + (3 << q)) * sizeof(float2); }
 };
 
+// raw-fused sixteen-point first sweep: [exchange tile][2 raw byte tiles of L x 4T bytes][128 B: mbarriers][stage
+// twiddles]; the inter-sweep tables stay in global memory (two look-ups per thread and tile, fetched before the
+// stages run) so that three CTAs fit an SM at L = 512. With T = 8 a row of the exchange tile is 64 bytes — half the
+// banks — and the four rows a warp writes after a radix-16 stage would all have the same parity: one spare row
+// after every sixteen (tile rows r -> r + (r >> 4)) spreads them again.
+template <int LOGL, int T>
+struct raw16_smem {
+  static constexpr int L = 1 << LOGL;
+  static constexpr int BUF = T * L;
+  static constexpr bool PAD = (T == 8) && ((L / 16) % 16 == 0);
+  static constexpr int XBUF = PAD ? BUF + BUF / 16 : BUF;
+  static constexpr size_t bytes = (size_t)XBUF * sizeof(float2) + 2 * (size_t)BUF * 4 + 128 + (size_t)L * sizeof(float2);
+};
+
 // Column pass, persistent: view [A][L][B] (B = elements between consecutive FFT points). A tile is the
 // L x T box at (row a*L, column b0) of the 2-D tensor [A*L][B]; ONE TMA box load (per 256 rows) brings
 // it into shared memory in exactly the column-mode layout [idx][t], double buffered across tiles.
@@ -1146,14 +1205,18 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_
   using SC = sched16<LOGL>;
   constexpr int L = 1 << LOGL, U = L / 16, S = SC::S, BUF = tile_tma_smem<LOGL, T>::BUF;
   constexpr int ROWS_PER_BOX = (L < 256) ? L : 256;
+  constexpr bool PADX = (RAW != 0) && raw16_smem<LOGL, T>::PAD;  // exchange tile with a spare row per sixteen
+  constexpr int XBUF = (RAW != 0) ? raw16_smem<LOGL, T>::XBUF : BUF;
+  constexpr int UP = PADX ? U + U / 16 : U;                         // distance of a thread's sixteen slots
   extern __shared__ __align__(128) unsigned char smraw[];
   float2* const buf0 = reinterpret_cast<float2*>(smraw);
-  float2* const buf1 = buf0 + BUF;
-  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);
+  float2* const buf1 = buf0 + XBUF;
   unsigned char* const raw0 = reinterpret_cast<unsigned char*>(buf1);
   unsigned char* const raw1 = raw0 + (size_t)BUF * 4;
-  float2* const ltw = reinterpret_cast<float2*>(smraw + tile_tma_smem<LOGL, T>::data_bytes + 128);
-  float2* const stw = ltw + L;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);  // RAW: right after the two raw tiles (2 * 4 BUF bytes)
+  float2* const ltw = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(mbar) + 128);
+  // inter-sweep tables: staged in shared memory, except for the raw-fused sweep (see raw16_smem)
+  const float2* const stw = (RAW != 0) ? btw.tab : ltw + L;
   const int tid = threadIdx.x;
   const int t = tid % T, u = tid / T;
   if (tid == 0) {
@@ -1161,7 +1224,8 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_
     mbar_init(&mbar[1], 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < (3 << btw.q); i += blockDim.x) stw[i] = __ldg(&btw.tab[i]);
+  if constexpr (RAW == 0)
+    for (int i = tid; i < (3 << btw.q); i += blockDim.x) ltw[L + i] = __ldg(&btw.tab[i]);
   for (int i = tid; i < L; i += blockDim.x) ltw[i] = __ldg(&tw[i]);
   __syncthreads();
   pdl_launch_dependents();
@@ -1193,6 +1257,13 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_
     mbar_wait(&mbar[b], (it >> 1) & 1);
     float2 v[16];
     int oidx[16];
+    const int up = PADX ? u + (u >> 4) : u;  // tile row of slot 0
+    float2 wb, r1;                           // inter-sweep twiddle of slot 0 and the ratio between slots
+    if constexpr (RAW != 0) {                // from global memory: issued before the stages to hide the latency
+      const uint32_t bb = (tile % btiles) * T + t;
+      wb = big_tw_lookup_ldg(stw, btw.q, (uint32_t)u * bb);
+      r1 = big_tw_lookup_ldg(stw, btw.q, (uint32_t)U * bb);
+    }
     if constexpr (RAW == 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) v[e] = sm[(u + e * U) * T + t];
@@ -1237,30 +1308,32 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_
         else v[e] = make_float2((float)g[rp.o0], (float)g[rp.o1]);
       }
     }
-    stage_compute16<LOGL, SC::logr(0), 0, FWD>(v, u, ltw, oidx);
+    stage_compute16<LOGL, SC::logr(0), 0, FWD, LOGL - SC::logr(0), PADX>(v, u, ltw, oidx);
     if constexpr (RAW == 0) __syncthreads();  // every thread has read the tile before it is overwritten
 #pragma unroll
     for (int e = 0; e < 16; e++) sm[oidx[e] * T + t] = v[e];
     __syncthreads();
     if constexpr (S == 3) {
 #pragma unroll
-      for (int e = 0; e < 16; e++) v[e] = sm[(u + e * U) * T + t];
+      for (int e = 0; e < 16; e++) v[e] = sm[(up + e * UP) * T + t];
       __syncthreads();
-      stage_compute16<LOGL, SC::logr(1), SC::logns(1), FWD>(v, u, ltw, oidx);
+      stage_compute16<LOGL, SC::logr(1), SC::logns(1), FWD, LOGL - SC::logns(1) - SC::logr(1), PADX>(v, u, ltw, oidx);
 #pragma unroll
       for (int e = 0; e < 16; e++) sm[oidx[e] * T + t] = v[e];
       __syncthreads();
     }
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = sm[(u + e * U) * T + t];
+    for (int e = 0; e < 16; e++) v[e] = sm[(up + e * UP) * T + t];
     stage_compute16<LOGL, SC::logr(S - 1), SC::logns(S - 1), FWD>(v, u, ltw, oidx);
     {
       // store k = u + e*U of column b0 + t, times W_{L*B}^{k (b0 + t)} = wb * r1^e; the sixteen powers
       // are formed as hi[e >> 2] * lo[e & 3] (products of at most three table values deep)
       const uint32_t a = tile / btiles, b0 = (tile % btiles) * T;
-      const uint32_t bb = b0 + t;
-      float2 wb = big_tw_lookup(stw, btw.q, (uint32_t)u * bb);
-      float2 r1 = big_tw_lookup(stw, btw.q, (uint32_t)U * bb);
+      if constexpr (RAW == 0) {
+        const uint32_t bb = b0 + t;
+        wb = big_tw_lookup(stw, btw.q, (uint32_t)u * bb);
+        r1 = big_tw_lookup(stw, btw.q, (uint32_t)U * bb);
+      }
       if (!FWD) {
         wb.y = -wb.y;
         r1.y = -r1.y;
@@ -1729,14 +1802,19 @@ __global__ void __launch_bounds__(2 * T * ((1 << LOGL) / 16), 3)
       const uint32_t tau = tile % tiles_per_rest, rest = tile / tiles_per_rest;
       const uint32_t k10 = tau * T;
       const bool last_tile = (tau == tiles_per_rest - 1);  // k10 == L1/2: only its slot 0 is new work
-      // thread (u1, t1): primary slot t = t1 % T, output indices kk = u1 + e*U for e in [8*(t1/T), 8*(t1/T)+8)
-      const int t = t1 % T, e0 = 8 * (t1 / T);
+      // split mapping (its own; the results sit in shared memory): a warp takes primary slots t = 0..7 and the four
+      // residues kk mod 16 = {c, c+8, c+1, c+9}, in that order over its four groups of eight lanes: 8-byte shared
+      // loads are served per HALF warp, and with rows LP = L + 1 apart t + kk then covers every value mod 16 exactly
+      // once in each half — one wavefront per half for the element and for its mirror (the former (u1, t1) mapping
+      // needed two); kk = residue + 16 e, warps 4..7 (L = 256) taking e = 8..15
+      const int lane = tid & 31, wsp = tid >> 5;
+      const int t = lane & 7, kl = 2 * (wsp & 3) + (lane >> 4) + 8 * ((lane >> 3) & 1), e0 = 8 * (wsp >> 2);
       const uint32_t k1 = k10 + t;
       const uint32_t prest = rest_digit_swap(rest, S_, rest_inner);
       const float2 wbase = r2c_split_twiddle((size_t)k1 + (size_t)L1 * prest, M);
 #pragma unroll
       for (int e = e0; e < e0 + 8; e++) {
-        const int kk = u1 + e * U;
+        const int kk = kl + e * 16;
         const float2 hk = sm[t * LP + kk];
         const float2 hm = sm[(T2 - 1 - t) * LP + (L - 1 - kk)];
         const size_t gk = (size_t)k1 + (size_t)L1 * prest + (size_t)A * kk;

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -26,6 +27,10 @@ using namespace srtb_b200;
 static thread_local std::string g_last_error;
 
 struct srtb_b200_ctx {
+  // a context may be shared by the threads of a pipeline (the reference hands one sycl::queue to every pipe): every
+  // C-ABI entry takes this lock, so the planning state below (tables, scratch sizes, kernel attributes) is never
+  // mutated concurrently. Recursive because the block entries call the stage entries.
+  std::recursive_mutex mu;
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
@@ -62,6 +67,8 @@ struct srtb_b200_ctx {
   int slot_streams[SRTB_B200_RING_SLOTS] = {0};
   size_t slot_L[SRTB_B200_RING_SLOTS] = {0};
   bool slot_busy[SRTB_B200_RING_SLOTS] = {false};
+  cudaEvent_t slot_done_alt[SRTB_B200_RING_SLOTS] = {nullptr};  // second lane's completion of the slot's block
+  bool slot_alt_used[SRTB_B200_RING_SLOTS] = {false};
   int slot_ticket[SRTB_B200_RING_SLOTS] = {0};
   // per-slot outputs: ctx-owned working buffers / pinned series unless the caller supplied its own (submit_block_ex)
   float* slot_stream_buf[SRTB_B200_RING_SLOTS][4] = {};
@@ -95,7 +102,59 @@ struct srtb_b200_ctx {
   size_t d_baseband_bytes = 0;
   float* stream_buf[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t stream_buf_elems = 0;
+  // K12 phase table of the current (block geometry, DM): see chirp_phase_table_kernel
+  float* chirp_tab = nullptr;
+  size_t chirp_tab_bytes = 0;
+  double chirp_tab_key[6] = {0, 0, 0, 0, 0, 0};  // n, f_min, df, inv_fc, f_c, ddm
+  // second lane: the data streams of one block are independent until their result headers are read back, so the
+  // odd-numbered ones run on a second CUDA stream of this context with their own scratch (one lane's kernel tails and
+  // small detector kernels overlap the other lane's FFT sweeps). lane_swap() exchanges every member a stream's chain
+  // writes through with the copy kept here, so the launch code itself is lane-agnostic.
+  struct lane_state {
+    cudaStream_t stream = nullptr;
+    void* fft_scratch = nullptr;
+    size_t fft_scratch_bytes = 0;
+    double* partial = nullptr;
+    unsigned* ticket = nullptr;
+    unsigned* detect_ticket = nullptr;
+    float* mean = nullptr;
+    float* colsum_partial = nullptr;
+    size_t colsum_partial_elems = 0;
+    float* acc = nullptr;
+    size_t acc_elems = 0;
+    void* long_stats = nullptr;
+    size_t long_stats_bytes = 0;
+    void* long_zap = nullptr;
+    size_t long_zap_bytes = 0;
+  } alt;
+  bool alt_ready = false, on_alt = false;
+  int lanes = 1;  // SRTB_B200_LANES (default 2): CUDA streams per context the data streams of a block are spread over
+  cudaEvent_t lane_fork = nullptr, lane_join = nullptr;
 };
+
+static void lane_swap(srtb_b200_ctx* ctx) {
+  auto& a = ctx->alt;
+  std::swap(ctx->stream, a.stream);
+  std::swap(ctx->fft_scratch, a.fft_scratch);
+  std::swap(ctx->fft_scratch_bytes, a.fft_scratch_bytes);
+  std::swap(ctx->partial, a.partial);
+  std::swap(ctx->ticket, a.ticket);
+  std::swap(ctx->detect_ticket, a.detect_ticket);
+  std::swap(ctx->mean, a.mean);
+  std::swap(ctx->colsum_partial, a.colsum_partial);
+  std::swap(ctx->colsum_partial_elems, a.colsum_partial_elems);
+  std::swap(ctx->acc, a.acc);
+  std::swap(ctx->acc_elems, a.acc_elems);
+  std::swap(ctx->long_stats, a.long_stats);
+  std::swap(ctx->long_stats_bytes, a.long_stats_bytes);
+  std::swap(ctx->long_zap, a.long_zap);
+  std::swap(ctx->long_zap_bytes, a.long_zap_bytes);
+  ctx->on_alt = !ctx->on_alt;
+}
+
+#define API_LOCK(c)                                         \
+  std::unique_lock<std::recursive_mutex> api_lock_;         \
+  if (c) api_lock_ = std::unique_lock<std::recursive_mutex>((c)->mu)
 
 static int fail(srtb_b200_ctx* ctx, int code, const std::string& msg) {
   g_last_error = msg;
@@ -112,10 +171,17 @@ static int fail(srtb_b200_ctx* ctx, int code, const std::string& msg) {
                       std::to_string(__LINE__) + ")");                                    \
   } while (0)
 
+// both lanes of the context idle (before anything either of them may still use is freed)
+static int sync_lanes(srtb_b200_ctx* ctx) {
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->alt_ready) CK(cudaStreamSynchronize(ctx->alt.stream));
+  return 0;
+}
+
 static int ensure(srtb_b200_ctx* ctx, void** p, size_t* have, size_t want_bytes) {
   if (*have >= want_bytes && *p) return 0;
   if (*p) {
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (int rc = sync_lanes(ctx)) return rc;
     CK(cudaFree(*p));
     *p = nullptr;
     *have = 0;
@@ -195,6 +261,8 @@ int srtb_b200_ctx_create(int device, void* cuda_stream, srtb_b200_ctx** out) {
     srtb_b200_ctx_destroy(ctx);  // frees whatever was allocated before the failure
     return fail(nullptr, SRTB_B200_E_CUDA, msg);
   }
+  if (const char* v = std::getenv("SRTB_B200_LANES")) ctx->lanes = std::atoi(v) >= 2 ? 2 : 1;
+  else ctx->lanes = 2;
   *out = ctx;
   return 0;
 }
@@ -202,7 +270,23 @@ int srtb_b200_ctx_create(int device, void* cuda_stream, srtb_b200_ctx** out) {
 int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->device);
+  if (ctx->on_alt) lane_swap(ctx);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->alt_ready) {
+    cudaStreamSynchronize(ctx->alt.stream);
+    cudaFree(ctx->alt.fft_scratch);
+    cudaFree(ctx->alt.partial);
+    cudaFree(ctx->alt.ticket);
+    cudaFree(ctx->alt.detect_ticket);
+    cudaFree(ctx->alt.mean);
+    cudaFree(ctx->alt.colsum_partial);
+    cudaFree(ctx->alt.acc);
+    cudaFree(ctx->alt.long_stats);
+    cudaFree(ctx->alt.long_zap);
+    cudaStreamDestroy(ctx->alt.stream);
+  }
+  if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
+  if (ctx->lane_join) cudaEventDestroy(ctx->lane_join);
   for (auto& p : ctx->tw)
     if (p) cudaFree(p);
   for (auto& kv : ctx->bigtw) cudaFree(kv.second);
@@ -223,12 +307,14 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
   cudaFree(ctx->sweep_res);
   cudaFree(ctx->long_stats);
   cudaFree(ctx->long_zap);
+  cudaFree(ctx->chirp_tab);
   for (int i = 0; i < SRTB_B200_RING_SLOTS; i++) {
     cudaFree(ctx->slot_baseband[i]);
     for (auto& p : ctx->slot_stream_buf[i]) cudaFree(p);
     if (ctx->slot_h_series[i]) cudaFreeHost(ctx->slot_h_series[i]);
     if (ctx->slot_h2d[i]) cudaEventDestroy(ctx->slot_h2d[i]);
     if (ctx->slot_done[i]) cudaEventDestroy(ctx->slot_done[i]);
+    if (ctx->slot_done_alt[i]) cudaEventDestroy(ctx->slot_done_alt[i]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   for (auto& p : ctx->stream_buf) cudaFree(p);
@@ -240,6 +326,7 @@ int srtb_b200_ctx_destroy(srtb_b200_ctx* ctx) {
 }
 
 int srtb_b200_ctx_set_stream(srtb_b200_ctx* ctx, void* cuda_stream) {
+  API_LOCK(ctx);
   if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "set_stream: ctx is null");
   ctx->stream = static_cast<cudaStream_t>(cuda_stream);
   return 0;
@@ -247,7 +334,14 @@ int srtb_b200_ctx_set_stream(srtb_b200_ctx* ctx, void* cuda_stream) {
 
 int srtb_b200_synchronize(srtb_b200_ctx* ctx) {
   if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "synchronize: ctx is null");
-  CK(cudaStreamSynchronize(ctx->stream));
+  cudaStream_t s0, s1 = nullptr;
+  {
+    API_LOCK(ctx);  // the wait itself runs unlocked: other threads keep enqueueing meanwhile
+    s0 = ctx->on_alt ? ctx->alt.stream : ctx->stream;
+    if (ctx->alt_ready) s1 = ctx->on_alt ? ctx->stream : ctx->alt.stream;
+  }
+  CK(cudaStreamSynchronize(s0));
+  if (s1) CK(cudaStreamSynchronize(s1));
   return 0;
 }
 
@@ -258,12 +352,14 @@ const char* srtb_b200_last_error(const srtb_b200_ctx* ctx) {
 uint64_t srtb_b200_launch_count(const srtb_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int srtb_b200_stage_stats_enable(srtb_b200_ctx* ctx, int on) {
+  API_LOCK(ctx);
   if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "stage_stats_enable: ctx is null");
   ctx->stats_on = on != 0;
   return 0;
 }
 
 int srtb_b200_stage_stats(srtb_b200_ctx* ctx, int stage, double* ms, double* bytes) {
+  API_LOCK(ctx);
   if (!ctx || !ms || !bytes) return fail(ctx, SRTB_B200_E_INVALID, "stage_stats: null argument");
   if (stage < 0 || stage >= SRTB_B200_STAGE_COUNT) return fail(ctx, SRTB_B200_E_INVALID, "stage_stats: unknown stage");
   if (!ctx->stat_have[stage]) return fail(ctx, SRTB_B200_E_INVALID, "stage_stats: stage not timed yet (enable first)");
@@ -307,6 +403,7 @@ static int launch_unpack_il2(srtb_b200_ctx* ctx, const void* d_in, float* o1, fl
 
 extern "C" int srtb_b200_unpack(srtb_b200_ctx* ctx, const void* d_in, size_t in_bytes, int bits,
                                 int format, int window, float* const d_out[4], size_t out_count) {
+  API_LOCK(ctx);
   if (!ctx || !d_in || !d_out || !d_out[0]) return fail(ctx, SRTB_B200_E_INVALID, "unpack: null argument");
   if (window < 0 || window > 2) return fail(ctx, SRTB_B200_E_INVALID, "unpack: unknown window");
   if (out_count == 0) return 0;
@@ -758,8 +855,9 @@ static int launch_col_tma_raw(srtb_b200_ctx* ctx, const raw_source& src, float2*
     if (use_col16()) {
       auto kern16 = fft_col16_tma_kernel<LOGL, T, true, RAW>;
       constexpr int threads = col16_threads<LOGL, T>::value;
-      if (int rc = persistent_grid(ctx, kern16, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
-      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, rp,
+      constexpr size_t smem16 = raw16_smem<LOGL, T>::bytes;  // inter-sweep tables stay in global memory here
+      if (int rc = persistent_grid(ctx, kern16, threads, smem16, smem16, ntiles, &grid)) return rc;
+      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem16, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw, rp,
                     row_chirp_params{}));
       ctx->launches++;
       CK(cudaGetLastError());
@@ -982,6 +1080,7 @@ static int launch_bigrow(srtb_b200_ctx* ctx, const float2* in, float2* out, size
     return 0;
   };
   if constexpr (!FWD) {
+    if (sk && chirp && chirp->newton == 5) return go(fft_bigrow_kernel<LOGL, false, true, 5>, true);
     if (sk && chirp && chirp->newton == 1) return go(fft_bigrow_kernel<LOGL, false, true, 1>, true);
     if (sk && chirp && chirp->newton == 3) return go(fft_bigrow_kernel<LOGL, false, true, 3>, true);
     if (sk && chirp && chirp->newton == 4) return go(fft_bigrow_kernel<LOGL, false, true, 4>, true);
@@ -1063,6 +1162,7 @@ static int fft_c2c_impl(srtb_b200_ctx* ctx, float2* x, size_t n, size_t batch) {
 }
 
 extern "C" int srtb_b200_fft_c2c(srtb_b200_ctx* ctx, void* d_x, size_t length, size_t batch, int direction) {
+  API_LOCK(ctx);
   if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "fft_c2c: null argument");
   if (length == 0 || batch == 0) return fail(ctx, SRTB_B200_E_INVALID, "fft_c2c: zero size");
   if (!is_pow2(length))
@@ -1074,6 +1174,7 @@ extern "C" int srtb_b200_fft_c2c(srtb_b200_ctx* ctx, void* d_x, size_t length, s
 }
 
 extern "C" int srtb_b200_watfft_c2c_backward(srtb_b200_ctx* ctx, void* d_x, size_t length, size_t batch) {
+  API_LOCK(ctx);
   if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "watfft: ctx is null");
   stage_scope stats_(ctx, SRTB_B200_STAGE_WATFFT, 16.0 * (double)length * (double)batch);
   return srtb_b200_fft_c2c(ctx, d_x, length, batch, -1);
@@ -1083,6 +1184,7 @@ static int fft_r2c_with_power_mean(srtb_b200_ctx* ctx, float* d_inout, size_t n_
                                    bool* raw_used = nullptr);
 
 extern "C" int srtb_b200_fft_r2c_inplace(srtb_b200_ctx* ctx, float* d_inout, size_t n_real) {
+  API_LOCK(ctx);
   if (!ctx || !d_inout) return fail(ctx, SRTB_B200_E_INVALID, "fft_r2c: null argument");
   if (n_real < 2 || !is_pow2(n_real))
     return fail(ctx, SRTB_B200_E_SIZE, "[fft] n must be a power of 2, got " + std::to_string(n_real));
@@ -1314,6 +1416,7 @@ extern "C" int srtb_b200_rfi_range_to_bins(float f1, float f2, float freq_low, f
 extern "C" int srtb_b200_rfi_s1(srtb_b200_ctx* ctx, void* d_x, size_t count, float avg_threshold,
                                 float norm_coef, const size_t* h_bin_ranges, size_t n_ranges,
                                 float* d_mean_out) {
+  API_LOCK(ctx);
   if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s1: null argument");
   if (count == 0) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s1: zero count");
   if (n_ranges && !h_bin_ranges) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s1: null ranges");
@@ -1352,6 +1455,7 @@ extern "C" int srtb_b200_rfi_s1(srtb_b200_ctx* ctx, void* d_x, size_t count, flo
 // ------------------------------------------------------------------------------------
 extern "C" int srtb_b200_dedisperse(srtb_b200_ctx* ctx, void* d_x, size_t count, float f_min, float f_c,
                                     float df, float dm) {
+  API_LOCK(ctx);
   if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "dedisperse: null argument");
   if (count == 0) return 0;
   CK(cudaSetDevice(ctx->device));
@@ -1425,6 +1529,7 @@ extern "C" size_t srtb_b200_nsamps_reserved(size_t baseband_input_count, size_t 
 // ------------------------------------------------------------------------------------
 extern "C" int srtb_b200_rfi_s2_sk(srtb_b200_ctx* ctx, void* d_x, size_t time_count, size_t chan_count,
                                    float sk_threshold, float* d_sk_out) {
+  API_LOCK(ctx);
   if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s2: null argument");
   if (time_count == 0 || chan_count == 0) return fail(ctx, SRTB_B200_E_INVALID, "rfi_s2: zero size");
   CK(cudaSetDevice(ctx->device));
@@ -1445,7 +1550,7 @@ extern "C" int srtb_b200_rfi_s2_sk(srtb_b200_ctx* ctx, void* d_x, size_t time_co
 static int detect_prepare(srtb_b200_ctx* ctx, int slot, size_t time_count, size_t need_partial_elems) {
   const size_t series_need = (size_t)SRTB_B200_MAX_BOXCARS * time_count;
   if (ctx->series_elems < series_need) {
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (int rc = sync_lanes(ctx)) return rc;
     for (auto& p : ctx->series) {
       if (p) CK(cudaFree(p));
       p = nullptr;
@@ -1615,6 +1720,7 @@ static int watfft_sk_detect_fused(srtb_b200_ctx* ctx, int slot, float2* x, size_
       // kernel variants: 1 = (1, 1), 3 = (2, 1), 4 = (2, 2), 2 = exact
       cpv.newton = (far_steps == 0 || near_steps == 0) ? 2
                    : (far_steps == 1 ? 1 : (near_steps == 1 ? 3 : 4));
+      if (cpv.phase) cpv.newton = 5;  // tabulated phases (block path): no reciprocal at all
     }
     const float2* s_ = src ? src : x;
     rc = (time_count == 8192) ? launch_bigrow<13, false>(ctx, s_, x, chan_count, &p, chirp ? &cpv : nullptr, &chunks)
@@ -1777,6 +1883,7 @@ extern "C" int srtb_b200_signal_detect(srtb_b200_ctx* ctx, const void* d_x, size
                                        size_t chan_count, size_t time_reserved_count, float snr_threshold,
                                        float channel_threshold, size_t max_boxcar_length,
                                        srtb_b200_detect_result* h_result, float* h_series, int copy_all) {
+  API_LOCK(ctx);
   if (!ctx || !d_x || !h_result) return fail(ctx, SRTB_B200_E_INVALID, "signal_detect: null argument");
   if (time_count == 0 || chan_count == 0) return fail(ctx, SRTB_B200_E_INVALID, "signal_detect: zero size");
   CK(cudaSetDevice(ctx->device));
@@ -1849,7 +1956,7 @@ static bool raw_sources_for(const srtb_b200_block_config* cfg, const void* d_bas
 // unpack_pipe.hpp:65-67) owned by the ctx
 static int ensure_stream_bufs(srtb_b200_ctx* ctx, float* (&bufs)[4], size_t* elems, size_t N, int streams) {
   if (*elems < N + 2) {
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (int rc = sync_lanes(ctx)) return rc;
     for (auto& p : bufs) {
       if (p) CK(cudaFree(p));
       p = nullptr;
@@ -1867,9 +1974,57 @@ static int ensure_stream_bufs(srtb_b200_ctx* ctx, float* (&bufs)[4], size_t* ele
 
 // bufs[s]: working buffer of stream s (N + 2 floats, 16-byte aligned for the fused routes) — holds the dynamic
 // spectrum [C][L] when the block is done. host_series (optional): pinned host memory that receives positive series.
+// K12 phase table for the whole-row waterfall kernel (block path; SRTB_B200_CHIRP_TABLE=0 evaluates every phase on the
+// fly like the DM sweep does). Rebuilt when the geometry or the DM changes; built synchronously, so both lanes and any
+// later launch may read it.
+static bool use_chirp_table() {
+  static const bool on = [] {
+    const char* e = std::getenv("SRTB_B200_CHIRP_TABLE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+static int get_chirp_table(srtb_b200_ctx* ctx, size_t n, const row_chirp_params& cp, const float** out) {
+  *out = nullptr;
+  if (!use_chirp_table() || n * sizeof(float) > ((size_t)2 << 30)) return 0;
+  const double key[6] = {(double)n, cp.f_min, cp.df, cp.inv_fc, cp.f_c, cp.ddm};
+  if (ctx->chirp_tab && std::memcmp(key, ctx->chirp_tab_key, sizeof(key)) == 0) {
+    *out = ctx->chirp_tab;
+    return 0;
+  }
+  if (int rc = ensure(ctx, reinterpret_cast<void**>(&ctx->chirp_tab), &ctx->chirp_tab_bytes, n * sizeof(float))) return rc;
+  if (int rc = sync_lanes(ctx)) return rc;  // a block still in flight may be reading the previous table
+  chirp_phase_table_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(ctx->chirp_tab, n, cp.f_min, cp.df, cp.inv_fc,
+                                                                           cp.f_c, cp.ddm);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(ctx->chirp_tab_key, key, sizeof(key));
+  *out = ctx->chirp_tab;
+  return 0;
+}
+
+// second lane of a context (see srtb_b200_ctx::lane_state): created on first use
+static int ensure_alt_lane(srtb_b200_ctx* ctx) {
+  if (ctx->alt_ready) return 0;
+  auto& a = ctx->alt;
+  CK(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+  CK(cudaMalloc(&a.partial, sizeof(double) * 4096));
+  CK(cudaMalloc(&a.ticket, sizeof(unsigned)));
+  CK(cudaMemset(a.ticket, 0, sizeof(unsigned)));
+  CK(cudaMalloc(&a.detect_ticket, sizeof(unsigned)));
+  CK(cudaMemset(a.detect_ticket, 0, sizeof(unsigned)));
+  CK(cudaMalloc(&a.mean, sizeof(float)));
+  CK(cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ctx->lane_join, cudaEventDisableTiming));
+  ctx->alt_ready = true;
+  return 0;
+}
+
+// join_lanes: the first lane waits for the second at the end (process_block); the ring leaves the lanes free-running
+// (each copies its own result headers back, *alt_used tells the caller to record a completion event on both).
 static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, const void* d_baseband,
                          size_t baseband_bytes, int res_base, int* streams_out, size_t* L_out, float* const* bufs,
-                         float* host_series) {
+                         float* host_series, bool join_lanes = true, bool* alt_used = nullptr) {
   const int streams = format_streams(cfg->baseband_format);
   if (!streams) return fail(ctx, SRTB_B200_E_UNSUPPORTED, "process_block: unknown format");
   const size_t N = cfg->baseband_input_count;
@@ -1884,7 +2039,17 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
   } series_scope_{ctx};
   ctx->host_series_dst = host_series;
   ctx->pdl_auto = N <= ((size_t)1 << 25);
-  CK(cudaMemsetAsync(ctx->d_res, 0, sizeof(detect_dev_result) * streams, ctx->stream));
+  // the data streams of a block are independent: odd ones go to the context's second lane (per-stage timing wants the
+  // kernels alone, so it keeps one lane)
+  const bool two_lanes = ctx->lanes >= 2 && streams >= 2 && !ctx->stats_on;
+  if (alt_used) *alt_used = two_lanes;
+  if (two_lanes) {
+    if (int rc = ensure_alt_lane(ctx)) return rc;
+  } else {
+    // result headers zeroed before the first kernel (a memset between kernels would break the dependent-launch chain);
+    // with two lanes every stream zeroes its own header at the head of its chain, on its lane
+    CK(cudaMemsetAsync(ctx->d_res, 0, sizeof(detect_dev_result) * streams, ctx->stream));
+  }
   ctx->res_zeroed = true;
   // unpack: fused into the first FFT pass when the samples are 8-bit and every complex point of a
   // stream is one fixed-size byte group (simple, "1 1 2 2", "1 2 1 2"); otherwise the unpack kernel
@@ -1920,8 +2085,16 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
                                                     cfg->baseband_bandwidth, cfg->baseband_sample_rate, cfg->dm,
                                                     cfg->baseband_reserve_sample) /
                           batch;
-  for (int s = 0; s < streams; s++) {
+  auto fork_lanes = [&]() -> int {  // called on the first lane: the second lane continues from this point of it
+    CK(cudaEventRecord(ctx->lane_fork, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->alt.stream, ctx->lane_fork, 0));
+    return 0;
+  };
+  if (two_lanes)
+    if (int rc = fork_lanes()) return rc;
+  auto enqueue_stream = [&](int s) -> int {
     float* buf = bufs[s];
+    if (two_lanes) CK(cudaMemsetAsync(ctx->d_res + s, 0, sizeof(detect_dev_result), ctx->stream));
     {
       stage_scope stats_(ctx, SRTB_B200_STAGE_FUSED_R2C,
                          (double)N * (fuse_unpack ? (double)std::abs(cfg->baseband_input_bits) / 8.0 : 4.0) + 4.0 * (double)N);
@@ -1933,7 +2106,10 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
         // later it would overwrite finished streams with their unpacked input
         if (fuse_unpack && !unpacked && s > 0)
           return fail(ctx, SRTB_B200_E_UNSUPPORTED, "process_block: fused unpack refused stream " + std::to_string(s) + " after accepting stream 0");
+        const bool was_unpacked = unpacked;
         if (int rc2 = ensure_unpacked()) return rc2;
+        if (two_lanes && !was_unpacked)
+          if (int rc2 = fork_lanes()) return rc2;  // s == 0 here: the second lane must see the unpacked samples
         rc = fft_r2c_with_power_mean(ctx, buf, N);
       }
       if (rc) return rc;
@@ -1946,13 +2122,15 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
       constexpr double D = 4.148808e3;  // coherent_dedispersion.hpp:67
       row_chirp_params cp{(double)f_min, (double)df, 1.0 / (double)f_c, (double)f_c, (D * 1e6) * (double)cfg->dm,
                           ctx->mean, cfg->mitigate_rfi_average_method_threshold, coef};
+      if (use_bigrow() && (L == 8192 || L == 16384))
+        if (int rc = get_chirp_table(ctx, Nc, cp, &cp.phase)) return rc;
       if (int rc = watfft_sk_detect_fused(ctx, s, reinterpret_cast<float2*>(buf), L, batch, reserved,
                                           cfg->mitigate_rfi_spectral_kurtosis_threshold,
                                           cfg->signal_detect_signal_noise_threshold,
                                           cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length,
                                           &cp))
         return rc;
-      continue;
+      return 0;
     }
     if (long_fusable(L, reinterpret_cast<float2*>(buf))) {
       // long rows: manual zap on the raw spectrum, then chirp-on-load column sweep, last sweep with SK statistics,
@@ -1967,7 +2145,7 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
                                        cfg->signal_detect_max_boxcar_length, cp);
       if (rc != SRTB_B200_E_UNSUPPORTED) {
         if (rc) return rc;
-        continue;
+        return 0;
       }
     }
     if (int rc = rfi_s1_dedisperse_fused(ctx, reinterpret_cast<float2*>(buf), Nc,
@@ -1981,7 +2159,7 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
                                           cfg->signal_detect_signal_noise_threshold,
                                           cfg->signal_detect_channel_threshold, cfg->signal_detect_max_boxcar_length))
         return rc;
-      continue;
+      return 0;
     }
     if (int rc = srtb_b200_watfft_c2c_backward(ctx, buf, L, batch)) return rc;
     if (sk_detect_fusable(L)) {
@@ -1997,9 +2175,29 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
                                   cfg->signal_detect_max_boxcar_length))
         return rc;
     }
+    return 0;
+  };
+  for (int s = 0; s < streams; s++) {
+    const bool alt = two_lanes && (s & 1);
+    if (alt) lane_swap(ctx);
+    int rc = enqueue_stream(s);
+    if (!rc && two_lanes) {
+      const cudaError_t e = cudaMemcpyAsync(ctx->h_res + res_base + s, ctx->d_res + s, sizeof(detect_dev_result),
+                                            cudaMemcpyDeviceToHost, ctx->stream);
+      if (e != cudaSuccess) rc = fail(ctx, SRTB_B200_E_CUDA, std::string("result header copy: ") + cudaGetErrorString(e));
+    }
+    if (alt) lane_swap(ctx);
+    if (rc) return rc;
   }
-  CK(cudaMemcpyAsync(ctx->h_res + res_base, ctx->d_res, sizeof(detect_dev_result) * streams, cudaMemcpyDeviceToHost,
-                     ctx->stream));
+  if (two_lanes) {
+    if (join_lanes) {
+      CK(cudaEventRecord(ctx->lane_join, ctx->alt.stream));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->lane_join, 0));
+    }
+  } else {
+    CK(cudaMemcpyAsync(ctx->h_res + res_base, ctx->d_res, sizeof(detect_dev_result) * streams, cudaMemcpyDeviceToHost,
+                       ctx->stream));
+  }
   *streams_out = streams;
   *L_out = L;
   return 0;
@@ -2009,6 +2207,7 @@ extern "C" int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b20
                                               const void* d_baseband, size_t baseband_bytes,
                                               srtb_b200_detect_result* h_results, float* h_series,
                                               int copy_all) {
+  API_LOCK(ctx);
   if (!ctx || !cfg || !d_baseband || !h_results) return fail(ctx, SRTB_B200_E_INVALID, "process_block: null argument");
   CK(cudaSetDevice(ctx->device));
   int streams = 0;
@@ -2028,6 +2227,7 @@ extern "C" int srtb_b200_process_block_device(srtb_b200_ctx* ctx, const srtb_b20
 extern "C" int srtb_b200_process_block(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg,
                                        const void* h_baseband, size_t baseband_bytes,
                                        srtb_b200_detect_result* h_results, float* h_series, int copy_all) {
+  API_LOCK(ctx);
   if (!ctx || !cfg || !h_baseband) return fail(ctx, SRTB_B200_E_INVALID, "process_block: null argument");
   CK(cudaSetDevice(ctx->device));
   if (int rc = ensure(ctx, &ctx->d_baseband, &ctx->d_baseband_bytes, baseband_bytes)) return rc;
@@ -2042,6 +2242,7 @@ extern "C" int srtb_b200_process_block_dm_sweep(srtb_b200_ctx* ctx, const srtb_b
                                                 const void* baseband, size_t baseband_bytes, int on_device,
                                                 const float* h_dms, size_t n_dm,
                                                 srtb_b200_detect_result* h_results /* [n_dm][streams] */) {
+  API_LOCK(ctx);
   if (!ctx || !cfg || !baseband || !h_dms || !h_results || n_dm == 0)
     return fail(ctx, SRTB_B200_E_INVALID, "dm_sweep: bad argument");
   CK(cudaSetDevice(ctx->device));
@@ -2160,6 +2361,7 @@ static inline int ring_ticket(uint64_t submit_count) {
   return (int)(submit_count % ((uint64_t)SRTB_B200_RING_SLOTS << 28));
 }
 extern "C" int srtb_b200_debug_set_submit_count(srtb_b200_ctx* ctx, uint64_t value) {
+  API_LOCK(ctx);
   if (!ctx) return fail(nullptr, SRTB_B200_E_INVALID, "debug_set_submit_count: ctx is null");
   for (int i = 0; i < SRTB_B200_RING_SLOTS; i++)
     if (ctx->slot_busy[i]) return fail(ctx, SRTB_B200_E_INVALID, "debug_set_submit_count: ring not empty");
@@ -2172,6 +2374,7 @@ extern "C" int srtb_b200_debug_set_submit_count(srtb_b200_ctx* ctx, uint64_t val
 // one block's results. Up to SRTB_B200_RING_SLOTS blocks may be in flight.
 extern "C" int srtb_b200_submit_block_ex(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, const void* baseband,
                                          size_t baseband_bytes, int on_device, const srtb_b200_block_outputs* outputs) {
+  API_LOCK(ctx);
   if (!ctx || !cfg || !baseband) return fail(ctx, SRTB_B200_E_INVALID, "submit_block: null argument");
   CK(cudaSetDevice(ctx->device));
   const int slot = (int)(ctx->submit_count % SRTB_B200_RING_SLOTS);
@@ -2202,7 +2405,7 @@ extern "C" int srtb_b200_submit_block_ex(srtb_b200_ctx* ctx, const srtb_b200_blo
   if (!h_series) {
     const size_t need = (size_t)streams * SRTB_B200_MAX_BOXCARS * L;
     if (ctx->slot_h_series_elems[slot] < need) {
-      CK(cudaStreamSynchronize(ctx->stream));
+      if (int rc = sync_lanes(ctx)) return rc;
       if (ctx->slot_h_series[slot]) CK(cudaFreeHost(ctx->slot_h_series[slot]));
       ctx->slot_h_series[slot] = nullptr;
       ctx->slot_h_series_elems[slot] = 0;
@@ -2224,10 +2427,16 @@ extern "C" int srtb_b200_submit_block_ex(srtb_b200_ctx* ctx, const srtb_b200_blo
     CK(cudaStreamWaitEvent(ctx->stream, ctx->slot_h2d[slot], 0));
     d_baseband = ctx->slot_baseband[slot];
   }
+  bool alt_used = false;
   if (int rc = block_enqueue(ctx, cfg, d_baseband, baseband_bytes, 4 * (1 + slot), &ctx->slot_streams[slot],
-                             &ctx->slot_L[slot], bufs, h_series))
+                             &ctx->slot_L[slot], bufs, h_series, /*join_lanes=*/false, &alt_used))
     return rc;
   CK(cudaEventRecord(ctx->slot_done[slot], ctx->stream));
+  ctx->slot_alt_used[slot] = alt_used;
+  if (alt_used) {
+    if (!ctx->slot_done_alt[slot]) CK(cudaEventCreateWithFlags(&ctx->slot_done_alt[slot], cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->slot_done_alt[slot], ctx->alt.stream));
+  }
   for (int s = 0; s < 4; s++) ctx->slot_out_spectrum[slot][s] = bufs[s];
   ctx->slot_out_series[slot] = h_series;
   ctx->slot_busy[slot] = true;
@@ -2250,12 +2459,19 @@ extern "C" int srtb_b200_submit_block_device(srtb_b200_ctx* ctx, const srtb_b200
 
 extern "C" int srtb_b200_collect_block_ex(srtb_b200_ctx* ctx, int ticket, srtb_b200_detect_result* h_results,
                                           const float** h_series, const void** d_spectrum) {
+  API_LOCK(ctx);
   if (!ctx || !h_results || ticket < 0) return fail(ctx, SRTB_B200_E_INVALID, "collect_block: bad argument");
   const int slot = ticket % SRTB_B200_RING_SLOTS;
   if (!ctx->slot_busy[slot] || ctx->slot_ticket[slot] != ticket)
     return fail(ctx, SRTB_B200_E_INVALID, "collect_block: nothing submitted under this ticket");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaEventSynchronize(ctx->slot_done[slot]));
+  {
+    const cudaEvent_t e0 = ctx->slot_done[slot], e1 = ctx->slot_alt_used[slot] ? ctx->slot_done_alt[slot] : nullptr;
+    api_lock_.unlock();  // the wait runs unlocked (a ticket is collected once, by one thread)
+    CK(cudaEventSynchronize(e0));
+    if (e1) CK(cudaEventSynchronize(e1));
+    api_lock_.lock();
+  }
   const int streams = ctx->slot_streams[slot];
   std::memcpy(h_results, ctx->h_res + 4 * (1 + slot), sizeof(srtb_b200_detect_result) * streams);
   if (h_series) *h_series = ctx->slot_out_series[slot];

@@ -64,7 +64,9 @@ def _check_work(w, prefix, bb, oracle, n, C_, dm):
     spec = np.fromfile(f"{prefix}{w['block']}.{w['stream']}.bin", dtype=np.complex64).reshape(C_, L)
     espec = work[:n].view(np.complex64).reshape(C_, L)
     gz, ez = np.all(spec == 0, axis=1), np.all(espec == 0, axis=1)
-    assert (gz != ez).sum() <= 1
+    nz = ~(gz | ez)
+    whole = np.linalg.norm(spec[nz].astype(np.complex128) - espec[nz]) / max(1e-30, np.linalg.norm(espec[nz].astype(np.complex128)))
+    assert (gz != ez).sum() <= 1, (int(gz.sum()), int(ez.sum()), float(whole), w)
     same = gz == ez
     den = np.linalg.norm(espec[same].astype(np.complex128))
     if den == 0:        # everything zapped in both
