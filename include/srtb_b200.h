@@ -160,6 +160,22 @@ int srtb_b200_signal_detect(srtb_b200_ctx* ctx, const void* d_x, size_t time_cou
                             float channel_threshold, size_t max_boxcar_length,
                             srtb_b200_detect_result* h_result, float* h_series, int copy_all);
 
+/* ---- alternates of the refft path (defined by the reference, not wired in its main.cpp): spectra laid out
+ * [time][frequency], as refft_1d_c2c_pipe leaves them (pipeline/fft_pipe.hpp:197-278) ------------------------------
+ * mitigate_rfi_spectral_kurtosis_method (v1, spectrum/rfi_mitigation.hpp:181-275, normalization = false):
+ * d_x is [time_counts][fft_bins]; every frequency column whose sk = M s4 / s2^2 over the time_counts spectra leaves
+ * the thresholds is zeroed. d_sk_out (optional, fft_bins floats) receives sk. */
+int srtb_b200_rfi_sk_v1(srtb_b200_ctx* ctx, void* d_x, size_t fft_bins, size_t time_counts, float sk_threshold,
+                        float* d_sk_out);
+/* signal_detect_pipe (v1, pipeline/signal_detect_pipe.hpp:51-230): SK v1 in place, masked channels counted over the
+ * first spectrum, one time-series value per spectrum (sum over its count_per_batch bins of |x|^2), mean removal,
+ * count_signal, boxcars 2..max (series lengths batch_size - boxcar; nothing is trimmed). h_series rows are
+ * batch_size floats apart. Synchronises the stream. */
+int srtb_b200_signal_detect_v1(srtb_b200_ctx* ctx, void* d_x, size_t count_per_batch, size_t batch_size,
+                               float sk_threshold, float snr_threshold, float channel_threshold,
+                               size_t max_boxcar_length, srtb_b200_detect_result* h_result, float* h_series,
+                               int copy_all);
+
 /* ---- the whole path on one block (main.cpp:170-204 for one work item) -----------------
  * configuration scalars = the srtb::configs fields the path reads (config.hpp:80-249). */
 typedef struct {

@@ -266,6 +266,44 @@ int srtb_ref_signal_detect_pipe(const float* x, size_t time_count, size_t chan_c
   return n;
 }
 
+// ---- alternates of the refft path ([time][frequency]): SK v1 (spectrum/rfi_mitigation.hpp:181-275) and
+// signal_detect_pipe v1 (pipeline/signal_detect_pipe.hpp:51-230), both as the reference defines them
+void srtb_ref_sk_v1(float* x, size_t fft_bins, size_t time_counts, float sk_threshold) {
+  auto d = to_device<C>(x, fft_bins * time_counts);
+  srtb::spectrum::mitigate_rfi_spectral_kurtosis_method(d.get(), fft_bins, time_counts, sk_threshold, queue());
+  std::memcpy(x, d.get(), fft_bins * time_counts * sizeof(C));
+}
+
+int srtb_ref_signal_detect_pipe_v1(float* x, size_t count_per_batch, size_t batch_size, float sk_threshold, float snr,
+                                   float chan_thr, size_t max_boxcar, unsigned long long* boxcar_length,
+                                   unsigned long long* series_length, unsigned long long* signal_count,
+                                   float* series_out, int max_series) {
+  auto& cfg = srtb::config;
+  cfg.mitigate_rfi_spectral_kurtosis_threshold = sk_threshold;
+  cfg.signal_detect_signal_noise_threshold = snr;
+  cfg.signal_detect_channel_threshold = chan_thr;
+  cfg.signal_detect_max_boxcar_length = max_boxcar;
+  srtb::pipeline::signal_detect_pipe pipe{queue()};
+  srtb::work::signal_detect_work w;
+  w.ptr = to_device<C>(x, count_per_batch * batch_size);
+  w.count = count_per_batch;
+  w.batch_size = batch_size;
+  auto out = pipe(std::stop_token{}, w).value();
+  std::memcpy(x, out.ptr.get(), count_per_batch * batch_size * sizeof(C));  // spectrum after SK v1
+  int n = 0;
+  for (auto& h : out.time_series) {
+    if (n >= max_series) break;
+    h.transfer_event.wait();
+    boxcar_length[n] = h.boxcar_length;
+    series_length[n] = h.time_series_length;
+    std::memcpy(series_out + (size_t)n * batch_size, h.h_time_series.get(), h.time_series_length * sizeof(float));
+    signal_count[n] = srtb::signal_detect::count_signal<srtb::real>(h.h_time_series.get(), h.time_series_length,
+                                                                    snr, queue());
+    n++;
+  }
+  return n;
+}
+
 // count_signal alone (signal_detect.hpp:32-72)
 unsigned long long srtb_ref_count_signal(const float* v, size_t n, float snr) {
   return srtb::signal_detect::count_signal<srtb::real>(const_cast<float*>(v), n, snr, queue());

@@ -632,6 +632,95 @@ void srtb_oracle_signal_detect(const float* x_, size_t time_count, size_t chan_c
 }
 
 // ---------------------------------------------------------------------------
+// alternates of the refft path: spectra laid out [time][frequency]
+// SK v1 (S/spectrum/rfi_mitigation.hpp:181-275, normalization = false): per frequency column j the sums run over
+// the spectra i = 0..M-1 in ascending order, in fp32 (sum_real_t = T, :186).
+// ---------------------------------------------------------------------------
+void srtb_oracle_sk_v1(float* x_, size_t fft_bins, size_t time_counts, float sk_threshold, float* sk_out,
+                       uint8_t* zap) {
+  cf* x = reinterpret_cast<cf*>(x_);
+  float lo, hi;
+  srtb_oracle_sk_thresholds(time_counts, sk_threshold, &lo, &hi);
+  std::vector<uint8_t> z(fft_bins);
+#pragma omp parallel for schedule(static)
+  for (long jj = 0; jj < (long)fft_bins; jj++) {
+    const size_t j = (size_t)jj;
+    float s2 = 0, s4 = 0;
+    for (size_t i = 0; i < time_counts; i++) {
+      const float x2 = cnorm(x[i * fft_bins + j]);
+      const float x4 = x2 * x2;
+      s2 += x2;
+      s4 += x4;
+    }
+    const float sk = static_cast<float>(time_counts) * (s4 / (s2 * s2));
+    z[j] = (sk > hi || sk < lo) ? 1 : 0;
+    if (sk_out) sk_out[j] = sk;
+    if (zap) zap[j] = z[j];
+  }
+#pragma omp parallel for schedule(static)
+  for (long ii = 0; ii < (long)time_counts; ii++)
+    for (size_t j = 0; j < fft_bins; j++)
+      if (z[j]) x[(size_t)ii * fft_bins + j] = cf{0, 0};
+}
+
+// signal_detect_pipe v1 (S/pipeline/signal_detect_pipe.hpp:51-230): x is [batch_size = time][count_per_batch =
+// frequency]; SK v1 in place (:66-68), zero_count over the first count_per_batch elements (:74-90), one value per
+// spectrum (:93-107; the reference's work-group order is device dependent, ascending order here), mean removal
+// (:115-126), count_signal, inclusive scan, boxcars 2, 4, .. (:166-205; nothing is trimmed, lengths n - boxcar).
+// series_out rows are batch_size floats apart.
+void srtb_oracle_signal_detect_v1(float* x_, size_t count_per_batch, size_t batch_size, float sk_threshold,
+                                  float snr_threshold, float channel_threshold, size_t max_boxcar_length,
+                                  srtb_oracle_detect_result* res, float* series_out) {
+  srtb_oracle_sk_v1(x_, count_per_batch, batch_size, sk_threshold, nullptr, nullptr);
+  const cf* x = reinterpret_cast<const cf*>(x_);
+  std::memset(res, 0, sizeof(*res));
+  uint64_t zero_count = 0;
+  for (size_t j = 0; j < count_per_batch; j++)
+    if (cnorm(x[j]) == 0) zero_count++;
+  res->zero_count = zero_count;
+  const size_t n = batch_size;
+  res->time_series_count = n;
+  float* ts = series_out;
+#pragma omp parallel for schedule(static)
+  for (long ii = 0; ii < (long)n; ii++) {
+    const cf* row = x + (size_t)ii * count_per_batch;
+    float s = 0;
+    for (size_t j = 0; j < count_per_batch; j++) s += cnorm(row[j]);
+    ts[ii] = s;
+  }
+  const float avg = parallel_pairwise_sum(n, [&](size_t i) { return ts[i]; }) / static_cast<float>(n);
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < (long)n; i++) ts[i] -= avg;
+  res->detect_enabled =
+      (static_cast<float>(zero_count) < channel_threshold * static_cast<float>(count_per_batch)) ? 1 : 0;
+  if (!res->detect_enabled) return;
+  int nb = 0;
+  res->boxcar_length[nb] = 1;
+  res->series_length[nb] = n;
+  count_signal(ts, n, snr_threshold, &res->variance[nb], &res->threshold[nb], &res->signal_count[nb]);
+  nb++;
+  std::vector<float> acc(n);
+  {
+    float a = 0;
+    for (size_t i = 0; i < n; i++) {
+      a += ts[i];
+      acc[i] = a;
+    }
+  }
+  for (size_t b = 2; (b <= max_boxcar_length && b < n) && nb < 32; b *= 2) {
+    const size_t m = n - b;
+    float* bc = series_out + (size_t)nb * n;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)m; i++) bc[i] = acc[(size_t)i + b] - acc[i];
+    res->boxcar_length[nb] = b;
+    res->series_length[nb] = m;
+    count_signal(bc, m, snr_threshold, &res->variance[nb], &res->threshold[nb], &res->signal_count[nb]);
+    nb++;
+  }
+  res->n_boxcars = nb;
+}
+
+// ---------------------------------------------------------------------------
 // whole chain on one stream ("simple" format) — used as the CPU baseline.
 // work = caller buffer of N+2 floats. Returns 0 on success.
 // fft_kind: 0 = restated naive radix-2 (what the reference runs without FFTW,

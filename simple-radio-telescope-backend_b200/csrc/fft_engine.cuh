@@ -899,13 +899,23 @@ __global__ void __launch_bounds__(((1 << LOGL) / 16) * T, CHIRP ? SRTB_ROW16_CHI
       // rfi_mitigation_s1 (zap + normalise, rfi_mitigation_pipe.hpp:66-79) and the dedispersion chirp
       // (coherent_dedispersion.hpp:223-237) applied to the spectrum on its way into the waterfall FFT
       const float limit = cp.threshold * __ldg(cp.mean);
+      if (cp.phase != nullptr) {
+        // tabulated phases (block path): consecutive lanes read consecutive entries
+        const float* const ph = cp.phase + (valid ? (row << LOGL) + u : 0);
+        float ang[16];
 #pragma unroll
-      for (int e = 0; e < 16; e++) {
-        float2 a = v[e];
-        if (a.x * a.x + a.y * a.y > limit) a = make_float2(0.f, 0.f);
-        else a = make_float2(a.x * cp.coef, a.y * cp.coef);
-        const float2 w = chirp_factor(cp.f_min, cp.df, cp.inv_fc, cp.f_c, cp.ddm, (unsigned)((row << LOGL) + u + e * U));
-        v[e] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+        for (int e = 0; e < 16; e++) ang[e] = __ldg(ph + e * U);
+#pragma unroll
+        for (int e = 0; e < 16; e++) v[e] = chirp_point_tab(v[e], ang[e], limit, cp.coef);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+          float2 a = v[e];
+          if (a.x * a.x + a.y * a.y > limit) a = make_float2(0.f, 0.f);
+          else a = make_float2(a.x * cp.coef, a.y * cp.coef);
+          const float2 w = chirp_factor(cp.f_min, cp.df, cp.inv_fc, cp.f_c, cp.ddm, (unsigned)((row << LOGL) + u + e * U));
+          v[e] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+        }
       }
     }
     stage_compute16_row<LOGL, SC::logr(0), 0, FWD>(v, u, ctw, oidx);
@@ -1270,23 +1280,33 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_
       if constexpr (CH) {
         const uint32_t ta = tile / btiles, tb0 = (tile % btiles) * T;
         const float limit = cp.threshold * __ldg(cp.mean);
-        double idx = (double)(((size_t)ta << LOGL) * B + (size_t)u * B + tb0 + t);
-        const double step = (double)((size_t)U * B);
-        double f = fma(cp.df, idx, cp.f_min);
-        double r = __drcp_rn(f);
+        if (cp.phase != nullptr) {
+          // tabulated phases (block path): T consecutive entries per tile row
+          const float* const ph = cp.phase + ((size_t)ta << LOGL) * B + (size_t)u * B + tb0 + t;
+          float ang[16];
 #pragma unroll
-        for (int e = 0; e < 16; e++) {
-          if (e > 0) {
-            idx += step;
-            f = fma(cp.df, idx, cp.f_min);
-            if (cp.newton == 0) {
-              r = __drcp_rn(f);
-            } else {
-              r = fma(r, fma(-f, r, 1.0), r);
-              if (cp.newton > 1) r = fma(r, fma(-f, r, 1.0), r);
+          for (int e = 0; e < 16; e++) ang[e] = __ldg(ph + (size_t)e * U * B);
+#pragma unroll
+          for (int e = 0; e < 16; e++) v[e] = chirp_point_tab(v[e], ang[e], limit, cp.coef);
+        } else {
+          double idx = (double)(((size_t)ta << LOGL) * B + (size_t)u * B + tb0 + t);
+          const double step = (double)((size_t)U * B);
+          double f = fma(cp.df, idx, cp.f_min);
+          double r = __drcp_rn(f);
+#pragma unroll
+          for (int e = 0; e < 16; e++) {
+            if (e > 0) {
+              idx += step;
+              f = fma(cp.df, idx, cp.f_min);
+              if (cp.newton == 0) {
+                r = __drcp_rn(f);
+              } else {
+                r = fma(r, fma(-f, r, 1.0), r);
+                if (cp.newton > 1) r = fma(r, fma(-f, r, 1.0), r);
+              }
             }
+            v[e] = chirp_point(v[e], f, r, cp, limit);
           }
-          v[e] = chirp_point(v[e], f, r, cp, limit);
         }
       }
     } else if constexpr (RAW == 3) {

@@ -1034,4 +1034,64 @@ __global__ void __launch_bounds__(1024) detect_boxcar_kernel(float* __restrict__
   }
 }
 
+// ---- alternates of the refft path (spectra laid out [time][frequency]) ----------------------------
+// spectral kurtosis v1 (spectrum/rfi_mitigation.hpp:181-275, normalization = false): per FREQUENCY column j over the
+// time_counts spectra, s2 = sum |x|^2, s4 = sum |x|^4, sk = M s4 / s2^2; columns outside the thresholds are zeroed.
+// Block (32, 8): lanes along frequency (coalesced), eight time phases per column folded in a fixed order.
+__global__ void __launch_bounds__(256) sk_v1_stats_kernel(const float2* __restrict__ x, size_t fft_bins, size_t time_counts,
+                                                          float thr_lo, float thr_hi, unsigned char* __restrict__ zap,
+                                                          float* __restrict__ sk_out) {
+  __shared__ float p2[8][33], p4[8][33];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const size_t j = (size_t)blockIdx.x * 32 + cx;
+  float s2 = 0.f, s4 = 0.f;
+  if (j < fft_bins) {
+    for (size_t i = ty; i < time_counts; i += 8) {
+      const float2 v = x[i * fft_bins + j];
+      const float x2 = v.x * v.x + v.y * v.y;
+      s2 += x2;
+      s4 += x2 * x2;
+    }
+  }
+  p2[ty][cx] = s2;
+  p4[ty][cx] = s4;
+  __syncthreads();
+  if (ty == 0 && j < fft_bins) {
+    float a = p2[0][cx], b = p4[0][cx];
+#pragma unroll
+    for (int g = 1; g < 8; g++) {
+      a += p2[g][cx];
+      b += p4[g][cx];
+    }
+    const float sk = (float)time_counts * (b / (a * a));
+    zap[j] = (sk > thr_hi || sk < thr_lo) ? 1 : 0;  // NaN (an all-zero column): untouched
+    if (sk_out) sk_out[j] = sk;
+  }
+}
+
+__global__ void __launch_bounds__(256) sk_v1_zero_kernel(float2* __restrict__ x, size_t fft_bins, size_t time_counts,
+                                                         const unsigned char* __restrict__ zap) {
+  const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= fft_bins || !zap[j]) return;
+  for (size_t i = blockIdx.y; i < time_counts; i += gridDim.y) x[i * fft_bins + j] = make_float2(0.f, 0.f);
+}
+
+// signal_detect_pipe v1 (pipeline/signal_detect_pipe.hpp:101-117): one value per spectrum = sum over its frequency bins
+// of |x|^2 (multi_mapreduce with one work group per spectrum). One warp per spectrum, fixed shuffle tree.
+__global__ void __launch_bounds__(256) rowsum_norm_kernel(const float2* __restrict__ x, size_t count_per_batch,
+                                                          size_t batch_size, float* __restrict__ out) {
+  const size_t row = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= batch_size) return;
+  const int lane = threadIdx.x & 31;
+  const float2* const p = x + row * count_per_batch;
+  float a = 0.f;
+  for (size_t j = lane; j < count_per_batch; j += 32) {
+    const float2 v = p[j];
+    a += v.x * v.x + v.y * v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[row] = a;
+}
+
 }  // namespace srtb_b200

@@ -1577,12 +1577,16 @@ static int detect_prepare(srtb_b200_ctx* ctx, int slot, size_t time_count, size_
 }
 
 // column-sum reduction over `chunks` partial rows, zero count, scan, boxcar ladder
+// zero_stride / zero_count_n: where the detector looks for masked channels — the first time sample of every channel
+// of [C][L] (stride L, C of them; the default), or the first spectrum of [time][frequency] (stride 1; v1 detector)
 static int detect_tail(srtb_b200_ctx* ctx, int slot, const float2* x, size_t time_count, size_t chan_count,
-                       size_t ts_count, size_t chunks, float snr, float chan_thr, size_t max_boxcar) {
+                       size_t ts_count, size_t chunks, float snr, float chan_thr, size_t max_boxcar,
+                       size_t zero_stride = 0) {
+  if (zero_stride == 0) zero_stride = time_count;
   float* const host_series = ctx->host_series_dst ? ctx->host_series_dst + (size_t)slot * SRTB_B200_MAX_BOXCARS * time_count : nullptr;
   stage_scope stats_(ctx, SRTB_B200_STAGE_FUSED_DETECT_TAIL, 4.0 * (double)chunks * (double)ts_count);
   CK(launch_pdl(ctx, colsum_final_scan_kernel, dim3((unsigned)std::min<size_t>((ts_count + 31) / 32, (size_t)ctx->sm_count)),
-                dim3(1024), 0, (const float*)ctx->colsum_partial, ts_count, chunks, ctx->series[slot], ctx->acc, x, time_count,
+                dim3(1024), 0, (const float*)ctx->colsum_partial, ts_count, chunks, ctx->series[slot], ctx->acc, x, zero_stride,
                 chan_count, chan_thr, max_boxcar, ctx->detect_ticket, ctx->d_res + slot));
   ctx->launches++;
   CK(cudaGetLastError());
@@ -1896,6 +1900,59 @@ extern "C" int srtb_b200_signal_detect(srtb_b200_ctx* ctx, const void* d_x, size
   return detect_collect(ctx, 0, h_result, h_series, copy_all);
 }
 
+// ---- alternates of the refft path: spectra laid out [time][frequency] ------------------------------------------
+static int sk_v1_enqueue(srtb_b200_ctx* ctx, float2* x, size_t fft_bins, size_t time_counts, float sk_threshold,
+                         float* d_sk_out) {
+  if (int rc = ensure(ctx, &ctx->long_zap, &ctx->long_zap_bytes, fft_bins)) return rc;
+  unsigned char* zap = static_cast<unsigned char*>(ctx->long_zap);
+  const float M_ = static_cast<float>(time_counts);
+  float hi = sk_threshold, lo = 2 - sk_threshold;
+  if (lo > hi) std::swap(lo, hi);
+  const float lo_ = lo * ((M_ - 1) / (M_ + 1)) + 1, hi_ = hi * ((M_ - 1) / (M_ + 1)) + 1;
+  sk_v1_stats_kernel<<<(unsigned)((fft_bins + 31) / 32), 256, 0, ctx->stream>>>(x, fft_bins, time_counts, lo_, hi_, zap, d_sk_out);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  const unsigned gy = (unsigned)std::max<size_t>(1, std::min<size_t>(time_counts, 64));
+  sk_v1_zero_kernel<<<dim3((unsigned)((fft_bins + 255) / 256), gy), 256, 0, ctx->stream>>>(x, fft_bins, time_counts, zap);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int srtb_b200_rfi_sk_v1(srtb_b200_ctx* ctx, void* d_x, size_t fft_bins, size_t time_counts,
+                                   float sk_threshold, float* d_sk_out) {
+  API_LOCK(ctx);
+  if (!ctx || !d_x) return fail(ctx, SRTB_B200_E_INVALID, "rfi_sk_v1: null argument");
+  if (fft_bins == 0 || time_counts == 0) return fail(ctx, SRTB_B200_E_INVALID, "rfi_sk_v1: zero size");
+  CK(cudaSetDevice(ctx->device));
+  return sk_v1_enqueue(ctx, static_cast<float2*>(d_x), fft_bins, time_counts, sk_threshold, d_sk_out);
+}
+
+extern "C" int srtb_b200_signal_detect_v1(srtb_b200_ctx* ctx, void* d_x, size_t count_per_batch, size_t batch_size,
+                                          float sk_threshold, float snr_threshold, float channel_threshold,
+                                          size_t max_boxcar_length, srtb_b200_detect_result* h_result, float* h_series,
+                                          int copy_all) {
+  API_LOCK(ctx);
+  if (!ctx || !d_x || !h_result) return fail(ctx, SRTB_B200_E_INVALID, "signal_detect_v1: null argument");
+  if (count_per_batch == 0 || batch_size == 0) return fail(ctx, SRTB_B200_E_INVALID, "signal_detect_v1: zero size");
+  CK(cudaSetDevice(ctx->device));
+  float2* x = static_cast<float2*>(d_x);
+  if (int rc = sk_v1_enqueue(ctx, x, count_per_batch, batch_size, sk_threshold, nullptr)) return rc;
+  // one value per spectrum; then the same tail as the v2 detector (mean removal, scan, boxcars) on a series of
+  // batch_size values, masked channels counted over the first spectrum
+  if (int rc = detect_prepare(ctx, 0, batch_size, batch_size)) return rc;
+  CK(cudaMemsetAsync(ctx->d_res, 0, sizeof(detect_dev_result), ctx->stream));
+  rowsum_norm_kernel<<<(unsigned)((batch_size + 7) / 8), 256, 0, ctx->stream>>>(x, count_per_batch, batch_size, ctx->colsum_partial);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (int rc = detect_tail(ctx, 0, x, batch_size, count_per_batch, batch_size, 1, snr_threshold, channel_threshold,
+                           max_boxcar_length, /*zero_stride=*/1))
+    return rc;
+  CK(cudaMemcpyAsync(ctx->h_res, ctx->d_res, sizeof(detect_dev_result), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return detect_collect(ctx, 0, h_result, h_series, copy_all);
+}
+
 // ------------------------------------------------------------------------------------
 // whole block
 // ------------------------------------------------------------------------------------
@@ -1986,7 +2043,7 @@ static bool use_chirp_table() {
 }
 static int get_chirp_table(srtb_b200_ctx* ctx, size_t n, const row_chirp_params& cp, const float** out) {
   *out = nullptr;
-  if (!use_chirp_table() || n * sizeof(float) > ((size_t)2 << 30)) return 0;
+  if (!use_chirp_table() || n * sizeof(float) > ((size_t)4 << 30)) return 0;
   const double key[6] = {(double)n, cp.f_min, cp.df, cp.inv_fc, cp.f_c, cp.ddm};
   if (ctx->chirp_tab && std::memcmp(key, ctx->chirp_tab_key, sizeof(key)) == 0) {
     *out = ctx->chirp_tab;
@@ -2122,8 +2179,7 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
       constexpr double D = 4.148808e3;  // coherent_dedispersion.hpp:67
       row_chirp_params cp{(double)f_min, (double)df, 1.0 / (double)f_c, (double)f_c, (D * 1e6) * (double)cfg->dm,
                           ctx->mean, cfg->mitigate_rfi_average_method_threshold, coef};
-      if (use_bigrow() && (L == 8192 || L == 16384))
-        if (int rc = get_chirp_table(ctx, Nc, cp, &cp.phase)) return rc;
+      if (int rc = get_chirp_table(ctx, Nc, cp, &cp.phase)) return rc;
       if (int rc = watfft_sk_detect_fused(ctx, s, reinterpret_cast<float2*>(buf), L, batch, reserved,
                                           cfg->mitigate_rfi_spectral_kurtosis_threshold,
                                           cfg->signal_detect_signal_noise_threshold,
@@ -2139,6 +2195,8 @@ static int block_enqueue(srtb_b200_ctx* ctx, const srtb_b200_block_config* cfg, 
       constexpr double D = 4.148808e3;
       row_chirp_params cp{(double)f_min, (double)df, 1.0 / (double)f_c, (double)f_c, (D * 1e6) * (double)cfg->dm,
                           ctx->mean, cfg->mitigate_rfi_average_method_threshold, coef, 0};
+      // (no phase table here: the long-row column sweep is DRAM-bound and the 4 extra bytes per bin cost more than
+      // the fp64 evaluation they would replace — measured 74 against 77 Gsamples/s at 2^29 bins)
       const int rc = watfft_long_fused(ctx, s, reinterpret_cast<float2*>(buf), reinterpret_cast<const float2*>(buf), L, batch,
                                        reserved, cfg->mitigate_rfi_spectral_kurtosis_threshold,
                                        cfg->signal_detect_signal_noise_threshold, cfg->signal_detect_channel_threshold,

@@ -102,6 +102,8 @@ SYMBOLS = {
     "srtb_b200_nsamps_reserved": (_SZ, [_SZ, _SZ, _F, _F, _F, _F, _I]),
     "srtb_b200_rfi_s2_sk": (_I, [_P, _P, _SZ, _SZ, _F, _P]),
     "srtb_b200_signal_detect": (_I, [_P, _P, _SZ, _SZ, _SZ, _F, _F, _SZ, C.POINTER(DetectResult), _P, _I]),
+    "srtb_b200_rfi_sk_v1": (_I, [_P, _P, _SZ, _SZ, _F, _P]),
+    "srtb_b200_signal_detect_v1": (_I, [_P, _P, _SZ, _SZ, _F, _F, _F, _SZ, C.POINTER(DetectResult), _P, _I]),
     "srtb_b200_process_block": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, C.POINTER(DetectResult), _P, _I]),
     "srtb_b200_process_block_device": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, C.POINTER(DetectResult), _P, _I]),
     "srtb_b200_process_block_dm_sweep": (_I, [_P, C.POINTER(BlockConfig), _P, _SZ, _I, C.POINTER(_F), _SZ,
@@ -223,6 +225,19 @@ class Context:
         self._ck(self.lib.srtb_b200_signal_detect(self.h, _ptr(d_x), time_count, chan_count,
                                                   time_reserved_count, snr, channel_threshold, max_boxcar,
                                                   C.byref(res), _ptr(h_series), int(copy_all)))
+        return res
+
+    def rfi_sk_v1(self, d_x, fft_bins: int, time_counts: int, sk_threshold: float, d_sk_out=None):
+        """SK v1 on spectra laid out [time][frequency] (reference: spectrum/rfi_mitigation.hpp:181-275)"""
+        self._ck(self.lib.srtb_b200_rfi_sk_v1(self.h, _ptr(d_x), fft_bins, time_counts, sk_threshold, _ptr(d_sk_out)))
+
+    def signal_detect_v1(self, d_x, count_per_batch: int, batch_size: int, sk_threshold: float, snr: float,
+                         channel_threshold: float, max_boxcar: int, h_series=None, copy_all: bool = False):
+        """signal_detect_pipe v1 (reference: pipeline/signal_detect_pipe.hpp:51-230)"""
+        res = DetectResult()
+        self._ck(self.lib.srtb_b200_signal_detect_v1(self.h, _ptr(d_x), count_per_batch, batch_size, sk_threshold, snr,
+                                                     channel_threshold, max_boxcar, C.byref(res), _ptr(h_series),
+                                                     int(copy_all)))
         return res
 
     def stage_stats_enable(self, on: bool = True):

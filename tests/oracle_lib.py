@@ -208,6 +208,25 @@ class Oracle:
                                            max_boxcar, C.byref(res), series.ctypes.data)
         return res, series
 
+    # ---- alternates of the refft path ([time][frequency])
+    def sk_v1(self, x, fft_bins, time_counts, thr):
+        y = np.ascontiguousarray(x, dtype=np.complex64).copy()
+        sk = np.zeros(fft_bins, np.float32)
+        zap = np.zeros(fft_bins, np.uint8)
+        self.lib.srtb_oracle_sk_v1(C.c_void_p(y.ctypes.data), C.c_size_t(fft_bins), C.c_size_t(time_counts), C.c_float(thr),
+                                   C.c_void_p(sk.ctypes.data), C.c_void_p(zap.ctypes.data))
+        return y, sk, zap
+
+    def signal_detect_v1(self, x, count_per_batch, batch_size, sk_thr, snr, chan_thr, max_boxcar):
+        """returns (spectrum after SK v1, result header, series [MAXB][batch_size])"""
+        y = np.ascontiguousarray(x, dtype=np.complex64).copy()
+        res = DetectResult()
+        series = np.zeros((MAXB, batch_size), np.float32)
+        self.lib.srtb_oracle_signal_detect_v1(C.c_void_p(y.ctypes.data), C.c_size_t(count_per_batch), C.c_size_t(batch_size),
+                                              C.c_float(sk_thr), C.c_float(snr), C.c_float(chan_thr),
+                                              C.c_size_t(max_boxcar), C.byref(res), C.c_void_p(series.ctypes.data))
+        return y, res, series
+
     # ---- whole chain (CPU baseline)
     def chain(self, baseband: np.ndarray, cfg: ChainConfig):
         n = int(cfg.baseband_input_count)

@@ -143,6 +143,26 @@ class Ref:
         return [dict(boxcar=int(bl[i]), length=int(sl[i]), count=int(sc[i]), series=series[i, :int(sl[i])].copy())
                 for i in range(n)]
 
+    def sk_v1(self, x, fft_bins, time_counts, thr):
+        y = np.ascontiguousarray(x, dtype=np.complex64).copy()
+        self.lib.srtb_ref_sk_v1(C.c_void_p(y.ctypes.data), C.c_size_t(fft_bins), C.c_size_t(time_counts), C.c_float(thr))
+        return y
+
+    def signal_detect_pipe_v1(self, x, count_per_batch, batch_size, sk_thr, snr, chan_thr, max_boxcar):
+        """the reference's signal_detect_pipe (v1): returns (spectrum after its SK v1, holders)"""
+        y = np.ascontiguousarray(x, dtype=np.complex64).copy()
+        bl = np.zeros(MAXS, np.uint64)
+        sl = np.zeros(MAXS, np.uint64)
+        sc = np.zeros(MAXS, np.uint64)
+        series = np.zeros((MAXS, batch_size), np.float32)
+        self.lib.srtb_ref_signal_detect_pipe_v1.restype = C.c_int
+        n = self.lib.srtb_ref_signal_detect_pipe_v1(
+            C.c_void_p(y.ctypes.data), C.c_size_t(count_per_batch), C.c_size_t(batch_size), C.c_float(sk_thr),
+            C.c_float(snr), C.c_float(chan_thr), C.c_size_t(max_boxcar), C.c_void_p(bl.ctypes.data),
+            C.c_void_p(sl.ctypes.data), C.c_void_p(sc.ctypes.data), C.c_void_p(series.ctypes.data), C.c_int(MAXS))
+        return y, [dict(boxcar=int(bl[i]), length=int(sl[i]), count=int(sc[i]), series=series[i, :int(sl[i])].copy())
+                   for i in range(n)]
+
     def count_signal(self, v, snr):
         v = np.ascontiguousarray(v, dtype=np.float32)
         return int(self.lib.srtb_ref_count_signal(v.ctypes.data, v.size, snr))

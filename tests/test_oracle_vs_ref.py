@@ -219,3 +219,58 @@ def test_whole_chain_composition(oracle, logn, C_, dm, bits):
         for bc, h in got.items():
             b = [i for i in range(res.n_boxcars) if res.boxcar_length[i] == bc][0]
             assert h["length"] == res.series_length[b]
+
+
+def _refft_layout_block(rng, nt, nf):
+    """spectra [time][frequency]: noise, one steady tone (low kurtosis), one bursty channel (high kurtosis), one
+    manually zapped channel, and a broadband burst over a few consecutive spectra"""
+    x = (rng.standard_normal((nt, nf)) + 1j * rng.standard_normal((nt, nf))).astype(np.complex64)
+    x[:, 5] = 3
+    x[::8, 9] *= 9
+    x[:, 11] = 0
+    x[nt // 3:nt // 3 + 16, :] *= 1.6   # mild enough to stay inside the kurtosis thresholds of the detector tests
+    return x
+
+
+@pytest.mark.parametrize("nt,nf", [(256, 64), (1000, 48)])
+def test_sk_v1(oracle, nt, nf):
+    """alternate f-4: mitigate_rfi_spectral_kurtosis_method (v1) on the [time][frequency] layout of the refft path"""
+    x = _refft_layout_block(np.random.default_rng(nt + nf), nt, nf)
+    thr = 1.1
+    r = ref.sk_v1(x.reshape(-1), nf, nt, thr).reshape(nt, nf)
+    o, sk, zap = oracle.sk_v1(x.reshape(-1), nf, nt, thr)
+    o = o.reshape(nt, nf)
+    lo, hi = oracle.sk_thresholds(nt, thr)
+    fin = np.isfinite(sk)
+    border = np.zeros(nf, bool)
+    border[fin] = (np.abs(sk[fin] / hi - 1) < 1e-4) | (np.abs(sk[fin] / lo - 1) < 1e-4)
+    rz, oz = np.all(r == 0, axis=0), np.all(o == 0, axis=0)
+    assert np.array_equal(rz[~border], oz[~border])
+    assert rz[5] and rz[9] and rz[11] and zap[11] == 0      # the all-zero channel is NaN -> left alone
+    same = rz == oz
+    assert np.array_equal(r[:, same], o[:, same])            # same serial fp32 sums: identical where decisions agree
+
+
+@pytest.mark.parametrize("nt,nf,maxbox", [(512, 64, 32), (1000, 128, 256)])
+def test_signal_detect_pipe_v1(oracle, nt, nf, maxbox):
+    """alternate f-4: the reference's signal_detect_pipe (v1: SK v1 + per-spectrum sums + boxcars) against the oracle.
+    The spectrum length is a multiple of the device's work-group size here: multi_mapreduce cuts the flat array into
+    pieces of ceil(size / (items * groups)) * items elements (algorithm/multi_reduce.hpp:93-101), which are the rows
+    only then; the oracle restates the intended per-spectrum sum."""
+    x = _refft_layout_block(np.random.default_rng(7 * nt + nf), nt, nf)
+    sk_thr, snr, chan_thr = 1.4, 5.0, 0.9
+    rspec, holders = ref.signal_detect_pipe_v1(x.reshape(-1), nf, nt, sk_thr, snr, chan_thr, maxbox)
+    ospec, res, series = oracle.signal_detect_v1(x.reshape(-1), nf, nt, sk_thr, snr, chan_thr, maxbox)
+    assert np.array_equal(rspec.reshape(nt, nf), ospec.reshape(nt, nf))
+    assert res.detect_enabled == 1 and res.zero_count == int(np.sum(np.abs(ospec.reshape(nt, nf)[0]) == 0))
+    got = {h["boxcar"]: h for h in holders}
+    exp = {int(res.boxcar_length[b]): b for b in range(res.n_boxcars) if res.signal_count[b] > 0}
+    assert len(got) > 0
+    for bc, h in got.items():
+        b = [i for i in range(res.n_boxcars) if res.boxcar_length[i] == bc][0]
+        assert h["length"] == res.series_length[b]
+        if bc == 1:   # (the reference re-uses one device buffer for every boxcar > 1 and copies it asynchronously: SURVEY q3)
+            scale = np.sqrt(np.mean(h["series"].astype(np.float64) ** 2))
+            assert np.abs(h["series"] - series[b, :h["length"]]).max() < 1e-4 * scale
+            assert abs(h["count"] - int(res.signal_count[b])) <= 1
+    assert set(exp) - set(got) <= {bc for bc, b in exp.items() if res.signal_count[b] <= 1}
