@@ -38,6 +38,12 @@ import threading
 import time
 from pathlib import Path
 
+# The two lanes of a context rely on the driver giving their CUDA streams separate hardware work queues. With NCCL in
+# the process (torchrun, N > 1) and this variable unset the lanes were seen to alias (config 3: 120 instead of 131
+# Gsamples/s per GPU); 8 — the documented default — set explicitly restores it, 1 serialises them, 32 co-schedules the
+# big sweeps and is slower (profiles/r02s_connections.md). Must be in the environment before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "8")
+
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT / "simple-radio-telescope-backend_b200"))
 sys.path.insert(0, str(ROOT / "tests"))
@@ -83,13 +89,18 @@ def workload_string(wname: str, w: dict) -> str:
 def sweep_bytes_per_sample(w: dict) -> float:
     """bytes the kernels process_block launches for this workload MUST move per input sample (every sweep reads and
     writes its tile once): fused first sweep b/8 + 4, every further R2C sweep 8, then either the one-kernel
-    waterfall (8) or, for rows longer than 2^14, chirp sweep 8 + two waterfall sweeps 16 + SK 4 + column sums 4"""
+    waterfall (8; + 2 for the tabulated chirp phases, 4 bytes per bin) or, for rows of 2^15..2^18, chirp-on-load
+    column sweep 8 + last sweep 8 + zap-aware column sums 4"""
     q = w["log2n"] - 1                      # complex points of the packed transform
     r2c_sweeps = 1 if q <= 12 else (2 if q <= 20 else (3 if q <= 26 else 4))
     rows = (1 << q) // w["channels"]
-    first = (abs(w["bits"]) / 8 + 4) if abs(w["bits"]) == 8 and w["fmt"] in ("simple", "naocpsr_snap1", "interleaved_samples_2") \
-        else (abs(w["bits"]) / 8 + 4 + 8)   # separate unpack kernel, then the first sweep
-    waterfall = 8 if 1024 <= rows <= 16384 else 8 + 16 + 4 + 4
+    fused_first = (abs(w["bits"]) == 8 and w["fmt"] in ("simple", "naocpsr_snap1", "interleaved_samples_2", "gznupsr_a1")) or \
+                  (abs(w["bits"]) in (2, 4) and w["fmt"] == "simple")
+    first = (abs(w["bits"]) / 8 + 4) if fused_first else (abs(w["bits"]) / 8 + 4 + 8)  # else: unpack kernel, then the sweep
+    if "dms" in w:                           # DM sweep: R2C once, then per trial the waterfall group (on-the-fly chirp)
+        per_trial = 8 if 1024 <= rows <= 16384 else 8 + 8 + 4
+        return first + 8 * (r2c_sweeps - 1) + per_trial * len(w["dms"])
+    waterfall = (8 + 2) if 1024 <= rows <= 16384 else 8 + 8 + 4
     return first + 8 * (r2c_sweeps - 1) + waterfall
 
 
@@ -424,6 +435,8 @@ def emit(text: str):
 def default_contexts(w: dict) -> int:
     """contexts (CUDA streams) per GPU that blocks alternate over: short blocks leave gaps between their kernels that
     other blocks fill; long sweeps are pure HBM streams with little left to overlap"""
+    if FORMAT_STREAM_COUNT[w["fmt"]] >= 2 and w["log2n"] >= 26:
+        return 1  # a context spreads the streams of a block over two lanes itself: more contexts add nothing here
     return 6 if w["log2n"] <= 24 else (4 if w["log2n"] < 28 else 2)
 
 
@@ -533,7 +546,7 @@ class Harness:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         if dist:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         barrier()
@@ -693,8 +706,8 @@ def main():
     ap.add_argument("--no-pulse", action="store_true", help="noise-only blocks (no injected dispersed pulse)")
     ap.add_argument("--stage-iters", type=int, default=5)
     ap.add_argument("--contexts", type=int, default=int(os.environ.get("SRTB_BENCH_CONTEXTS", "0")),
-                    help="contexts (CUDA streams) per GPU that blocks alternate over (0 = 6 up to 2^24-sample blocks, 4 up "
-                         "to 2^27, 2 above)")
+                    help="contexts per GPU that blocks alternate over (0 = 1 for multi-stream blocks of >= 2^26 samples, whose "
+                         "streams the context overlaps itself; else 6 up to 2^24-sample blocks, 4 up to 2^27, 2 above)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     wname = args.workload
@@ -714,7 +727,10 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if os.environ.get("SRTB_BENCH_GLOO_BARRIER") == "1":   # diagnostic: no NCCL in the process at all
+            dist_mod.init_process_group("gloo")
+        else:
+            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
     if wname == "config4":

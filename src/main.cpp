@@ -155,6 +155,9 @@ std::jthread start_udp_source(size_t id, const std::string& address, unsigned sh
 
 int main(int argc, char** argv) {
   using namespace srtb::pipeline;
+  // separate hardware work queues for the streams of a context's two lanes: the documented default,
+  // pinned before CUDA initialises; an exported value wins
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "8", /*overwrite=*/0);
   std::vector<std::string> args(argv + 1, argv + argc);
   const std::string devices_opt = take_option(args, "gpu_devices", "");
   const int chains_per_gpu = std::max(1, std::atoi(take_option(args, "chains_per_gpu", "2").c_str()));
@@ -219,6 +222,32 @@ int main(int argc, char** argv) {
   std::signal(SIGTERM, on_signal);
   round_robin_out_functor rr{gpu_queues, submitted};
   const size_t streams = srtb::io::backend_registry::get_data_stream_count(cfg.baseband_format_type);
+  // a live stream cannot wait for the first blocks' one-time work (scratch and ring allocations, twiddle and chirp
+  // tables, pinned buffers): run silent blocks through every chain before the source starts. (Not with
+  // baseband_write_all, whose sink would record them.)
+  if (cfg.input_file_path.empty() && !cfg.baseband_write_all) {
+    const size_t block_bytes = cfg.baseband_input_count * static_cast<size_t>(std::abs(cfg.baseband_input_bits)) /
+                               srtb::BITS_PER_BYTE * streams;
+    auto h_zero = srtb::host_allocator.allocate_shared<std::byte>(block_bytes);
+    std::memset(h_zero.get(), 0, block_bytes);
+    uint64_t pushed = 0;
+    for (int round = 0; round < chains_per_gpu * (ring_depth + 1); round++)
+      for (auto& gq : gpu_queues) {
+        srtb::work::copy_to_device_work w;
+        w.ptr = nullptr;
+        w.count = block_bytes;
+        w.baseband_data = {h_zero, block_bytes};
+        w.timestamp = 0;
+        w.udp_packet_counter = w.no_udp_packet_counter;
+        w.data_stream_id = 0;
+        while (!gq->push(w)) std::this_thread::sleep_for(std::chrono::microseconds(50));
+        pushed++;
+      }
+    while (done->load() < pushed * streams && !g_interrupted) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    done->store(0);
+    positives->store(0);
+    SRTB_LOGI << " [main] " << "warmed up with " << pushed << " silent block(s)";
+  }
   const auto t0 = std::chrono::steady_clock::now();
   if (!synth_rate_opt.empty()) {
     // synthetic live stream (BASELINE config #5): one paced receiver, blocks dealt over the GPUs; ends after
