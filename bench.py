@@ -13,15 +13,18 @@ Contract (driver): python bench.py --gpus N --steps K --warmup W [--impl referen
     N > 1 shards independent blocks across ranks (weak scaling, no collective on the data path);
     `secondary` repeats value / e2e on BASELINE configs[1] (2^24 samples, one stream);
   * `value`  = samples / time with the blocks already resident in HBM (ring of distinct blocks larger than L2);
-    blocks alternate over `contexts_per_gpu` contexts (CUDA streams), two blocks in flight per context;
+    through ONE context per GPU for multi-stream blocks (a context spreads the streams of a block over two lanes
+    itself), over several contexts for single-stream ones (`contexts_per_gpu`), two blocks in flight per context;
     `single_context` is the same through ONE context (the reference drives one queue per device);
   * `e2e`    = the same from pinned HOST buffers through srtb_b200_submit_block()/collect_block() (the
     pinned-host ring: H2D of block i overlaps the compute of block i-1); every block's H2D and the D2H
     of its detector result (and of positive series) are inside the timed region;
-  * `roofline` = dominant per-pipe stage: algorithmic bytes / CUDA-event time vs the measured
-    copy peak (MEASURED_PEAKS.json hbm_gbs, else 6650 fallback); `stages` has every stage; `fused` times the
-    kernel groups the block path really launches against the bytes THEY must move; `roofline.chain` states the
-    unfused algorithmic bytes, the launched kernels' sweep bytes and (when a capture is committed) measured DRAM bytes;
+  * `roofline` = the dominant kernel of the block path (the one-kernel waterfall group: s1 + chirp + waterfall FFT + SK +
+    column sums): its compulsory bytes per launch / its launch time, CUDA events inside the library on the launching
+    stream, vs the measured copy peak (MEASURED_PEAKS.json hbm_gbs, else 6650 fallback); `traffic` = its DRAM bytes per
+    launch from the committed ncu capture; `roofline.fused` has every kernel group of the block path against the bytes
+    THEY must move; `stages` every per-pipe C-ABI stage alone (SURVEY.md §8d bytes); `roofline.chain` the whole block on
+    three byte counts (unfused algorithmic, the launched kernels' sweep bytes, measured DRAM bytes);
   * `cpu_baseline` = the CPU oracle (port of the reference operators, OpenMP, all host cores) on a bounded
     sample of the same workload (rank 0, N = 1 only).
 --impl reference times that CPU path alone (rank 0) with the same JSON shape.
@@ -96,7 +99,9 @@ def sweep_bytes_per_sample(w: dict) -> float:
     rows = (1 << q) // w["channels"]
     fused_first = (abs(w["bits"]) == 8 and w["fmt"] in ("simple", "naocpsr_snap1", "interleaved_samples_2", "gznupsr_a1")) or \
                   (abs(w["bits"]) in (2, 4) and w["fmt"] == "simple")
-    first = (abs(w["bits"]) / 8 + 4) if fused_first else (abs(w["bits"]) / 8 + 4 + 8)  # else: unpack kernel, then the sweep
+    # a stream's first sweep reads the bytes of EVERY stream of an interleaved block (each stream picks its own samples)
+    raw = abs(w["bits"]) / 8 * (FORMAT_STREAM_COUNT[w["fmt"]] if fused_first else 1)
+    first = (raw + 4) if fused_first else (raw + 4 + 8)  # else: unpack kernel, then the sweep
     if "dms" in w:                           # DM sweep: R2C once, then per trial the waterfall group (on-the-fly chirp)
         per_trial = 8 if 1024 <= rows <= 16384 else 8 + 8 + 4
         return first + 8 * (r2c_sweeps - 1) + per_trial * len(w["dms"])
@@ -146,6 +151,20 @@ def measured_dram_bytes_per_sample(wname: str):
         return float(d["block_dram_bytes"]) / float(d["block_samples"])
     except Exception:
         return None
+
+
+def measured_kernel_traffic(wname: str, needle: tuple):
+    """(mean DRAM read + write bytes per launch, mean ncu duration in us, kernel name) of the kernels of the committed
+    capture whose name contains one of `needle`, or (None, None, None)"""
+    p = ROOT / "profiles" / f"traffic_{wname}.json"
+    try:
+        ks = [k for k in json.loads(p.read_text())["kernels"] if any(nd in k["kernel"] for nd in needle)]
+        if not ks:
+            return None, None, None
+        return (float(np.mean([k["dram_read"] + k["dram_write"] for k in ks])), float(np.mean([k["time_us"] for k in ks])),
+                ks[0]["kernel"].split("(")[0])
+    except Exception:
+        return None, None, None
 
 
 _NCU_US = {}   # per-stage sum of kernel durations in the same committed capture (no launch / event overhead)
@@ -245,6 +264,53 @@ def synth_block_with_pulse(n: int, streams: int, seed: int, w: dict) -> np.ndarr
         else:                                        # "1 2 1 2"
             out.reshape(-1, streams)[:, s_] = q
     return out
+
+
+class RankSync:
+    """Plumbing between the ranks of one node. The default process group is NCCL, as the launch contract says, but it
+    is created lazily and this path has no data-path collective, so NO NCCL communicator exists while blocks are timed:
+    barriers and the max-over-ranks go through a gloo group on host scalars. (A communicator in the process costs the
+    two-lane path up to 8 %: its streams take hardware work queues, profiles/r02s_connections.md.) NCCL is exercised
+    once, after everything is measured, by close(). SRTB_BENCH_EAGER_NCCL=1 restores an eager communicator and NCCL
+    barriers for comparison."""
+
+    def __init__(self, dist_mod, torch, local_rank):
+        self.d, self.torch = dist_mod, torch
+        self.eager = os.environ.get("SRTB_BENCH_EAGER_NCCL") == "1"
+        if self.eager:
+            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.group = None
+        else:
+            dist_mod.init_process_group("nccl")
+            self.group = dist_mod.new_group(backend="gloo")
+        self.ReduceOp = dist_mod.ReduceOp
+
+    def get_world_size(self):
+        return self.d.get_world_size()
+
+    def barrier(self):
+        self.d.barrier(group=self.group) if self.group is not None else self.d.barrier()
+
+    def all_gather_scalar(self, value: float):
+        t = self.torch.tensor([value], dtype=self.torch.float64, device="cuda" if self.eager else "cpu")
+        every = [self.torch.zeros_like(t) for _ in range(self.get_world_size())]
+        self.d.all_gather(every, t, group=self.group)
+        return [float(x.item()) for x in every]
+
+    def all_reduce(self, t, op):
+        if self.eager:
+            self.d.all_reduce(t, op=op)
+            return
+        c = t.cpu()
+        self.d.all_reduce(c, op=op, group=self.group)
+        t.copy_(c)
+
+    def destroy_process_group(self):
+        # one NCCL collective over NVLink after the measurements: the ranks agree on the world size
+        t = self.torch.ones(1, device="cuda")
+        self.d.all_reduce(t)
+        assert int(t.item()) == self.get_world_size()
+        self.d.destroy_process_group()
 
 
 class ClockSampler:
@@ -545,10 +611,10 @@ class Harness:
         e1.record(self.stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
+        self.last_ms_by_rank = [ms]
         if dist:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda" if dist.get_backend() == "nccl" else "cpu")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            self.last_ms_by_rank = dist.all_gather_scalar(ms)   # the reported time is the slowest rank's
+            ms = max(self.last_ms_by_rank)
         barrier()
         return ms
 
@@ -611,10 +677,11 @@ def run_dm_sweep(args, torch, srtb_b200, w, wname, rank, local_rank, world, dist
                     "d2h_bytes_per_step": C.sizeof(srtb_b200.DetectResult) * H.streams * len(dms) * world},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                         "note": "per trial: chirp sweep 8N + waterfall 16N + SK 4N + column sums 4N (rows of 2^15 exceed the "
-                                 "one-kernel waterfall); R2C once per block",
-                         "achieved": (29 + 32 * len(dms) - 8) * H.n / (ms * 1e-3) / 1e9,
-                         "frac": (29 + 32 * len(dms) - 8) * H.n / (ms * 1e-3) / 1e9 / peak},
+                         "note": "sweep bytes: raw-fused R2C once per block (21 bytes per sample), then per trial the long-row "
+                                 "group: chirp-on-load column sweep 8 + last sweep 8 + zap-aware column sums 4",
+                         "bytes_per_sample": sweep_bytes_per_sample(w),
+                         "achieved": sweep_bytes_per_sample(w) * H.n / (ms * 1e-3) / 1e9,
+                         "frac": sweep_bytes_per_sample(w) * H.n / (ms * 1e-3) / 1e9 / peak},
             "cpu_baseline": None,
         }
         emit(json.dumps(line))
@@ -727,11 +794,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
-        if os.environ.get("SRTB_BENCH_GLOO_BARRIER") == "1":   # diagnostic: no NCCL in the process at all
-            dist_mod.init_process_group("gloo")
-        else:
-            dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        dist = dist_mod
+        dist = RankSync(dist_mod, torch, local_rank)
 
     if wname == "config4":
         return run_dm_sweep(args, torch, srtb_b200, w, wname, rank, local_rank, world, dist)
@@ -752,6 +815,7 @@ def main():
     l0 = H.launch_count
     H.detections = H.blocks_with_detection = 0
     ms_total = H.timed(H.step_device, args.steps, dist)
+    ms_by_rank = [m / args.steps for m in H.last_ms_by_rank]
     launches = H.launch_count - l0
     detections, det_blocks = H.detections, H.blocks_with_detection
     if rank == 0 and not sampler.rows:
@@ -873,11 +937,27 @@ def main():
                 "frac": dram_bps / per_sample_s / 1e9 / peak,
                 "note": "ncu dram__bytes_read + write of one process_block at this workload (profiles/)"},
         }
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic.get(dom),
-                    "traffic_source": (f"ncu --set full capture profiles/{traffic_tag}_summary.md (dram read+write of the "
-                                       "stage's kernels, one launch each, L2 flushed)") if traffic_tag else None,
-                    "peak_source": peak_src, "fused": fused, "chain": chain}
+        if fused.get("waterfall"):
+            # the dominant kernel of the block path: the one-kernel waterfall group (s1 + chirp + waterfall FFT + SK +
+            # column sums) — its compulsory bytes per launch over its launch time, measured above with CUDA events
+            # inside the library; DRAM traffic per launch from the committed ncu capture of the same workload
+            kt, kus, kname = measured_kernel_traffic(wname, ("fft_bigrow_kernel", "fft_row16_tma_kernel"))
+            group_ms = sum(v_["ms"] for v_ in fused.values())
+            roofline = {"bound": "hbm", "kernel": kname or "waterfall kernel (s1 + chirp + FFT + SK + column sums)",
+                        "achieved": fused["waterfall"]["gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": fused["waterfall"]["frac"], "bytes_per_launch": fused["waterfall"]["compulsory_bytes"],
+                        "ms_per_launch": fused["waterfall"]["ms"], "share_of_stream_time": fused["waterfall"]["ms"] / group_ms,
+                        "traffic": kt, "ncu_us_per_launch": kus,
+                        "traffic_source": (f"profiles/traffic_{wname}.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, "
+                                           "mean per launch)") if kt else None,
+                        "peak_source": peak_src, "per_pipe_dominant": {"stage": dom, **stages[dom]}, "fused": fused,
+                        "chain": chain}
+        else:
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": stages[dom]["gbs"], "peak": peak,
+                        "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic.get(dom),
+                        "traffic_source": (f"ncu --set full capture profiles/{traffic_tag}_summary.md (dram read+write of the "
+                                           "stage's kernels, one launch each, L2 flushed)") if traffic_tag else None,
+                        "peak_source": peak_src, "fused": fused, "chain": chain}
 
     # ---- secondary workload (BASELINE configs[1]) in brief: value + e2e
     secondary = None
@@ -929,6 +1009,7 @@ def main():
                        "parallelism": f"block-sharded x{world} (no collective)",
                        "l2": f"inputs larger than L2: ring of {ring} distinct blocks ({ring * block_bytes >> 20} MiB)",
                        "contexts_per_gpu": n_ctx_used, "warmup_steps_run": warm,
+                       "ms_per_step_by_rank": [round(m, 4) for m in ms_by_rank],
                        "injected_pulse": "every second block of the ring carries a dispersed pulse (S/N ~ 25)" if not args.no_pulse else "none",
                        "detections": detections, "blocks_with_detection": det_blocks},
             "clocks": clocks,

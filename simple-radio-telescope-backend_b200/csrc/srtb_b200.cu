@@ -2064,7 +2064,18 @@ static int get_chirp_table(srtb_b200_ctx* ctx, size_t n, const row_chirp_params&
 static int ensure_alt_lane(srtb_b200_ctx* ctx) {
   if (ctx->alt_ready) return 0;
   auto& a = ctx->alt;
-  CK(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+  {
+    // SRTB_B200_LANE_PRIORITY=1: the second lane at the lowest stream priority, so that its CTAs only fill what the
+    // first lane leaves free instead of being co-scheduled with it (experiment; default: equal priorities)
+    const char* e = std::getenv("SRTB_B200_LANE_PRIORITY");
+    if (e && e[0] == '1') {
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&a.stream, cudaStreamNonBlocking, lo));
+    } else {
+      CK(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+    }
+  }
   CK(cudaMalloc(&a.partial, sizeof(double) * 4096));
   CK(cudaMalloc(&a.ticket, sizeof(unsigned)));
   CK(cudaMemset(a.ticket, 0, sizeof(unsigned)));

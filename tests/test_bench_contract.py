@@ -50,6 +50,10 @@ def test_sweep_byte_model():
     """bytes the launched kernels must move per sample (bench.py roofline.chain.sweep_bytes)"""
     sys.path.insert(0, str(ROOT))
     import bench
-    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config2"]) == 1 + 4 + 8 + 8 + 8          # 3-sweep R2C, fused waterfall
-    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config3"]) == 29
-    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config1"]) == 0.25 + 4 + 8 + 24 + 32      # unpack + 4 sweeps + unfused tail
+    # raw-fused first sweep (b/8 + 4), two more R2C sweeps, one-kernel waterfall (8) + its tabulated chirp phases (2)
+    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config2"]) == 1 + 4 + 8 + 8 + 8 + 2
+    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config3"]) == 32    # two interleaved streams: 2 raw bytes per sample
+    # packed 2-bit first sweep, three more R2C sweeps, long rows: chirp-on-load sweep + last sweep + column sums
+    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config1"]) == 0.25 + 4 + 24 + 8 + 8 + 4
+    # DM sweep: the R2C once, the waterfall group (rows of 2^15: 20 bytes) once per trial
+    assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config4"]) == 1 + 4 + 16 + 20 * 21
