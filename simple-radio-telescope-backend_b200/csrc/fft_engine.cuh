@@ -1053,6 +1053,20 @@ struct raw16_smem {
   static constexpr size_t bytes = (size_t)XBUF * sizeof(float2) + 2 * (size_t)BUF * 4 + 128 + (size_t)L * sizeof(float2);
 };
 
+// the same two measures for the plain (complex input) sixteen-point column sweep with 64-byte tile rows: both TMA
+// buffers get the spare rows (the tile lands dense, the exchange uses the padded rows), the inter-sweep tables stay in
+// global memory, three CTAs per SM at L = 512. Not for the chirp-on-load variant (two CTAs per SM by registers).
+template <int LOGL, int T, bool CH>
+struct col16_smem {
+  static constexpr int L = 1 << LOGL;
+  static constexpr int BUF = T * L;
+  static constexpr bool PAD = raw16_smem<LOGL, T>::PAD && !CH;
+  static constexpr size_t bytes(int q) {
+    return PAD ? 2 * (size_t)(BUF + BUF / 16) * sizeof(float2) + 128 + (size_t)L * sizeof(float2)
+               : tile_tma_smem<LOGL, T>::bytes(q);
+  }
+};
+
 // Column pass, persistent: view [A][L][B] (B = elements between consecutive FFT points). A tile is the
 // L x T box at (row a*L, column b0) of the 2-D tensor [A*L][B]; ONE TMA box load (per 256 rows) brings
 // it into shared memory in exactly the column-mode layout [idx][t], double buffered across tiles.
@@ -1215,18 +1229,20 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_
   using SC = sched16<LOGL>;
   constexpr int L = 1 << LOGL, U = L / 16, S = SC::S, BUF = tile_tma_smem<LOGL, T>::BUF;
   constexpr int ROWS_PER_BOX = (L < 256) ? L : 256;
-  constexpr bool PADX = (RAW != 0) && raw16_smem<LOGL, T>::PAD;  // exchange tile with a spare row per sixteen
-  constexpr int XBUF = (RAW != 0) ? raw16_smem<LOGL, T>::XBUF : BUF;
+  // exchange tile with a spare row per sixteen (raw16_smem / col16_smem); with it the inter-sweep tables stay global
+  constexpr bool PADX = (RAW != 0) ? raw16_smem<LOGL, T>::PAD : col16_smem<LOGL, T, CH>::PAD;
+  constexpr bool STWG = (RAW != 0) || PADX;
+  constexpr int XBUF = PADX ? BUF + BUF / 16 : BUF;
   constexpr int UP = PADX ? U + U / 16 : U;                         // distance of a thread's sixteen slots
   extern __shared__ __align__(128) unsigned char smraw[];
   float2* const buf0 = reinterpret_cast<float2*>(smraw);
   float2* const buf1 = buf0 + XBUF;
   unsigned char* const raw0 = reinterpret_cast<unsigned char*>(buf1);
   unsigned char* const raw1 = raw0 + (size_t)BUF * 4;
-  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + BUF);  // RAW: right after the two raw tiles (2 * 4 BUF bytes)
+  // RAW: right after the two raw tiles (2 * 4 BUF bytes = BUF elements); else after the second tile buffer
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(buf1 + ((RAW != 0) ? BUF : XBUF));
   float2* const ltw = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(mbar) + 128);
-  // inter-sweep tables: staged in shared memory, except for the raw-fused sweep (see raw16_smem)
-  const float2* const stw = (RAW != 0) ? btw.tab : ltw + L;
+  const float2* const stw = STWG ? btw.tab : ltw + L;
   const int tid = threadIdx.x;
   const int t = tid % T, u = tid / T;
   if (tid == 0) {
@@ -1234,7 +1250,7 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_
     mbar_init(&mbar[1], 1);
     fence_mbar_init();
   }
-  if constexpr (RAW == 0)
+  if constexpr (!STWG)
     for (int i = tid; i < (3 << btw.q); i += blockDim.x) ltw[L + i] = __ldg(&btw.tab[i]);
   for (int i = tid; i < L; i += blockDim.x) ltw[i] = __ldg(&tw[i]);
   __syncthreads();
@@ -1269,7 +1285,7 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_
     int oidx[16];
     const int up = PADX ? u + (u >> 4) : u;  // tile row of slot 0
     float2 wb, r1;                           // inter-sweep twiddle of slot 0 and the ratio between slots
-    if constexpr (RAW != 0) {                // from global memory: issued before the stages to hide the latency
+    if constexpr (STWG) {                    // from global memory: issued before the stages to hide the latency
       const uint32_t bb = (tile % btiles) * T + t;
       wb = big_tw_lookup_ldg(stw, btw.q, (uint32_t)u * bb);
       r1 = big_tw_lookup_ldg(stw, btw.q, (uint32_t)U * bb);
@@ -1349,7 +1365,7 @@ __global__ void __launch_bounds__(col16_threads<LOGL, T>::value, CH ? 2 : col16_
       // store k = u + e*U of column b0 + t, times W_{L*B}^{k (b0 + t)} = wb * r1^e; the sixteen powers
       // are formed as hi[e >> 2] * lo[e & 3] (products of at most three table values deep)
       const uint32_t a = tile / btiles, b0 = (tile % btiles) * T;
-      if constexpr (RAW == 0) {
+      if constexpr (!STWG) {
         const uint32_t bb = b0 + t;
         wb = big_tw_lookup(stw, btw.q, (uint32_t)u * bb);
         r1 = big_tw_lookup(stw, btw.q, (uint32_t)U * bb);

@@ -786,7 +786,8 @@ static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, siz
     if (use_col16()) {
       auto kern16 = fft_col16_tma_kernel<LOGL, T, FWD>;
       constexpr int threads = col16_threads<LOGL, T>::value;
-      if (int rc = persistent_grid(ctx, kern16, threads, smem, tile_tma_smem<LOGL, T>::bytes(10), ntiles, &grid)) return rc;
+      const size_t smem16 = col16_smem<LOGL, T, false>::bytes(btw.q);
+      if (int rc = persistent_grid(ctx, kern16, threads, smem16, col16_smem<LOGL, T, false>::bytes(10), ntiles, &grid)) return rc;
       if constexpr (!FWD) {
         if (chirp) {  // s1 + chirp applied as the tile is read (long waterfall rows)
           auto kernc = fft_col16_tma_kernel<LOGL, T, FWD, 0, true>;
@@ -799,7 +800,7 @@ static int launch_col_tma(srtb_b200_ctx* ctx, const float2* in, float2* out, siz
           return 0;
         }
       }
-      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
+      CK(launch_pdl(ctx, kern16, dim3(grid), dim3(threads), smem16, tm, out, B, (uint32_t)(B / T), (uint32_t)ntiles, btw, tw,
                     raw_params{}, row_chirp_params{}));
       ctx->launches++;
       CK(cudaGetLastError());
