@@ -266,6 +266,31 @@ def synth_block_with_pulse(n: int, streams: int, seed: int, w: dict) -> np.ndarr
     return out
 
 
+def bind_to_gpu_numa_node(torch, device_index: int):
+    """Multi-rank runs: keep this rank's thread (and with it the pinned host blocks it allocates from now on) on the
+    NUMA node its GPU hangs off — eight ranks pulling 55 GB/s each out of host memory otherwise depend on where the
+    scheduler happened to start them (8 GPUs: 430 against 270 Gsamples/s end to end, profiles/r02t_scaling.md).
+    Returns the node, or None when the topology cannot be read (nothing is changed then)."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        target = cpus & set(os.sched_getaffinity(0))
+        if len(target) < 2:
+            return None
+        os.sched_setaffinity(0, target)
+        return node
+    except Exception as e:  # unknown attribute names, no sysfs, restricted cpuset: run unbound
+        print(f"[bench] NUMA binding skipped: {e}", file=sys.stderr)
+        return None
+
+
 class RankSync:
     """Plumbing between the ranks of one node. The default process group is NCCL, as the launch contract says, but it
     is created lazily and this path has no data-path collective, so NO NCCL communicator exists while blocks are timed:
@@ -795,6 +820,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank) if world > 1 and args.impl != "reference" else None
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -1014,6 +1040,7 @@ def main():
                        "l2": f"inputs larger than L2: ring of {ring} distinct blocks ({ring * block_bytes >> 20} MiB)",
                        "contexts_per_gpu": n_ctx_used, "warmup_steps_run": warm,
                        "ms_per_step_by_rank": [round(m, 4) for m in ms_by_rank],
+                       "rank0_numa_node": numa_node,
                        "injected_pulse": "every second block of the ring carries a dispersed pulse (S/N ~ 25)" if not args.no_pulse else "none",
                        "detections": detections, "blocks_with_detection": det_blocks},
             "clocks": clocks,
