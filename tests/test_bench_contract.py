@@ -57,3 +57,24 @@ def test_sweep_byte_model():
     assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config1"]) == 0.25 + 4 + 24 + 8 + 8 + 4
     # DM sweep: the R2C once, the waterfall group (rows of 2^15: 20 bytes) once per trial
     assert bench.sweep_bytes_per_sample(bench.WORKLOADS["config4"]) == 1 + 4 + 16 + 20 * 21
+
+
+def test_numa_binding_is_a_no_op_when_the_topology_cannot_be_read():
+    """multi-rank runs bind each rank to its GPU's NUMA node; an unknown device or node -1 must change nothing"""
+    import os
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    class Props:
+        pci_domain_id, pci_bus_id, pci_device_id = 0, 0xfe, 0x1f   # no such PCI device
+
+    class FakeTorch:
+        class cuda:
+            @staticmethod
+            def get_device_properties(i):
+                return Props()
+
+    before = os.sched_getaffinity(0)
+    assert bench.bind_to_gpu_numa_node(FakeTorch, 0) is None
+    assert os.sched_getaffinity(0) == before
+
