@@ -15,7 +15,12 @@
  *     re-sized when a call's size differs (mirrors fft_wrapper::set_size re-planning,
  *     fft/fft_wrapper.hpp:106-113);
  *   - return value 0 = ok, negative = srtb_b200_status; text via srtb_b200_last_error.
- *   - there is NO CPU fallback: without a CUDA device ctx_create fails.
+ *   - there is NO CPU fallback: without a CUDA device ctx_create fails;
+ *   - a ctx may be shared by several host threads (the reference copies one sycl::queue into every pipe): each entry
+ *     locks the ctx while it plans and enqueues, waits (synchronize, collect_block) run unlocked;
+ *   - a ctx spreads the data streams of a block over two CUDA streams of its own ("lanes": its stream for the even
+ *     streams, a private one for the odd ones); results are complete when process_block / collect_block returns.
+ *     SRTB_B200_LANES=1 keeps everything on the ctx's stream.
  */
 #ifndef SRTB_B200_H
 #define SRTB_B200_H
