@@ -302,8 +302,12 @@ class RankSync:
     def __init__(self, dist_mod, torch, local_rank):
         self.d, self.torch = dist_mod, torch
         self.eager = os.environ.get("SRTB_BENCH_EAGER_NCCL") == "1"
+        self.host_only = os.environ.get("SRTB_BENCH_SYNC_BACKEND") == "gloo"   # CPU tests of this class: no NCCL at all
         if self.eager:
             dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            self.group = None
+        elif self.host_only:
+            dist_mod.init_process_group("gloo")
             self.group = None
         else:
             dist_mod.init_process_group("nccl")
@@ -331,6 +335,9 @@ class RankSync:
         t.copy_(c)
 
     def destroy_process_group(self):
+        if self.host_only:
+            self.d.destroy_process_group()
+            return
         # one NCCL collective over NVLink after the measurements: the ranks agree on the world size
         try:
             t = self.torch.ones(1, device="cuda")

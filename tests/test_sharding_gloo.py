@@ -61,3 +61,40 @@ def test_sharding_is_a_partition():
                    for b in sharding.blocks_for_rank(37, world, r))
     with pytest.raises(ValueError):
         sharding.blocks_for_rank(4, 2, 2)
+
+
+def _ranksync_worker(rank, world, port, tmp):
+    """bench.py's rank plumbing (RankSync) on CPU: the host-only mode replaces the lazy NCCL default group by gloo,
+    everything else — barrier, gather of the per-rank step times, SUM / MAX reductions of a result vector — is the
+    code the multi-GPU bench runs"""
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    sys.path.insert(0, str(root))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      SRTB_BENCH_SYNC_BACKEND="gloo")
+    import torch.distributed as dist_mod
+    import bench
+    rs = bench.RankSync(dist_mod, torch, rank)
+    assert rs.get_world_size() == world
+    rs.barrier()
+    times = rs.all_gather_scalar(1.0 + 0.25 * rank)
+    vals = torch.tensor([float(rank + 1), 10.0 * rank], dtype=torch.float64)
+    mx = vals.clone()
+    rs.all_reduce(vals, op=rs.ReduceOp.SUM)
+    rs.all_reduce(mx, op=rs.ReduceOp.MAX)
+    if rank == 0:
+        np.save(os.path.join(tmp, "ranksync.npy"), np.array(times + vals.tolist() + mx.tolist()))
+    rs.barrier()
+    rs.destroy_process_group()
+
+
+def test_bench_ranksync_world2(tmp_path):
+    import torch.multiprocessing as mp
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_ranksync_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = np.load(tmp_path / "ranksync.npy")
+    assert r[:2].tolist() == [1.0, 1.25]          # per-rank step times, in rank order (the bench reports their max)
+    assert r[2:4].tolist() == [3.0, 10.0]         # SUM
+    assert r[4:6].tolist() == [2.0, 10.0]         # MAX
+
